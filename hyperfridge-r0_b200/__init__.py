@@ -1,0 +1,7 @@
+"""hyperfridge-r0_b200: B200-native STARK segment prover behind hyperfridge's `prover.prove(env, ELF)`.
+
+The directory name is not a Python identifier; import it through `hfb200_loader.load()` (repo root) which
+registers it as `hyperfridge_r0_b200`.
+"""
+from .binding import (Context, Hfb200Error, load_library, LIB_PATH, EXPORTS, CircuitDesc, Stats, N_GLOBAL, P,  # noqa: F401
+                      CHECKPOINT_NAMES)

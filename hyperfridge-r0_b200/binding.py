@@ -1,0 +1,261 @@
+"""ctypes binding of libhfb200.so (include/hfb200.h).
+
+This is host-side glue only: every call goes straight through the C ABI that a Rust `extern "C"` crate
+would bind.  There is no CPU fallback: if the CUDA library is missing or no B200 is
+visible, loading / `hfb200_init` raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhfb200.so")
+
+N_GLOBAL = 32
+P = 2013265921
+
+# Every symbol include/hfb200.h declares (tests check that the built library exports all of them).
+EXPORTS = [
+    "hfb200_init", "hfb200_destroy", "hfb200_free_error", "hfb200_version", "hfb200_host_alloc", "hfb200_host_free",
+    "hfb200_prove_segment", "hfb200_segment_begin", "hfb200_segment_finish", "hfb200_witgen_synth",
+    "hfb200_prove_resident", "hfb200_read_group", "hfb200_seal_words", "hfb200_checkpoint", "hfb200_last_stats",
+    "hfb200_total_launches", "hfb200_op_interpolate_ntt", "hfb200_op_expand_ntt", "hfb200_op_lde", "hfb200_op_merkle",
+    "hfb200_op_poseidon2", "hfb200_op_fri_fold", "hfb200_bench_lde", "hfb200_bench_merkle",
+]
+
+
+class Hfb200Error(RuntimeError):
+    pass
+
+
+class CircuitDesc(C.Structure):
+    _fields_ = [("w_code", C.c_uint32), ("w_data", C.c_uint32), ("w_accum", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_ntt_main", C.c_float), ("ms_hash_main", C.c_float),
+                ("ms_accum", C.c_float), ("ms_check", C.c_float), ("ms_deep", C.c_float), ("ms_fri", C.c_float),
+                ("launches", C.c_uint64), ("ntt_main_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def load_library(path=None):
+    """dlopen the product library.  Raises Hfb200Error when it has not been built (no fallback)."""
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise Hfb200Error("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(the prover has no CPU fallback)" % path)
+    lib = C.CDLL(path)
+    vp, u32, u64, sz = C.c_void_p, C.c_uint32, C.c_uint64, C.c_size_t
+    err = C.c_void_p  # const char* that we must free ourselves
+    sig = {
+        "hfb200_init": (err, [C.c_int, u32, C.POINTER(CircuitDesc), C.POINTER(vp)]),
+        "hfb200_destroy": (None, [vp]),
+        "hfb200_free_error": (None, [vp]),
+        "hfb200_version": (C.c_char_p, []),
+        "hfb200_host_alloc": (err, [sz, C.POINTER(vp)]),
+        "hfb200_host_free": (None, [vp]),
+        "hfb200_prove_segment": (err, [vp, u32, vp, vp, vp, u64, vp, sz, C.POINTER(sz)]),
+        "hfb200_segment_begin": (err, [vp, u32, vp, vp, vp, u64, vp, sz, C.POINTER(sz)]),
+        "hfb200_segment_finish": (err, [vp, vp, vp, sz, C.POINTER(sz)]),
+        "hfb200_witgen_synth": (err, [vp, u32, u64, u64, vp]),
+        "hfb200_prove_resident": (err, [vp, u64, vp, sz, C.POINTER(sz)]),
+        "hfb200_read_group": (err, [vp, u32, vp, sz]),
+        "hfb200_seal_words": (sz, [vp, u32]),
+        "hfb200_checkpoint": (err, [vp, C.c_char_p, vp, sz, C.POINTER(sz)]),
+        "hfb200_last_stats": (err, [vp, C.POINTER(Stats)]),
+        "hfb200_total_launches": (u64, [vp]),
+        "hfb200_op_interpolate_ntt": (err, [vp, vp, sz, sz, C.c_int]),
+        "hfb200_op_expand_ntt": (err, [vp, vp, vp, sz, sz, u32]),
+        "hfb200_op_lde": (err, [vp, vp, vp, sz, sz]),
+        "hfb200_op_merkle": (err, [vp, vp, sz, sz, vp]),
+        "hfb200_op_poseidon2": (err, [vp, vp, sz]),
+        "hfb200_op_fri_fold": (err, [vp, vp, vp, sz, vp]),
+        "hfb200_bench_lde": (err, [vp, u32, u32, u32, C.POINTER(C.c_float)]),
+        "hfb200_bench_merkle": (err, [vp, u32, u32, u32, C.POINTER(C.c_float)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _u32(a):
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    return a
+
+
+CHECKPOINT_NAMES = ["globals_hash", "code_root", "data_root", "accum_mix", "accum_root", "poly_mix", "check_root", "z",
+                    "hash_u", "deep_mix", "final_poly_hash", "fri_root_0", "fri_mix_0", "fri_root_1", "fri_mix_1",
+                    "fri_root_2", "fri_mix_2", "fri_root_3", "fri_mix_3", "fri_final_hash", "query_positions"]
+
+
+class Context:
+    """One hfb200_ctx: one host thread <-> one GPU.  Mirrors upstream's `segment_prover(hashfn)` object."""
+
+    def __init__(self, device=0, max_po2=20, circuit=(16, 192, 48), lib=None):
+        self.lib = lib or load_library()
+        self.circuit = tuple(int(x) for x in circuit)
+        self.max_po2 = max_po2
+        desc = CircuitDesc(self.circuit[0], self.circuit[1], self.circuit[2], 0)
+        h = C.c_void_p()
+        self._h = None
+        self._check(self.lib.hfb200_init(device, max_po2, C.byref(desc), C.byref(h)))
+        self._h = h
+
+    def _check(self, e):
+        if e:
+            msg = C.cast(e, C.c_char_p).value.decode(errors="replace")
+            self.lib.hfb200_free_error(e)
+            raise Hfb200Error(msg)
+
+    def close(self):
+        if self._h:
+            self.lib.hfb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def version(self):
+        return self.lib.hfb200_version().decode()
+
+    # ---- segment prover ----
+    def seal_words(self, po2):
+        return self.lib.hfb200_seal_words(self._h, po2)
+
+    def prove_segment(self, po2, globals_, code, data, blind_seed):
+        globals_, code, data = _u32(globals_), _u32(code), _u32(data)
+        n = 1 << po2
+        if globals_.size != N_GLOBAL or code.size != self.circuit[0] * n or data.size != self.circuit[1] * n:
+            raise Hfb200Error("prove_segment: trace shape does not match (circuit, po2)")
+        cap = self.seal_words(po2)
+        seal = np.empty(cap, np.uint32)
+        got = C.c_size_t()
+        self._check(self.lib.hfb200_prove_segment(self._h, po2, _ptr(globals_), _ptr(code), _ptr(data), blind_seed, _ptr(seal), cap, C.byref(got)))
+        return seal[:got.value]
+
+    def segment_begin(self, po2, globals_, code, data, blind_seed):
+        globals_, code, data = _u32(globals_), _u32(code), _u32(data)
+        mix = np.empty(self.circuit[2], np.uint32)
+        got = C.c_size_t()
+        self._check(self.lib.hfb200_segment_begin(self._h, po2, _ptr(globals_), _ptr(code), _ptr(data), blind_seed, _ptr(mix), mix.size, C.byref(got)))
+        self._po2 = po2
+        return mix[:got.value]
+
+    def segment_finish(self, accum=None):
+        accum = _u32(accum) if accum is not None else None
+        cap = self.seal_words(self._po2)
+        seal = np.empty(cap, np.uint32)
+        got = C.c_size_t()
+        self._check(self.lib.hfb200_segment_finish(self._h, _ptr(accum), _ptr(seal), cap, C.byref(got)))
+        return seal[:got.value]
+
+    def witgen_synth(self, po2, trace_seed, blind_seed):
+        g = np.empty(N_GLOBAL, np.uint32)
+        self._check(self.lib.hfb200_witgen_synth(self._h, po2, trace_seed, blind_seed, _ptr(g)))
+        self._po2 = po2
+        return g
+
+    def prove_resident(self, blind_seed):
+        cap = self.seal_words(self._po2)
+        seal = np.empty(cap, np.uint32)
+        got = C.c_size_t()
+        self._check(self.lib.hfb200_prove_resident(self._h, blind_seed, _ptr(seal), cap, C.byref(got)))
+        return seal[:got.value]
+
+    def read_group(self, group):
+        w = {0: self.circuit[2], 1: self.circuit[0], 2: self.circuit[1]}[group]
+        out = np.empty((w, 1 << self._po2), np.uint32)
+        self._check(self.lib.hfb200_read_group(self._h, group, _ptr(out), out.size))
+        return out
+
+    def checkpoint(self, name):
+        buf = np.empty(4096, np.uint32)
+        got = C.c_size_t()
+        self._check(self.lib.hfb200_checkpoint(self._h, name.encode(), _ptr(buf), buf.size, C.byref(got)))
+        return buf[:got.value].copy()
+
+    def checkpoints(self):
+        out = {}
+        for name in CHECKPOINT_NAMES:
+            try:
+                out[name] = self.checkpoint(name)
+            except Hfb200Error:
+                pass
+        return out
+
+    def last_stats(self):
+        s = Stats()
+        self._check(self.lib.hfb200_last_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def total_launches(self):
+        return self.lib.hfb200_total_launches(self._h)
+
+    # ---- HAL-level operators ----
+    def op_interpolate_ntt(self, cols, zk_shift=False):
+        a = _u32(cols).copy()
+        a2 = a.reshape(-1, a.shape[-1])
+        self._check(self.lib.hfb200_op_interpolate_ntt(self._h, _ptr(a), a2.shape[0], a2.shape[1], int(zk_shift)))
+        return a
+
+    def op_expand_ntt(self, cols, expand_bits=2):
+        a = _u32(cols)
+        a2 = a.reshape(-1, a.shape[-1])
+        out = np.empty((a2.shape[0], a2.shape[1] << expand_bits), np.uint32)
+        self._check(self.lib.hfb200_op_expand_ntt(self._h, _ptr(out), _ptr(a), a2.shape[0], a2.shape[1], expand_bits))
+        return out
+
+    def op_lde(self, cols):
+        a = _u32(cols)
+        a2 = a.reshape(-1, a.shape[-1])
+        out = np.empty((a2.shape[0], a2.shape[1] * 4), np.uint32)
+        self._check(self.lib.hfb200_op_lde(self._h, _ptr(out), _ptr(a), a2.shape[0], a2.shape[1]))
+        return out
+
+    def op_merkle(self, matrix):
+        m = _u32(matrix)
+        cols, rows = m.shape
+        nodes = np.empty((2 * rows, 8), np.uint32)
+        self._check(self.lib.hfb200_op_merkle(self._h, _ptr(m), rows, cols, _ptr(nodes)))
+        return nodes
+
+    def op_poseidon2(self, states):
+        s = _u32(states).copy()
+        self._check(self.lib.hfb200_op_poseidon2(self._h, _ptr(s), s.size // 24))
+        return s
+
+    def op_fri_fold(self, coeffs, mix4):
+        a = _u32(coeffs)
+        n = a.shape[-1]
+        out = np.empty((4, n // 16), np.uint32)
+        m = _u32(mix4)
+        self._check(self.lib.hfb200_op_fri_fold(self._h, _ptr(out), _ptr(a), n, _ptr(m)))
+        return out
+
+    def bench_lde(self, po2, count, iters):
+        ms = C.c_float()
+        self._check(self.lib.hfb200_bench_lde(self._h, po2, count, iters, C.byref(ms)))
+        return ms.value
+
+    def bench_merkle(self, po2, count, iters):
+        ms = C.c_float()
+        self._check(self.lib.hfb200_bench_merkle(self._h, po2, count, iters, C.byref(ms)))
+        return ms.value

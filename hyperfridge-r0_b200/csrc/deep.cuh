@@ -1,0 +1,212 @@
+// DEEP-ALI and FRI kernels.
+// Replaces the risc0-zkp 3.0.4 `Hal` ops used by `Prover::finalize` and `fri_prove`
+// (`batch_evaluate_any`, `mix_poly_coeffs`, combos prepare/divide, `eltwise_sum_extelem`,
+// `batch_bit_reverse`, `fri_fold`, Merkle openings; /root/reference/Cargo.lock:3195-3223, not vendored;
+// SURVEY.md Appendix A.7).  B200-first restructuring: upstream works on COEFFICIENTS (Horner-style
+// evaluation, coefficient mixing, synthetic division by (x - z w^-b)); here everything is done POINT-WISE on
+// the trace domain D1 = { w_N^i / 3 } where the committed polynomials g(y) = f(3y) take the raw trace
+// values, so the main groups never need their coefficient form:
+//   * g(z w^-b)  = sum_i trace[i-b] * L_i,   L_i = ((3z)^N - 1)/N * w^i / (3z - w^i)     (barycentric)
+//   * FRI input  = iNTT+zk_shift of  sum_c (mix-combination_c(i) - U_c(y_i)) / prod_b (y_i - z w^-b)
+// Field arithmetic is exact, so the seal is bit-identical to the coefficient-space formulation.
+#pragma once
+#include "ntt.cuh"
+
+namespace hf {
+
+// INV[i] = 1/(3z - w_N^i), L[i] = A * w_N^i * INV[i], INV4[i] = 1/(w_N^i/3 - z^4)
+struct DeepWeightsKernel {
+    static constexpr bool kBarrier = false;
+    HD static void run(const KCtx& cx, uint32_t*, E4* INV, E4* L, E4* INV4, E4 z3, E4 z4, E4 A, uint32_t po2, RootTables rt) {
+        const uint64_t n = 1ull << po2;
+        const uint64_t i = (uint64_t)cx.bx * cx.nt + cx.tid;
+        if (i >= n) return;
+        const uint32_t w = tab_pow(rt.f_lo, rt.f_hi, (uint32_t)(i << (24 - po2)));
+        E4 d = z3; d.c[0] = fsub(d.c[0], w);
+        const E4 inv = e4_inv(d);
+        INV[i] = inv;
+        L[i] = e4_scale(e4_mul(A, inv), w);
+        E4 d4 = e4_neg(z4); d4.c[0] = fadd(d4.c[0], fmul(w, INV3));
+        INV4[i] = e4_inv(d4);
+    }
+};
+
+// W[i] = x^(bitrev_n(i)) from the squarings xs[k] = x^(2^k): weights for evaluating bit-reversed coefficients.
+struct PowBitrevKernel {
+    static constexpr bool kBarrier = false;
+    HD static void run(const KCtx& cx, uint32_t*, E4* W, const E4* xs, uint32_t po2) {
+        const uint64_t n = 1ull << po2;
+        const uint64_t i = (uint64_t)cx.bx * cx.nt + cx.tid;
+        if (i >= n) return;
+        const uint32_t j = brev((uint32_t)i, po2);
+        E4 r = e4_one();
+        for (uint32_t k = 0; k < po2; k++) if ((j >> k) & 1u) r = e4_mul(r, xs[k]);
+        W[i] = r;
+    }
+};
+
+static constexpr uint32_t DOT_CPB = 4, DOT_RPB = 4096, DOT_T = 256;
+
+// partial[(col * nblk + blk) * 2 + b] = sum over the block's rows of cols[col][r] * Wt[(r + b) mod n]
+// (b = 1 only for col < n_back1).  grid.x = row blocks, grid.y = column groups of DOT_CPB.
+struct DotKernel {
+    static constexpr bool kBarrier = true;
+    HD static void run(const KCtx& cx, uint32_t* sm, const uint32_t* cols, uint64_t col_stride, uint32_t ncols, uint32_t n_back1, const E4* Wt, uint32_t po2, E4* partial) {
+        const uint64_t n = 1ull << po2;
+        const uint32_t nblk = cx.gx, c0 = cx.by * DOT_CPB;
+        const uint64_t row0 = (uint64_t)cx.bx * DOT_RPB;
+        E4* red = reinterpret_cast<E4*>(sm);  // [DOT_T][DOT_CPB*2]
+        for (uint32_t it = cx.tid; it < DOT_T; it += cx.nt) {
+            E4 acc[DOT_CPB][2];
+            for (uint32_t c = 0; c < DOT_CPB; c++) { acc[c][0] = e4_zero(); acc[c][1] = e4_zero(); }
+            for (uint64_t r = row0 + it; r < row0 + DOT_RPB && r < n; r += DOT_T) {
+                const E4 w0 = Wt[r], w1 = Wt[(r + 1) & (n - 1)];
+#pragma unroll
+                for (uint32_t c = 0; c < DOT_CPB; c++) {
+                    if (c0 + c >= ncols) break;
+                    const uint32_t t = cols[(uint64_t)(c0 + c) * col_stride + r];
+                    acc[c][0] = e4_add(acc[c][0], e4_scale(w0, t));
+                    if (c0 + c < n_back1) acc[c][1] = e4_add(acc[c][1], e4_scale(w1, t));
+                }
+            }
+            for (uint32_t c = 0; c < DOT_CPB; c++) { red[(it * DOT_CPB + c) * 2] = acc[c][0]; red[(it * DOT_CPB + c) * 2 + 1] = acc[c][1]; }
+        }
+        cx.sync();
+        for (uint32_t stride = DOT_T / 2; stride >= 1; stride >>= 1) {
+            for (uint32_t w = cx.tid; w < stride * DOT_CPB * 2; w += cx.nt) {
+                const uint32_t it = w / (DOT_CPB * 2), k = w % (DOT_CPB * 2);
+                red[it * DOT_CPB * 2 + k] = e4_add(red[it * DOT_CPB * 2 + k], red[(it + stride) * DOT_CPB * 2 + k]);
+            }
+            cx.sync();
+        }
+        for (uint32_t k = cx.tid; k < DOT_CPB * 2; k += cx.nt) {
+            const uint32_t c = k >> 1, b = k & 1;
+            if (c0 + c < ncols) partial[((uint64_t)(c0 + c) * nblk + cx.bx) * 2 + b] = red[k];
+        }
+    }
+};
+// out[col*2 + b] = sum_blk partial[(col*nblk + blk)*2 + b]
+struct DotReduceKernel {
+    static constexpr bool kBarrier = false;
+    HD static void run(const KCtx& cx, uint32_t*, const E4* partial, uint32_t ncols, uint32_t nblk, E4* out) {
+        const uint64_t t = (uint64_t)cx.bx * cx.nt + cx.tid;
+        if (t >= (uint64_t)ncols * 2) return;
+        const uint32_t col = (uint32_t)(t >> 1), b = (uint32_t)(t & 1);
+        E4 acc = e4_zero();
+        for (uint32_t k = 0; k < nblk; k++) acc = e4_add(acc, partial[((uint64_t)col * nblk + k) * 2 + b]);
+        out[t] = acc;
+    }
+};
+
+// S[k][i] = (sum_c mixpow[c] * check_coeffs[c][i])_k * 3^-bitrev(i)   (bit-reversed coefficient order kept)
+struct CheckMixKernel {
+    static constexpr bool kBarrier = false;
+    HD static void run(const KCtx& cx, uint32_t*, const uint32_t* check_coeffs /*[16][n]*/, const E4* mixpow /*16*/, uint32_t* S /*[4][n]*/, uint32_t po2, RootTables rt) {
+        const uint64_t n = 1ull << po2;
+        const uint64_t i = (uint64_t)cx.bx * cx.nt + cx.tid;
+        if (i >= n) return;
+        E4 acc = e4_zero();
+        for (uint32_t c = 0; c < 16; c++) acc = e4_add(acc, e4_scale(mixpow[c], check_coeffs[(uint64_t)c * n + i]));
+        const uint32_t un = tab_pow(rt.ip3_lo, rt.ip3_hi, brev((uint32_t)i, po2));
+        for (int k = 0; k < 4; k++) S[(uint64_t)k * n + i] = fmul(acc.c[k], un);
+    }
+};
+
+struct DeepMixArgs {
+    const uint32_t* tr[3];   // accum, code, data traces [w][n]
+    uint32_t w[3];
+    uint32_t n_back1[3];     // columns [0, n_back1) of the group are in combo {0,1}, the rest in combo {0}
+    const E4* mixpow;        // per register in taps order (accum, code, data), device
+    const uint32_t* S;       // [4][n] check combination on D1
+    const E4 *INV, *INV4;
+    uint32_t* out;           // [4][n]
+    E4 U0, U1a, U1b, Vc;     // combo_u: {0} -> U0 ; {0,1} -> U1a + U1b*y ; check -> Vc
+    uint32_t omega;          // w_N (Montgomery)
+    uint32_t po2;
+    RootTables rt;
+};
+// One thread per trace row: mix-combine all registers per tap-set, subtract the U polynomials, divide point-wise.
+struct DeepMixKernel {
+    static constexpr bool kBarrier = false;
+    HD static void run(const KCtx& cx, uint32_t*, DeepMixArgs p) {
+        const uint64_t n = 1ull << p.po2;
+        const uint64_t i = (uint64_t)cx.bx * cx.nt + cx.tid;
+        if (i >= n) return;
+        E4 c0 = e4_zero(), c1 = e4_zero();
+        uint32_t reg = 0;
+        for (int g = 0; g < 3; g++) {
+            const uint32_t* base = p.tr[g] + i;
+            for (uint32_t c = 0; c < p.w[g]; c++, reg++) {
+                const E4 t = e4_scale(p.mixpow[reg], base[(uint64_t)c * n]);
+                if (c < p.n_back1[g]) c1 = e4_add(c1, t); else c0 = e4_add(c0, t);
+            }
+        }
+        const uint32_t w = tab_pow(p.rt.f_lo, p.rt.f_hi, (uint32_t)(i << (24 - p.po2)));
+        const uint32_t y = fmul(w, INV3);
+        // 1/(y - z) = -3/(3z - w^i) ; 1/(y - z w^-1) = -3 w /(3z - w^(i+1))
+        const uint32_t m3 = fneg(THREE);
+        const E4 d0 = e4_scale(p.INV[i], m3);
+        const E4 d1 = e4_scale(p.INV[(i + 1) & (n - 1)], fmul(m3, p.omega));
+        E4 r = e4_mul(e4_sub(c0, p.U0), d0);
+        const E4 u1 = e4_add(p.U1a, e4_scale(p.U1b, y));
+        r = e4_add(r, e4_mul(e4_mul(e4_sub(c1, u1), d0), d1));
+        const E4 s = e4(p.S[i], p.S[n + i], p.S[2 * n + i], p.S[3 * n + i]);
+        r = e4_add(r, e4_mul(e4_sub(s, p.Vc), p.INV4[i]));
+        for (int k = 0; k < 4; k++) p.out[(uint64_t)k * n + i] = r.c[k];
+    }
+};
+
+// Hal::fri_fold: out[k][idx] = (sum_{i<16} mix^i * in[.][bitrev4(i)*m + idx])_k , m = n/16.
+struct FriFoldArgs { const uint32_t* in; uint32_t* out; uint32_t n; E4 mixpow[16]; };
+struct FriFoldKernel {
+    static constexpr bool kBarrier = false;
+    HD static void run(const KCtx& cx, uint32_t*, FriFoldArgs p) {
+        const uint32_t m = p.n / 16;
+        const uint64_t idx = (uint64_t)cx.bx * cx.nt + cx.tid;
+        if (idx >= m) return;
+        E4 tot = e4_zero();
+#pragma unroll
+        for (uint32_t i = 0; i < 16; i++) {
+            const uint64_t src = (uint64_t)brev(i, 4) * m + idx;
+            const E4 e = e4(p.in[src], p.in[(uint64_t)p.n + src], p.in[2ull * p.n + src], p.in[3ull * p.n + src]);
+            tot = e4_add(tot, e4_mul(p.mixpow[i], e));
+        }
+        for (int k = 0; k < 4; k++) p.out[(uint64_t)k * m + idx] = tot.c[k];
+    }
+};
+
+struct BitRevKernel {  // out[c][i] = in[c][bitrev(i)]
+    static constexpr bool kBarrier = false;
+    HD static void run(const KCtx& cx, uint32_t*, const uint32_t* in, uint32_t* out, uint32_t ncols, uint32_t lg) {
+        const uint64_t t = (uint64_t)cx.bx * cx.nt + cx.tid;
+        if (t >= ((uint64_t)ncols << lg)) return;
+        const uint32_t c = (uint32_t)(t >> lg), i = (uint32_t)(t & ((1u << lg) - 1));
+        out[t] = in[((uint64_t)c << lg) + brev(i, lg)];
+    }
+};
+
+// Merkle openings (MerkleTreeProver::prove) for all queries of all trees in one launch.
+struct OpenDesc {
+    const uint32_t* matrix; const uint32_t* nodes;
+    uint64_t col_stride;
+    uint32_t rows, cols, idx, top_size, out_off;
+};
+struct OpenKernel {  // grid.x = descriptors
+    static constexpr bool kBarrier = true;
+    HD static void run(const KCtx& cx, uint32_t*, const OpenDesc* descs, uint32_t* out) {
+        const OpenDesc d = descs[cx.bx];
+        uint32_t* o = out + d.out_off;
+        for (uint32_t c = cx.tid; c < d.cols; c += cx.nt) o[c] = d.matrix[(uint64_t)c * d.col_stride + d.idx];
+        o += d.cols;
+        // sibling path: i = idx + rows; while i >= 2*top: emit nodes[i^1]; i >>= 1
+        uint32_t steps = 0;
+        for (uint64_t i = (uint64_t)d.idx + d.rows; i >= 2ull * d.top_size; i >>= 1) steps++;
+        for (uint32_t w = cx.tid; w < steps * 8; w += cx.nt) {
+            const uint32_t s = w >> 3;
+            const uint64_t i = ((uint64_t)d.idx + d.rows) >> s;
+            o[w] = d.nodes[(i ^ 1) * 8 + (w & 7)];
+        }
+    }
+};
+
+}  // namespace hf

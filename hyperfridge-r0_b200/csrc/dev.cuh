@@ -1,0 +1,126 @@
+// Launch / memory plumbing shared by every kernel of libhfb200.
+//
+// Kernels are written once as `Body::run(const KCtx&, uint32_t* smem, args...)` functors:
+//   * real build (nvcc, sm_100a): `kernel_entry<Body, ...>` is the __global__ wrapper, launched on the
+//     context's stream; this is the only thing libhfb200.so contains.
+//   * -DHFB200_EMU (tests/emu only, never part of libhfb200.so): the same Body is executed on the host,
+//     block by block, so index arithmetic / twiddle schedules can be checked in the CPU-only test tier
+//     before GPU minutes are spent.  Barrier kernels (kBarrier = true) are written as work-item loops
+//     `for (i = cx.tid; i < n; i += cx.nt)` separated by cx.sync(), which the emulator runs with nt = 1.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <stdexcept>
+#include <vector>
+#include "field.cuh"
+
+namespace hf {
+
+struct KCtx {
+    int tid, nt;            // thread index / threads per block
+    unsigned bx, by, gx, gy;  // block index / grid size
+    HD void sync() const {
+#ifdef __CUDA_ARCH__
+        __syncthreads();
+#endif
+    }
+};
+
+struct Err : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#ifndef HFB200_EMU
+// ------------------------------------------------------------------ real CUDA build
+#define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { char b_[512]; std::snprintf(b_, sizeof b_, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); throw hf::Err(b_); } } while (0)
+
+template <typename Body, int MAXT, int MINB, typename... A>
+__global__ void __launch_bounds__(MAXT, MINB) kernel_entry(A... a) {
+    extern __shared__ uint4 smem_raw_[];
+    KCtx cx{(int)threadIdx.x, (int)blockDim.x, blockIdx.x, blockIdx.y, gridDim.x, gridDim.y};
+    Body::run(cx, reinterpret_cast<uint32_t*>(smem_raw_), a...);
+}
+
+struct Dev {
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    int sm_count = 148;
+    template <typename Body, int MAXT = 256, int MINB = 1, typename... A>
+    void launch(unsigned gx, unsigned gy, int block, size_t smem, A... a) {
+        if (gx == 0 || gy == 0) return;
+        auto k = kernel_entry<Body, MAXT, MINB, A...>;
+        if (smem > 48 * 1024) {
+            // per template instantiation and per host thread (= per device in the multi-GPU pool)
+            static thread_local size_t configured_bytes = 0;
+            if (smem > configured_bytes) {
+                CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured_bytes = smem;
+            }
+        }
+        k<<<dim3(gx, gy), block, smem, stream>>>(a...);
+        CUDA_CHECK(cudaGetLastError());
+        launches++;
+    }
+    void* alloc(size_t bytes) { void* p; CUDA_CHECK(cudaMalloc(&p, bytes)); return p; }
+    void free(void* p) { if (p) cudaFree(p); }
+    void h2d(void* d, const void* h, size_t bytes) { CUDA_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream)); }
+    void d2h(void* h, const void* d, size_t bytes) { CUDA_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, stream)); }
+    void d2d(void* d, const void* s, size_t bytes) { CUDA_CHECK(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, stream)); }
+    void zero(void* d, size_t bytes) { CUDA_CHECK(cudaMemsetAsync(d, 0, bytes, stream)); }
+    void sync() { CUDA_CHECK(cudaStreamSynchronize(stream)); }
+};
+
+struct Timer {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStream_t st = nullptr;
+    void init(cudaStream_t s) { st = s; CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); }
+    void destroy() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); e0 = e1 = nullptr; }
+    void start() { CUDA_CHECK(cudaEventRecord(e0, st)); }
+    void stop() { CUDA_CHECK(cudaEventRecord(e1, st)); }
+    float ms() { CUDA_CHECK(cudaEventSynchronize(e1)); float m = 0; CUDA_CHECK(cudaEventElapsedTime(&m, e0, e1)); return m; }
+};
+
+#else
+// ------------------------------------------------------------------ host emulator (tests/emu only)
+#define CUDA_CHECK(x) do { } while (0)
+struct Dev {
+    void* stream = nullptr;
+    uint64_t launches = 0;
+    int sm_count = 148;
+    template <typename Body, int MAXT = 256, int MINB = 1, typename... A>
+    void launch(unsigned gx, unsigned gy, int block, size_t smem, A... a) {
+        if (gx == 0 || gy == 0) return;
+        launches++;
+        #pragma omp parallel
+        {
+            std::vector<uint32_t> sm(smem / 4 + 8);
+            #pragma omp for collapse(2) schedule(dynamic)
+            for (long by = 0; by < (long)gy; by++)
+                for (long bx = 0; bx < (long)gx; bx++) {
+                    if (Body::kBarrier) {
+                        Body::run(KCtx{0, 1, (unsigned)bx, (unsigned)by, gx, gy}, sm.data(), a...);
+                    } else {
+                        for (int t = 0; t < block; t++) Body::run(KCtx{t, block, (unsigned)bx, (unsigned)by, gx, gy}, sm.data(), a...);
+                    }
+                }
+        }
+    }
+    void* alloc(size_t bytes) { void* p = std::malloc(bytes ? bytes : 1); if (!p) throw Err("emu: out of memory"); return p; }
+    void free(void* p) { std::free(p); }
+    void h2d(void* d, const void* h, size_t bytes) { std::memcpy(d, h, bytes); }
+    void d2h(void* h, const void* d, size_t bytes) { std::memcpy(h, d, bytes); }
+    void d2d(void* d, const void* s, size_t bytes) { std::memmove(d, s, bytes); }
+    void zero(void* d, size_t bytes) { std::memset(d, 0, bytes); }
+    void sync() {}
+};
+struct Timer {
+    void init(void*) {}
+    void destroy() {}
+    void start() {}
+    void stop() {}
+    float ms() { return 0.f; }
+};
+#endif
+
+}  // namespace hf

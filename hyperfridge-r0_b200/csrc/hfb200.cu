@@ -1,0 +1,266 @@
+// C ABI of libhfb200.so (see include/hfb200.h for the boundary contract and reference citations).
+#include "../../include/hfb200.h"
+#include "prover.cuh"
+
+using namespace hf;
+
+struct hfb200_ctx { Prover p; std::vector<uint32_t> seal; };
+
+static const char* dup_err(const std::string& s) {
+    char* m = (char*)std::malloc(s.size() + 1);
+    if (!m) return "hfb200: out of memory while reporting an error";
+    std::memcpy(m, s.c_str(), s.size() + 1);
+    return m;
+}
+#define API_TRY try {
+#define API_CATCH } catch (const std::exception& e) { return dup_err(e.what()); } catch (...) { return dup_err("hfb200: unknown error"); } return nullptr;
+
+static const char* emit_seal(hfb200_ctx* ctx, uint32_t* seal_out, size_t seal_cap, size_t* seal_words) {
+    if (seal_words) *seal_words = ctx->seal.size();
+    if (seal_cap < ctx->seal.size() || !seal_out) return dup_err("seal buffer too small: need " + std::to_string(ctx->seal.size()) + " words");
+    std::memcpy(seal_out, ctx->seal.data(), ctx->seal.size() * 4);
+    return nullptr;
+}
+
+extern "C" {
+
+const char* hfb200_version(void) {
+#ifdef HFB200_EMU
+    return "hfb200 0.1 (HOST EMULATOR - test build, not a product)";
+#else
+    return "hfb200 0.1 (sm_100a)";
+#endif
+}
+
+void hfb200_free_error(const char* msg) { std::free((void*)msg); }
+
+const char* hfb200_init(int device, uint32_t max_po2, const hfb200_circuit_desc* c, hfb200_ctx** out) {
+    API_TRY
+    if (!out) throw Err("hfb200_init: out is NULL");
+    *out = nullptr;
+    hfb200_circuit_desc d = c ? *c : hfb200_circuit_desc{16, 192, 48, 0};
+    hfb200_ctx* ctx = new hfb200_ctx();
+    try { ctx->p.init(device, max_po2, d.w_code, d.w_data, d.w_accum); } catch (...) { delete ctx; throw; }
+    *out = ctx;
+    API_CATCH
+}
+void hfb200_destroy(hfb200_ctx* ctx) {
+    if (!ctx) return;
+    try { ctx->p.destroy(); } catch (...) {}
+    delete ctx;
+}
+
+const char* hfb200_host_alloc(size_t bytes, void** out) {
+    API_TRY
+#ifndef HFB200_EMU
+    CUDA_CHECK(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+#else
+    *out = std::malloc(bytes);
+#endif
+    API_CATCH
+}
+void hfb200_host_free(void* p) {
+#ifndef HFB200_EMU
+    cudaFreeHost(p);
+#else
+    std::free(p);
+#endif
+}
+
+const char* hfb200_prove_segment(hfb200_ctx* ctx, uint32_t po2, const uint32_t* globals, const uint32_t* code, const uint32_t* data,
+                                 uint64_t blind_seed, uint32_t* seal_out, size_t seal_cap, size_t* seal_words) {
+    API_TRY
+    if (!ctx || !globals || !code || !data) throw Err("hfb200_prove_segment: NULL argument");
+    ctx->p.begin(po2, globals, code, data, blind_seed);
+    ctx->p.finish(nullptr, ctx->seal);
+    if (const char* e = emit_seal(ctx, seal_out, seal_cap, seal_words)) return e;
+    API_CATCH
+}
+
+const char* hfb200_segment_begin(hfb200_ctx* ctx, uint32_t po2, const uint32_t* globals, const uint32_t* code, const uint32_t* data,
+                                 uint64_t blind_seed, uint32_t* mix_out, size_t mix_cap, size_t* mix_words) {
+    API_TRY
+    if (!ctx || !globals) throw Err("hfb200_segment_begin: NULL argument");
+    ctx->p.begin(po2, globals, code, data, blind_seed);
+    if (mix_words) *mix_words = ctx->p.mix.size();
+    if (mix_out) {
+        if (mix_cap < ctx->p.mix.size()) throw Err("mix buffer too small");
+        std::memcpy(mix_out, ctx->p.mix.data(), ctx->p.mix.size() * 4);
+    }
+    API_CATCH
+}
+const char* hfb200_segment_finish(hfb200_ctx* ctx, const uint32_t* accum_or_null, uint32_t* seal_out, size_t seal_cap, size_t* seal_words) {
+    API_TRY
+    if (!ctx) throw Err("hfb200_segment_finish: NULL ctx");
+    ctx->p.finish(accum_or_null, ctx->seal);
+    if (const char* e = emit_seal(ctx, seal_out, seal_cap, seal_words)) return e;
+    API_CATCH
+}
+
+const char* hfb200_witgen_synth(hfb200_ctx* ctx, uint32_t po2, uint64_t trace_seed, uint64_t blind_seed, uint32_t* globals_out) {
+    API_TRY
+    if (!ctx || !globals_out) throw Err("hfb200_witgen_synth: NULL argument");
+    ctx->p.witgen(po2, trace_seed, blind_seed, globals_out);
+    API_CATCH
+}
+const char* hfb200_prove_resident(hfb200_ctx* ctx, uint64_t blind_seed, uint32_t* seal_out, size_t seal_cap, size_t* seal_words) {
+    API_TRY
+    if (!ctx) throw Err("hfb200_prove_resident: NULL ctx");
+    if (!ctx->p.have_trace) throw Err("hfb200_prove_resident: no resident trace (call hfb200_witgen_synth)");
+    uint32_t g[N_GLOBAL];
+    std::memcpy(g, ctx->p.globals, sizeof g);
+    ctx->p.begin(ctx->p.po2, g, nullptr, nullptr, blind_seed);
+    ctx->p.finish(nullptr, ctx->seal);
+    if (const char* e = emit_seal(ctx, seal_out, seal_cap, seal_words)) return e;
+    API_CATCH
+}
+const char* hfb200_read_group(hfb200_ctx* ctx, uint32_t group, uint32_t* out, size_t cap_words) {
+    API_TRY
+    if (!ctx || group > 2 || !ctx->p.tr[group]) throw Err("hfb200_read_group: bad argument");
+    const size_t words = (size_t)ctx->p.cir.group_width((int)group) << ctx->p.po2;
+    if (cap_words < words) throw Err("hfb200_read_group: buffer too small");
+    ctx->p.dev.d2h(out, ctx->p.tr[group], words * 4);
+    ctx->p.dev.sync();
+    API_CATCH
+}
+
+size_t hfb200_seal_words(const hfb200_ctx* ctx, uint32_t po2) { return ctx ? ctx->p.seal_words(po2) : 0; }
+
+const char* hfb200_checkpoint(hfb200_ctx* ctx, const char* name, uint32_t* out, size_t cap, size_t* n_words) {
+    API_TRY
+    if (!ctx || !name) throw Err("hfb200_checkpoint: NULL argument");
+    for (auto& kv : ctx->p.cps)
+        if (kv.first == name) {
+            if (n_words) *n_words = kv.second.size();
+            if (out) { if (cap < kv.second.size()) throw Err("checkpoint buffer too small"); std::memcpy(out, kv.second.data(), kv.second.size() * 4); }
+            return nullptr;
+        }
+    throw Err(std::string("no such checkpoint: ") + name);
+    API_CATCH
+}
+
+const char* hfb200_last_stats(hfb200_ctx* ctx, hfb200_stats* out) {
+    API_TRY
+    if (!ctx || !out) throw Err("hfb200_last_stats: NULL argument");
+    const Stats& s = ctx->p.stats;
+    out->ms_total = s.ms_total; out->ms_h2d = s.ms_h2d; out->ms_ntt_main = s.ms_ntt_main; out->ms_hash_main = s.ms_hash_main;
+    out->ms_accum = s.ms_accum; out->ms_check = s.ms_check; out->ms_deep = s.ms_deep; out->ms_fri = s.ms_fri;
+    out->launches = s.launches; out->ntt_main_bytes = s.ntt_main_bytes;
+    API_CATCH
+}
+uint64_t hfb200_total_launches(const hfb200_ctx* ctx) { return ctx ? ctx->p.dev.launches : 0; }
+
+// ---- HAL-level operators ------------------------------------------------------------------------
+struct DevBuf {
+    Dev& d; uint32_t* p;
+    DevBuf(Dev& dev, size_t words) : d(dev), p((uint32_t*)dev.alloc(words * 4)) {}
+    ~DevBuf() { d.free(p); }
+};
+
+const char* hfb200_op_interpolate_ntt(hfb200_ctx* ctx, uint32_t* io, size_t count, size_t n, int zk_shift) {
+    API_TRY
+    Dev& d = ctx->p.dev;
+    const int lg = ilog2(n);
+    if ((1ull << lg) != n || lg > 24 || count == 0) throw Err("op_interpolate_ntt: bad size");
+    DevBuf b(d, count * n);
+    d.h2d(b.p, io, count * n * 4);
+    ctx->p.ntt.interpolate(b.p, n, b.p, n, (uint32_t)count, lg, zk_shift != 0);
+    d.d2h(io, b.p, count * n * 4);
+    d.sync();
+    API_CATCH
+}
+const char* hfb200_op_expand_ntt(hfb200_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, size_t n_in, uint32_t expand_bits) {
+    API_TRY
+    Dev& d = ctx->p.dev;
+    const int lg = ilog2(n_in);
+    if ((1ull << lg) != n_in || lg + (int)expand_bits > 24 || (expand_bits != 0 && expand_bits != 2) || count == 0) throw Err("op_expand_ntt: bad size");
+    DevBuf bi(d, count * n_in), bo(d, (count * n_in) << expand_bits);
+    d.h2d(bi.p, in, count * n_in * 4);
+    ctx->p.ntt.expand_evaluate(bi.p, n_in, bo.p, n_in << expand_bits, (uint32_t)count, lg, (int)expand_bits);
+    d.d2h(out, bo.p, ((count * n_in) << expand_bits) * 4);
+    d.sync();
+    API_CATCH
+}
+const char* hfb200_op_lde(hfb200_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, size_t n_in) {
+    API_TRY
+    Dev& d = ctx->p.dev;
+    const int lg = ilog2(n_in);
+    if ((1ull << lg) != n_in || lg > 22 || count == 0) throw Err("op_lde: bad size");
+    DevBuf bi(d, count * n_in), bs(d, count * n_in), bo(d, count * n_in * 4);
+    d.h2d(bi.p, in, count * n_in * 4);
+    ctx->p.ntt.lde(bi.p, n_in, bo.p, n_in * 4, bs.p, (uint32_t)count, lg);
+    d.d2h(out, bo.p, count * n_in * 16);
+    d.sync();
+    API_CATCH
+}
+const char* hfb200_op_merkle(hfb200_ctx* ctx, const uint32_t* matrix, size_t rows, size_t cols, uint32_t* nodes_out) {
+    API_TRY
+    Dev& d = ctx->p.dev;
+    if ((1ull << ilog2(rows)) != rows || rows < 2 || cols == 0) throw Err("op_merkle: rows must be a power of two >= 2");
+    DevBuf bm(d, rows * cols), bn(d, 2 * rows * 8);
+    d.h2d(bm.p, matrix, rows * cols * 4);
+    d.zero(bn.p, 8 * 4);
+    ctx->p.merkle.build(bm.p, rows, (uint32_t)rows, (uint32_t)cols, bn.p);
+    d.d2h(nodes_out, bn.p, 2 * rows * 8 * 4);
+    d.sync();
+    API_CATCH
+}
+const char* hfb200_op_poseidon2(hfb200_ctx* ctx, uint32_t* states, size_t n) {
+    API_TRY
+    Dev& d = ctx->p.dev;
+    DevBuf b(d, n * 24);
+    d.h2d(b.p, states, n * 24 * 4);
+    d.launch<PermuteKernel, 128, 1>((unsigned)((n + 127) / 128), 1, 128, 0, b.p, (uint32_t)n);
+    d.d2h(states, b.p, n * 24 * 4);
+    d.sync();
+    API_CATCH
+}
+const char* hfb200_op_fri_fold(hfb200_ctx* ctx, uint32_t* out, const uint32_t* in, size_t n, const uint32_t* mix4) {
+    API_TRY
+    Dev& d = ctx->p.dev;
+    if (n < 16 || (n & 15)) throw Err("op_fri_fold: n must be a multiple of 16");
+    DevBuf bi(d, 4 * n), bo(d, 4 * n / 16);
+    d.h2d(bi.p, in, 4 * n * 4);
+    FriFoldArgs fa{};
+    fa.in = bi.p; fa.out = bo.p; fa.n = (uint32_t)n;
+    const E4 fm = e4(mix4[0], mix4[1], mix4[2], mix4[3]);
+    { E4 cur = e4_one(); for (int i = 0; i < 16; i++) { fa.mixpow[i] = cur; cur = e4_mul(cur, fm); } }
+    d.launch<FriFoldKernel, 256, 1>((unsigned)((n / 16 + 255) / 256), 1, 256, 0, fa);
+    d.d2h(out, bo.p, (4 * n / 16) * 4);
+    d.sync();
+    API_CATCH
+}
+
+const char* hfb200_bench_lde(hfb200_ctx* ctx, uint32_t po2, uint32_t count, uint32_t iters, float* ms_avg) {
+    API_TRY
+    Prover& p = ctx->p;
+    p.layout(po2);
+    if (count == 0 || count > p.cir.cd.w_data) throw Err("bench_lde: count must be in [1, w_data]");
+    if (!p.have_trace) throw Err("bench_lde: call hfb200_witgen_synth first");
+    const size_t N = (size_t)1 << po2;
+    Timer t; t.init(p.dev.stream);
+    p.ntt.lde(p.tr[GROUP_DATA], N, p.ev[GROUP_DATA], 4 * N, p.scratch, count, (int)po2);  // warm-up
+    t.start();
+    for (uint32_t i = 0; i < iters; i++) p.ntt.lde(p.tr[GROUP_DATA], N, p.ev[GROUP_DATA], 4 * N, p.scratch, count, (int)po2);
+    t.stop();
+    *ms_avg = t.ms() / (iters ? iters : 1);
+    t.destroy();
+    API_CATCH
+}
+const char* hfb200_bench_merkle(hfb200_ctx* ctx, uint32_t po2, uint32_t count, uint32_t iters, float* ms_avg) {
+    API_TRY
+    Prover& p = ctx->p;
+    p.layout(po2);
+    if (count == 0 || count > p.cir.cd.w_data) throw Err("bench_merkle: count must be in [1, w_data]");
+    const size_t D = (size_t)4 << po2;
+    Timer t; t.init(p.dev.stream);
+    p.merkle.build(p.ev[GROUP_DATA], D, (uint32_t)D, count, p.nodes[GROUP_DATA]);
+    t.start();
+    for (uint32_t i = 0; i < iters; i++) p.merkle.build(p.ev[GROUP_DATA], D, (uint32_t)D, count, p.nodes[GROUP_DATA]);
+    t.stop();
+    *ms_avg = t.ms() / (iters ? iters : 1);
+    t.destroy();
+    API_CATCH
+}
+
+}  // extern "C"

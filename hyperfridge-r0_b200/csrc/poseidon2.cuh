@@ -1,0 +1,228 @@
+// Poseidon2 (BabyBear, t = 24, x^7, 4+21+4 rounds) permutation, sponge and Merkle kernels.
+// Replaces risc0-zkp 3.0.4 `core::hash::poseidon2` + `Hal::hash_rows` / `Hal::hash_fold` (upstream GPU:
+// sppark poseidon2_rows/fold in risc0-sys 1.5.0; /root/reference/Cargo.lock:3174-3223, not vendored;
+// SURVEY.md Appendix A.3/A.4).  Integer-pipe bound: one thread owns one 24-word sponge state in
+// registers; a warp owns 32 consecutive rows so every column read is one coalesced 128-byte line.
+#pragma once
+#include "dev.cuh"
+
+namespace hf {
+
+#include "poseidon2_consts.inc"
+
+struct P2Consts {
+    uint32_t rc_first[96], rc_partial[21], rc_last[96], diag[24];  // Montgomery form
+};
+
+static inline P2Consts p2_make_consts() {
+    P2Consts c;
+    for (int i = 0; i < 96; i++) { c.rc_first[i] = to_mont(P2_RC_FULL_FIRST[i]); c.rc_last[i] = to_mont(P2_RC_FULL_LAST[i]); }
+    for (int i = 0; i < 21; i++) c.rc_partial[i] = to_mont(P2_RC_PARTIAL[i]);
+    for (int i = 0; i < 24; i++) c.diag[i] = to_mont(P2_M_INT_DIAG[i]);
+    return c;
+}
+
+#if !defined(HFB200_EMU)
+__constant__ P2Consts g_p2c;
+#define P2C_DEV g_p2c
+#endif
+static P2Consts g_p2c_host;
+static bool g_p2c_host_ready = false;
+static inline const P2Consts& p2_host_consts() {
+    if (!g_p2c_host_ready) { g_p2c_host = p2_make_consts(); g_p2c_host_ready = true; }
+    return g_p2c_host;
+}
+
+HD const P2Consts& p2c() {
+#if defined(__CUDA_ARCH__)
+    return P2C_DEV;
+#else
+    return g_p2c_host;
+#endif
+}
+
+HD uint32_t sbox7(uint32_t x) { uint32_t x2 = fmul(x, x), x3 = fmul(x2, x), x4 = fmul(x2, x2); return fmul(x3, x4); }
+
+// External layer: M4 on each 4-chunk (Poseidon2 add/double chain) then add the cross-chunk column sums.
+HD void p2_m_ext(uint32_t* s) {
+#pragma unroll
+    for (int c = 0; c < 24; c += 4) {
+        uint32_t a = s[c], b = s[c + 1], cc = s[c + 2], d = s[c + 3];
+        uint32_t t0 = fadd(a, b), t1 = fadd(cc, d);
+        uint32_t t2 = fadd(fadd(b, b), t1), t3 = fadd(fadd(d, d), t0);
+        uint32_t t4 = fadd(t1, t1); t4 = fadd(fadd(t4, t4), t3);
+        uint32_t t5 = fadd(t0, t0); t5 = fadd(fadd(t5, t5), t2);
+        s[c] = fadd(t3, t5); s[c + 1] = t5; s[c + 2] = fadd(t2, t4); s[c + 3] = t4;
+    }
+    uint32_t sum[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) sum[j] = fadd(fadd(fadd(s[j], s[4 + j]), fadd(s[8 + j], s[12 + j])), fadd(s[16 + j], s[20 + j]));
+#pragma unroll
+    for (int i = 0; i < 24; i++) s[i] = fadd(s[i], sum[i & 3]);
+}
+
+HD void p2_m_int(uint32_t* s, const P2Consts& k) {
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < 24; i++) sum = fadd(sum, s[i]);
+#pragma unroll
+    for (int i = 0; i < 24; i++) s[i] = fadd(sum, fmul(k.diag[i], s[i]));
+}
+
+HD void p2_mix(uint32_t* s) {
+    const P2Consts& k = p2c();
+    p2_m_ext(s);
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 24; i++) s[i] = sbox7(fadd(s[i], k.rc_first[r * 24 + i]));
+        p2_m_ext(s);
+    }
+#pragma unroll 1
+    for (int r = 0; r < 21; r++) {
+        s[0] = sbox7(fadd(s[0], k.rc_partial[r]));
+        p2_m_int(s, k);
+    }
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 24; i++) s[i] = sbox7(fadd(s[i], k.rc_last[r * 24 + i]));
+        p2_m_ext(s);
+    }
+}
+
+// ---- kernels ------------------------------------------------------------------------------------
+// Hal::hash_rows: leaf r = unpadded sponge over matrix[c * col_stride + r], c < cols.  Digest -> nodes[rows + r].
+struct HashRowsKernel {
+    static constexpr bool kBarrier = false;
+    HD static void run(const KCtx& cx, uint32_t*, const uint32_t* matrix, uint64_t col_stride, uint32_t rows, uint32_t cols, uint32_t* nodes) {
+        const uint64_t r = (uint64_t)cx.bx * cx.nt + cx.tid;
+        if (r >= rows) return;
+        uint32_t s[24];
+#pragma unroll
+        for (int i = 0; i < 24; i++) s[i] = 0;
+        const uint32_t* src = matrix + r;
+        uint32_t c = 0;
+        for (; c + 16 <= cols; c += 16) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) s[i] = src[(uint64_t)(c + i) * col_stride];
+            p2_mix(s);
+        }
+        if (c < cols || cols == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) s[i] = (c + i < cols) ? src[(uint64_t)(c + i) * col_stride] : 0u;
+            p2_mix(s);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(nodes + ((uint64_t)rows + r) * 8);
+        dst[0] = make_uint4(s[0], s[1], s[2], s[3]);
+        dst[1] = make_uint4(s[4], s[5], s[6], s[7]);
+    }
+};
+
+// Hal::hash_fold for one level: nodes[i] = H(nodes[2i] || nodes[2i+1]) for i in [level_size, 2*level_size).
+struct HashFoldKernel {
+    static constexpr bool kBarrier = false;
+    HD static void run(const KCtx& cx, uint32_t*, uint32_t* nodes, uint32_t level_size) {
+        const uint64_t t = (uint64_t)cx.bx * cx.nt + cx.tid;
+        if (t >= level_size) return;
+        const uint64_t i = level_size + t;
+        const uint4* in = reinterpret_cast<const uint4*>(nodes + 2 * i * 8);
+        uint32_t s[24];
+        uint4 v0 = in[0], v1 = in[1], v2 = in[2], v3 = in[3];
+        s[0] = v0.x; s[1] = v0.y; s[2] = v0.z; s[3] = v0.w; s[4] = v1.x; s[5] = v1.y; s[6] = v1.z; s[7] = v1.w;
+        s[8] = v2.x; s[9] = v2.y; s[10] = v2.z; s[11] = v2.w; s[12] = v3.x; s[13] = v3.y; s[14] = v3.z; s[15] = v3.w;
+#pragma unroll
+        for (int k = 16; k < 24; k++) s[k] = 0;
+        p2_mix(s);
+        uint4* dst = reinterpret_cast<uint4*>(nodes + i * 8);
+        dst[0] = make_uint4(s[0], s[1], s[2], s[3]);
+        dst[1] = make_uint4(s[4], s[5], s[6], s[7]);
+    }
+};
+
+// The last levels of the tree in one block: levels of size top, top/2, ..., 1 (top <= block threads).
+struct HashFoldTailKernel {
+    static constexpr bool kBarrier = true;
+    HD static void run(const KCtx& cx, uint32_t*, uint32_t* nodes, uint32_t top) {
+        for (uint32_t level = top; level >= 1; level >>= 1) {
+            for (uint32_t t = cx.tid; t < level; t += cx.nt) {
+                const uint64_t i = level + t;
+                uint32_t s[24];
+#pragma unroll
+                for (int k = 0; k < 16; k++) s[k] = nodes[2 * i * 8 + k];
+#pragma unroll
+                for (int k = 16; k < 24; k++) s[k] = 0;
+                p2_mix(s);
+#pragma unroll
+                for (int k = 0; k < 8; k++) nodes[i * 8 + k] = s[k];
+            }
+#ifdef __CUDA_ARCH__
+            __threadfence_block();
+#endif
+            cx.sync();
+        }
+    }
+};
+
+// poseidon2_mix on n independent states (parity probe for the permutation itself).
+struct PermuteKernel {
+    static constexpr bool kBarrier = false;
+    HD static void run(const KCtx& cx, uint32_t*, uint32_t* states, uint32_t n) {
+        const uint64_t t = (uint64_t)cx.bx * cx.nt + cx.tid;
+        if (t >= n) return;
+        uint32_t s[24];
+        for (int i = 0; i < 24; i++) s[i] = states[t * 24 + i];
+        p2_mix(s);
+        for (int i = 0; i < 24; i++) states[t * 24 + i] = s[i];
+    }
+};
+
+struct Merkle {
+    Dev* dev = nullptr;
+    void init(Dev* d) {
+        dev = d;
+        p2_host_consts();
+#if !defined(HFB200_EMU)
+        CUDA_CHECK(cudaMemcpyToSymbol(g_p2c, &g_p2c_host, sizeof(P2Consts)));
+#endif
+    }
+    // nodes: 2*rows digests (heap layout).  matrix element (r, c) at matrix[c*col_stride + r].
+    void build(const uint32_t* matrix, uint64_t col_stride, uint32_t rows, uint32_t cols, uint32_t* nodes) {
+        const int T = 128;
+        dev->launch<HashRowsKernel, 128, 1>((rows + T - 1) / T, 1, T, 0, matrix, col_stride, rows, cols, nodes);
+        uint32_t level = rows / 2;
+        for (; level >= 512; level >>= 1) dev->launch<HashFoldKernel, 128, 1>((level + T - 1) / T, 1, T, 0, nodes, level);
+        if (level >= 1) dev->launch<HashFoldTailKernel, 256, 1>(1, 1, 256, 0, nodes, level);
+    }
+};
+
+// ---- host-side sponge / RNG for the Fiat-Shamir transcript (WriteIOP) ---------------------------------
+struct Digest8 { uint32_t w[8]; };
+
+static inline Digest8 host_hash_elems(const uint32_t* in, size_t n) {
+    p2_host_consts();
+    uint32_t s[24] = {0};
+    size_t used = 0; bool any = false;
+    for (size_t i = 0; i < n; i++) {
+        s[used++] = in[i];
+        if (used == 16) { p2_mix(s); used = 0; any = true; }
+    }
+    if (used != 0 || !any) { for (size_t k = used; k < 16; k++) s[k] = 0; p2_mix(s); }
+    Digest8 d; for (int i = 0; i < 8; i++) d.w[i] = s[i];
+    return d;
+}
+
+struct HostRng {
+    uint32_t cells[24] = {0};
+    int pool_used = 0;
+    void mix(const uint32_t* d8) { p2_host_consts(); for (int i = 0; i < 8; i++) cells[i] = fadd(cells[i], d8[i]); p2_mix(cells); pool_used = 0; }
+    uint32_t random_elem() { if (pool_used == 16) { p2_mix(cells); pool_used = 0; } return cells[pool_used++]; }
+    E4 random_ext() { uint32_t a = random_elem(), b = random_elem(), c = random_elem(), d = random_elem(); return e4(a, b, c, d); }
+    uint32_t random_bits(unsigned bits) {
+        uint32_t v = from_mont(random_elem());
+        for (int i = 0; i < 3; i++) { uint32_t n = from_mont(random_elem()); if (v == 0) v = n; }
+        return v & (uint32_t)((1ull << bits) - 1);
+    }
+};
+
+}  // namespace hf

@@ -1,0 +1,472 @@
+// The segment prover: orchestration of the kernels + host-side Fiat-Shamir transcript.
+// Replaces risc0-circuit-rv32im 4.0.4 `SegmentProver::prove(&Segment) -> Seal` and the risc0-zkp 3.0.4
+// `Prover::{commit_group, finalize}` / `fri_prove` flow it drives (/root/reference/Cargo.lock:3087-3223,
+// not vendored; entered from /root/reference/host/src/main.rs:423).
+// Everything heavy stays on the device; the host only runs the (tiny, strictly sequential) transcript.
+#pragma once
+#include <chrono>
+#include <map>
+#include "ntt.cuh"
+#include "poseidon2.cuh"
+#include "circuit.cuh"
+#include "deep.cuh"
+
+namespace hf {
+
+static constexpr uint32_t QUERIES = 50, INV_RATE = 4, FRI_FOLD = 16, FRI_MIN_DEGREE = 256, CHECK_SIZE = 16;
+
+struct MerkleShape {
+    uint32_t rows, layers, top_layer, top_size;
+    explicit MerkleShape(uint32_t r) : rows(r) {
+        layers = (uint32_t)ilog2(r);
+        top_layer = 0;
+        for (uint32_t i = 1; i < layers; i++) { if ((1u << i) > QUERIES) break; top_layer = i; }
+        top_size = 1u << top_layer;
+    }
+    uint32_t path_words() const { return 8 * (layers - top_layer); }
+};
+
+struct Arena {
+    uint8_t* base = nullptr;
+    size_t cap = 0, off = 0;
+    template <typename T> T* take(size_t count) {
+        size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+        if (off + bytes > cap) throw Err("device arena exhausted (raise max_po2 at hfb200_init)");
+        T* p = reinterpret_cast<T*>(base + off);
+        off += bytes;
+        return p;
+    }
+};
+
+struct Stats {
+    float ms_total = 0, ms_h2d = 0, ms_ntt_main = 0, ms_hash_main = 0, ms_accum = 0, ms_check = 0, ms_deep = 0, ms_fri = 0;
+    uint64_t launches = 0, ntt_main_bytes = 0;
+};
+
+struct Tree { uint32_t* matrix; uint64_t col_stride; uint32_t rows, cols; uint32_t* nodes; };
+
+struct Prover {
+    Dev dev;
+    Ntt ntt;
+    Merkle merkle;
+    CircuitHost cir;
+    uint32_t max_po2 = 0;
+    Arena arena;
+    bool debug_checkpoints = false;
+
+    // ---- per-segment state ----
+    uint32_t po2 = 0;
+    bool have_trace = false, begun = false;
+    uint32_t* tr[3] = {nullptr, nullptr, nullptr};  // resident traces: accum, code, data
+    uint32_t* ev[3] = {nullptr, nullptr, nullptr};
+    uint32_t* nodes[3] = {nullptr, nullptr, nullptr};
+    uint32_t *scratch = nullptr, *check = nullptr, *ev_check = nullptr, *nodes_check = nullptr;
+    uint32_t* d_mix = nullptr;
+    size_t seg_mark = 0;  // arena offset after the per-po2 fixed buffers
+    uint32_t globals[N_GLOBAL];
+    std::vector<uint32_t> mix;
+    uint64_t blind_seed = 0;
+    std::vector<uint32_t> proof;
+    HostRng rng;
+    std::vector<std::pair<std::string, std::vector<uint32_t>>> cps;
+    Stats stats;
+    uint64_t launches_at_begin = 0;
+    std::chrono::steady_clock::time_point t_begin;
+#ifndef HFB200_EMU
+    static constexpr int N_EV = 16;
+    cudaEvent_t evs[N_EV] = {};
+#endif
+    float stage_ms[8] = {0};
+
+    void init(int device, uint32_t max_po2_, uint32_t wc, uint32_t wd, uint32_t wa) {
+        if (max_po2_ < 12 || max_po2_ > 22) throw Err("max_po2 must be in [12, 22]");
+        max_po2 = max_po2_;
+#ifndef HFB200_EMU
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) throw Err(std::string("no CUDA device available (libhfb200 has no CPU fallback): ") + cudaGetErrorString(e));
+        if (device < 0 || device >= count) throw Err("device index out of range");
+        CUDA_CHECK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) throw Err(std::string("libhfb200 is built for sm_100a only; found ") + prop.name);
+        dev.sm_count = prop.multiProcessorCount;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&dev.stream, cudaStreamNonBlocking));
+        for (auto& ev_ : evs) CUDA_CHECK(cudaEventCreate(&ev_));
+#else
+        (void)device;
+#endif
+        ntt.init(&dev);
+        merkle.init(&dev);
+        cir.init(&dev, wc, wd, wa);
+        arena.cap = arena_bytes(max_po2);
+        arena.base = (uint8_t*)dev.alloc(arena.cap);
+        if (const char* env = std::getenv("HFB200_DEBUG_CHECKPOINTS")) debug_checkpoints = std::atoi(env) != 0;
+    }
+    void destroy() {
+        dev.free(arena.base);
+        cir.destroy(&dev);
+        ntt.destroy();
+#ifndef HFB200_EMU
+        for (auto& ev_ : evs) if (ev_) cudaEventDestroy(ev_);
+        if (dev.stream) cudaStreamDestroy(dev.stream);
+#endif
+    }
+
+    size_t arena_bytes(uint32_t p) const {
+        const size_t N = (size_t)1 << p, W = cir.n_regs();
+        // traces W*N, LDE (W+16)*4N, trees 4 * 2*4N*8, scratch wd*N, check 16N, E4 side arrays, FRI (< 40N), slack
+        size_t words = W * N + (W + 16) * 4 * N + 4 * 64 * N + (size_t)cir.cd.w_data * N + 16 * N + 8 * 4 * N + 48 * N;
+        words += (W + 16) * ((N + DOT_RPB - 1) / DOT_RPB) * 8 + (1u << 20);
+        return words * 4 + (64u << 20);
+    }
+
+    void mark(int i) {
+#ifndef HFB200_EMU
+        CUDA_CHECK(cudaEventRecord(evs[i], dev.stream));
+#else
+        (void)i;
+#endif
+    }
+    float between(int i, int j) {
+#ifndef HFB200_EMU
+        float m = 0; CUDA_CHECK(cudaEventElapsedTime(&m, evs[i], evs[j])); return m;
+#else
+        (void)i; (void)j; return 0.f;
+#endif
+    }
+
+    void cp_add(const std::string& name, const uint32_t* w, size_t n) { cps.emplace_back(name, std::vector<uint32_t>(w, w + n)); }
+    void cp_add(const std::string& name, const E4& e) { cp_add(name, e.c, 4); }
+
+    // ---- buffers that depend on po2 only (resident trace lives here) ----
+    void layout(uint32_t p) {
+        if (p < 12 || p > max_po2) throw Err("po2 out of range for this context");
+        if (p == po2 && tr[0]) return;
+        po2 = p; have_trace = false;
+        const size_t N = (size_t)1 << p, D = 4 * N;
+        arena.off = 0;
+        const uint32_t w[3] = {cir.cd.w_accum, cir.cd.w_code, cir.cd.w_data};
+        for (int g = 0; g < 3; g++) tr[g] = arena.take<uint32_t>((size_t)w[g] * N);
+        for (int g = 0; g < 3; g++) ev[g] = arena.take<uint32_t>((size_t)w[g] * D);
+        for (int g = 0; g < 3; g++) nodes[g] = arena.take<uint32_t>(2 * D * 8);
+        ev_check = arena.take<uint32_t>(CHECK_SIZE * D);
+        nodes_check = arena.take<uint32_t>(2 * D * 8);
+        check = arena.take<uint32_t>(4 * D);
+        scratch = arena.take<uint32_t>((size_t)cir.cd.w_data * N);
+        d_mix = arena.take<uint32_t>(cir.n_mix());
+        seg_mark = arena.off;
+    }
+
+    // ---- commit helpers ----
+    void commit_tree(const Tree& t, const char* cp_name) {
+        const MerkleShape ms(t.rows);
+        std::vector<uint32_t> top((size_t)2 * ms.top_size * 8);
+        dev.d2h(top.data(), t.nodes, top.size() * 4);
+        dev.sync();
+        proof.insert(proof.end(), top.begin() + (size_t)ms.top_size * 8, top.end());
+        rng.mix(&top[8]);
+        cp_add(cp_name, &top[8], 8);
+    }
+    void commit_group(int g, const char* cp_name, int ev_ntt0, int ev_ntt1, int ev_hash1) {
+        const size_t N = (size_t)1 << po2, D = 4 * N;
+        const uint32_t w = cir.group_width(g);
+        mark(ev_ntt0);
+        ntt.lde(tr[g], N, ev[g], D, scratch, w, (int)po2);
+        mark(ev_ntt1);
+        merkle.build(ev[g], D, (uint32_t)D, w, nodes[g]);
+        mark(ev_hash1);
+        commit_tree(Tree{ev[g], D, (uint32_t)D, w, nodes[g]}, cp_name);
+    }
+
+    // ---- SegmentProver::prove, phase 1: header + CODE + DATA commits, returns the accum mix ----
+    void begin(uint32_t p, const uint32_t* globals_h, const uint32_t* code_h, const uint32_t* data_h, uint64_t blind) {
+        t_begin = std::chrono::steady_clock::now();
+        layout(p);
+        const size_t N = (size_t)1 << po2;
+        arena.off = seg_mark;
+        proof.clear(); cps.clear(); rng = HostRng(); stats = Stats();
+        for (auto& s : stage_ms) s = 0;
+        launches_at_begin = dev.launches;
+        blind_seed = blind;
+        std::memcpy(globals, globals_h, sizeof globals);
+        for (uint32_t i = 0; i < N_GLOBAL; i++) if (globals[i] >= P) throw Err("globals: non-canonical field element");
+        mark(0);
+        if (code_h) { dev.h2d(tr[GROUP_CODE], code_h, (size_t)cir.cd.w_code * N * 4); }
+        if (data_h) { dev.h2d(tr[GROUP_DATA], data_h, (size_t)cir.cd.w_data * N * 4); }
+        if (code_h && data_h) have_trace = true;
+        if (!have_trace) throw Err("no trace: pass code/data or call hfb200_witgen_synth first");
+        mark(1);
+        const Digest8 gh = host_hash_elems(globals, N_GLOBAL);
+        rng.mix(gh.w);
+        proof.insert(proof.end(), globals, globals + N_GLOBAL);
+        proof.push_back(po2);
+        cp_add("globals_hash", gh.w, 8);
+        commit_group(GROUP_CODE, "code_root", 1, 2, 3);
+        commit_group(GROUP_DATA, "data_root", 3, 4, 5);
+        stage_ms[0] = between(0, 1);
+        stage_ms[1] = between(1, 2) + between(3, 4);
+        stage_ms[2] = between(2, 3) + between(4, 5);
+        mix.resize(cir.n_mix());
+        for (auto& m : mix) m = rng.random_elem();
+        cp_add("accum_mix", mix.data(), mix.size());
+        begun = true;
+    }
+
+    void step_accum() {
+        const size_t N = (size_t)1 << po2;
+        const uint32_t nblk = (uint32_t)((N + ACC_RPB - 1) / ACC_RPB);
+        E4* partial = arena.take<E4>((size_t)cir.cd.n_chains * nblk);
+        const size_t sm1 = 2 * ACC_ITEMS * sizeof(E4);
+        dev.launch<AccumKernel, 256, 1>(nblk, cir.cd.n_chains, 256, sm1, tr[GROUP_ACCUM], (const uint32_t*)tr[GROUP_DATA], (const uint32_t*)d_mix, partial, cir.cd, po2, blind_seed, 0);
+        dev.launch<AccumOffsetsKernel, 256, 1>(1, cir.cd.n_chains, 256, 2 * (size_t)nblk * sizeof(E4), partial, nblk);
+        dev.launch<AccumKernel, 256, 1>(nblk, cir.cd.n_chains, 256, sm1, tr[GROUP_ACCUM], (const uint32_t*)tr[GROUP_DATA], (const uint32_t*)d_mix, partial, cir.cd, po2, blind_seed, 1);
+    }
+
+    static uint32_t rou_fwd(int k) { uint32_t g = to_mont(137); for (int i = k; i < 27; i++) g = fmul(g, g); return g; }
+
+    // evaluates `w` columns against weight vector Wt (and its shift by one for the first n_back1 columns)
+    void dot_group(const uint32_t* cols, uint32_t w, uint32_t n_back1, const E4* Wt, E4* out_dev) {
+        const size_t N = (size_t)1 << po2;
+        const uint32_t nblk = (uint32_t)((N + DOT_RPB - 1) / DOT_RPB);
+        const size_t save = arena.off;
+        E4* partial = arena.take<E4>((size_t)w * nblk * 2);
+        dev.launch<DotKernel, 256, 1>(nblk, (w + DOT_CPB - 1) / DOT_CPB, DOT_T, (size_t)DOT_T * DOT_CPB * 2 * sizeof(E4), cols, (uint64_t)N, w, n_back1, Wt, po2, partial);
+        dev.launch<DotReduceKernel, 128, 1>((2 * w + 127) / 128, 1, 128, 0, (const E4*)partial, w, nblk, out_dev);
+        arena.off = save;  // stream order makes reuse by later kernels safe
+    }
+
+    // ---- phase 2: ACCUM commit, check polynomial, DEEP, FRI, queries ----
+    void finish(const uint32_t* accum_h, std::vector<uint32_t>& seal_out) {
+        if (!begun) throw Err("segment_finish without segment_begin");
+        begun = false;
+        const size_t N = (size_t)1 << po2, D = 4 * N;
+        const CircuitDev& cd = cir.cd;
+        const uint32_t W = cir.n_regs(), T = cir.n_taps;
+
+        mark(5);
+        dev.h2d(d_mix, mix.data(), mix.size() * 4);
+        if (accum_h) dev.h2d(tr[GROUP_ACCUM], accum_h, (size_t)cd.w_accum * N * 4);
+        else step_accum();
+        mark(6);
+        stage_ms[3] = between(5, 6);
+        commit_group(GROUP_ACCUM, "accum_root", 6, 7, 8);
+        stage_ms[1] += between(6, 7);
+        stage_ms[2] += between(7, 8);
+
+        // ---- check polynomial ----
+        const E4 poly_mix = rng.random_ext();
+        cp_add("poly_mix", poly_mix);
+        {
+            const uint32_t nc = cd.n_constraints();
+            std::vector<E4> mp(nc);
+            E4 cur = e4_one();
+            for (auto& m : mp) { m = cur; cur = e4_mul(cur, poly_mix); }
+            E4* d_mp = arena.take<E4>(nc);
+            dev.h2d(d_mp, mp.data(), nc * sizeof(E4));
+            EvalCheckArgs a{};
+            a.ev_accum = ev[GROUP_ACCUM]; a.ev_code = ev[GROUP_CODE]; a.ev_data = ev[GROUP_DATA];
+            a.check = check; a.mixpow = d_mp; a.mix = d_mix; a.global0 = globals[0];
+            const uint32_t three_n = fpow(THREE, N), w4 = rou_fwd(2);
+            uint32_t y = three_n;
+            for (int s = 0; s < 4; s++) { a.yinv[s] = finv(fsub(y, ONE)); y = fmul(y, w4); }
+            a.po2 = po2; a.rows_per_block = 128; a.cd = cd;
+            dev.launch<EvalCheckKernel, 128, 1>((unsigned)((D + 127) / 128), 1, 128, (size_t)nc * sizeof(E4), a);
+            dev.sync();  // mp must outlive the copy
+        }
+        // 4 polys of 4N evaluations -> coefficients (no zk_shift); bit-reversed order makes them 16 polys of N
+        ntt.interpolate(check, D, check, D, 4, (int)po2 + 2, false);
+        ntt.expand_evaluate(check, N, ev_check, D, CHECK_SIZE, (int)po2, 2);
+        merkle.build(ev_check, D, (uint32_t)D, CHECK_SIZE, nodes_check);
+        mark(9);
+        commit_tree(Tree{ev_check, D, (uint32_t)D, CHECK_SIZE, nodes_check}, "check_root");
+        stage_ms[4] = between(8, 9);
+
+        // ---- DEEP: evaluations at z ----
+        const E4 z = rng.random_ext();
+        cp_add("z", z);
+        const uint32_t omega = rou_fwd((int)po2), back_one = finv(omega);
+        const E4 z3 = e4_scale(z, THREE), z4 = e4_pow(z, 4);
+        E4 A = e4_pow(z3, N); A.c[0] = fsub(A.c[0], ONE);
+        A = e4_scale(A, finv(to_mont((uint32_t)(N % P))));
+        E4* INV = arena.take<E4>(N); E4* Lw = arena.take<E4>(N); E4* INV4 = arena.take<E4>(N); E4* W4 = arena.take<E4>(N);
+        dev.launch<DeepWeightsKernel, 256, 1>((unsigned)((N + 255) / 256), 1, 256, 0, INV, Lw, INV4, z3, z4, A, po2, ntt.rt);
+        {
+            std::vector<E4> xs(po2);
+            E4 cur = z4;
+            for (uint32_t k = 0; k < po2; k++) { xs[k] = cur; cur = e4_mul(cur, cur); }
+            E4* d_xs = arena.take<E4>(po2);
+            dev.h2d(d_xs, xs.data(), po2 * sizeof(E4));
+            dev.launch<PowBitrevKernel, 256, 1>((unsigned)((N + 255) / 256), 1, 256, 0, W4, (const E4*)d_xs, po2);
+            dev.sync();
+        }
+        E4* d_evals = arena.take<E4>((size_t)2 * (W + CHECK_SIZE));
+        uint32_t goff[4] = {0, 2 * cd.w_accum, 2 * (cd.w_accum + cd.w_code), 2 * W};
+        for (int g = 0; g < 3; g++) dot_group(tr[g], cir.group_width(g), cir.group_back1(g), Lw, d_evals + goff[g]);
+        dot_group(check, CHECK_SIZE, 0, W4, d_evals + goff[3]);
+        std::vector<E4> h_evals((size_t)2 * (W + CHECK_SIZE));
+        dev.d2h(h_evals.data(), d_evals, h_evals.size() * sizeof(E4));
+        dev.sync();
+        // taps order: (group, column, back).  coeff_u: per register, interpolant through its tap points.
+        std::vector<E4> coeff_u(T + CHECK_SIZE);
+        std::vector<uint32_t> reg_tap(W);
+        std::vector<uint8_t> reg_two(W);
+        {
+            const E4 x0 = z, x1 = e4_scale(z, back_one);
+            const E4 dinv = e4_inv(e4_sub(x0, x1));
+            uint32_t t = 0, reg = 0;
+            for (int g = 0; g < 3; g++)
+                for (uint32_t c = 0; c < cir.group_width(g); c++, reg++) {
+                    const E4 u0 = h_evals[goff[g] + 2 * c], u1 = h_evals[goff[g] + 2 * c + 1];
+                    reg_tap[reg] = t;
+                    if (c < cir.group_back1(g)) {
+                        const E4 c1 = e4_mul(e4_sub(u0, u1), dinv);
+                        coeff_u[t] = e4_sub(u0, e4_mul(c1, x0));
+                        coeff_u[t + 1] = c1;
+                        reg_two[reg] = 1; t += 2;
+                    } else { coeff_u[t] = u0; reg_two[reg] = 0; t += 1; }
+                }
+            if (t != T) throw Err("internal: tap count mismatch");
+            for (uint32_t c = 0; c < CHECK_SIZE; c++) coeff_u[T + c] = h_evals[goff[3] + 2 * c];
+        }
+        proof.insert(proof.end(), reinterpret_cast<uint32_t*>(coeff_u.data()), reinterpret_cast<uint32_t*>(coeff_u.data()) + 4 * coeff_u.size());
+        const Digest8 hash_u = host_hash_elems(reinterpret_cast<uint32_t*>(coeff_u.data()), 4 * coeff_u.size());
+        rng.mix(hash_u.w);
+        cp_add("hash_u", hash_u.w, 8);
+
+        // ---- DEEP: quotient, point-wise on the trace domain ----
+        const E4 dmix = rng.random_ext();
+        cp_add("deep_mix", dmix);
+        std::vector<E4> reg_mix(W + CHECK_SIZE);
+        { E4 cur = e4_one(); for (auto& m : reg_mix) { m = cur; cur = e4_mul(cur, dmix); } }
+        DeepMixArgs da{};
+        da.U0 = da.U1a = da.U1b = da.Vc = e4_zero();
+        for (uint32_t reg = 0; reg < W; reg++) {
+            if (reg_two[reg]) { da.U1a = e4_add(da.U1a, e4_mul(reg_mix[reg], coeff_u[reg_tap[reg]])); da.U1b = e4_add(da.U1b, e4_mul(reg_mix[reg], coeff_u[reg_tap[reg] + 1])); }
+            else da.U0 = e4_add(da.U0, e4_mul(reg_mix[reg], coeff_u[reg_tap[reg]]));
+        }
+        for (uint32_t c = 0; c < CHECK_SIZE; c++) da.Vc = e4_add(da.Vc, e4_mul(reg_mix[W + c], coeff_u[T + c]));
+        E4* d_regmix = arena.take<E4>(W + CHECK_SIZE);
+        dev.h2d(d_regmix, reg_mix.data(), reg_mix.size() * sizeof(E4));
+        uint32_t* S0 = arena.take<uint32_t>(4 * N);
+        uint32_t* S1 = arena.take<uint32_t>(4 * N);
+        uint32_t* fin = arena.take<uint32_t>(4 * N);
+        dev.launch<CheckMixKernel, 256, 1>((unsigned)((N + 255) / 256), 1, 256, 0, (const uint32_t*)check, (const E4*)(d_regmix + W), S0, po2, ntt.rt);
+        ntt.expand_evaluate(S0, N, S1, N, 4, (int)po2, 0);
+        for (int g = 0; g < 3; g++) { da.tr[g] = tr[g]; da.w[g] = cir.group_width(g); da.n_back1[g] = cir.group_back1(g); }
+        da.mixpow = d_regmix; da.S = S1; da.INV = INV; da.INV4 = INV4; da.out = fin; da.omega = omega; da.po2 = po2; da.rt = ntt.rt;
+        dev.launch<DeepMixKernel, 256, 1>((unsigned)((N + 255) / 256), 1, 256, 0, da);
+        ntt.interpolate(fin, N, fin, N, 4, (int)po2, true);  // bit-reversed coefficients of the FRI polynomial
+        mark(10);
+        dev.sync();  // reg_mix upload done; stage boundary
+        stage_ms[5] = between(9, 10);
+        if (debug_checkpoints) {
+            std::vector<uint32_t> fc(4 * N);
+            dev.d2h(fc.data(), fin, fc.size() * 4); dev.sync();
+            const Digest8 d = host_hash_elems(fc.data(), fc.size());
+            cp_add("final_poly_hash", d.w, 8);
+        }
+
+        // ---- FRI ----
+        struct Round { Tree tree; };
+        std::vector<Round> rounds;
+        uint32_t* coeffs = fin;
+        size_t n = N;
+        while (n > FRI_MIN_DEGREE) {
+            const size_t dom = n * INV_RATE, rows = dom / FRI_FOLD;
+            uint32_t* evr = arena.take<uint32_t>(4 * dom);
+            uint32_t* ndr = arena.take<uint32_t>(2 * rows * 8);
+            ntt.expand_evaluate(coeffs, n, evr, dom, 4, ilog2(n), 2);
+            merkle.build(evr, rows, (uint32_t)rows, FRI_FOLD * 4, ndr);
+            Tree t{evr, rows, (uint32_t)rows, FRI_FOLD * 4, ndr};
+            const std::string rn = std::to_string(rounds.size());
+            commit_tree(t, ("fri_root_" + rn).c_str());
+            const E4 fm = rng.random_ext();
+            cp_add("fri_mix_" + rn, fm);
+            FriFoldArgs fa{};
+            fa.in = coeffs; fa.n = (uint32_t)n;
+            fa.out = arena.take<uint32_t>(4 * n / FRI_FOLD);
+            { E4 cur = e4_one(); for (int i = 0; i < 16; i++) { fa.mixpow[i] = cur; cur = e4_mul(cur, fm); } }
+            dev.launch<FriFoldKernel, 256, 1>((unsigned)((n / 16 + 255) / 256), 1, 256, 0, fa);
+            coeffs = fa.out;
+            n /= FRI_FOLD;
+            rounds.push_back(Round{t});
+        }
+        {
+            uint32_t* nat = arena.take<uint32_t>(4 * n);
+            dev.launch<BitRevKernel, 256, 1>((unsigned)((4 * n + 255) / 256), 1, 256, 0, (const uint32_t*)coeffs, nat, 4u, (uint32_t)ilog2(n));
+            std::vector<uint32_t> fc(4 * n);
+            dev.d2h(fc.data(), nat, fc.size() * 4); dev.sync();
+            proof.insert(proof.end(), fc.begin(), fc.end());
+            const Digest8 d = host_hash_elems(fc.data(), fc.size());
+            rng.mix(d.w);
+            cp_add("fri_final_hash", d.w, 8);
+        }
+        // ---- queries: every opening of every tree in one gather launch ----
+        {
+            const Tree main_trees[4] = {Tree{ev[0], D, (uint32_t)D, cd.w_accum, nodes[0]}, Tree{ev[1], D, (uint32_t)D, cd.w_code, nodes[1]},
+                                        Tree{ev[2], D, (uint32_t)D, cd.w_data, nodes[2]}, Tree{ev_check, D, (uint32_t)D, CHECK_SIZE, nodes_check}};
+            std::vector<OpenDesc> descs;
+            std::vector<uint32_t> positions;
+            uint32_t off = 0;
+            auto add = [&](const Tree& t, uint32_t idx) {
+                const MerkleShape ms(t.rows);
+                descs.push_back(OpenDesc{t.matrix, t.nodes, t.col_stride, t.rows, t.cols, idx, ms.top_size, off});
+                off += t.cols + ms.path_words();
+            };
+            for (uint32_t q = 0; q < QUERIES; q++) {
+                uint32_t pos = rng.random_bits((unsigned)ilog2(D)) % (uint32_t)D;
+                positions.push_back(pos);
+                for (const Tree& t : main_trees) add(t, pos);
+                for (const Round& r : rounds) { pos %= r.tree.rows; add(r.tree, pos); }
+            }
+            cp_add("query_positions", positions.data(), positions.size());
+            OpenDesc* d_descs = arena.take<OpenDesc>(descs.size());
+            uint32_t* d_out = arena.take<uint32_t>(off);
+            dev.h2d(d_descs, descs.data(), descs.size() * sizeof(OpenDesc));
+            dev.launch<OpenKernel, 128, 1>((unsigned)descs.size(), 1, 128, 0, (const OpenDesc*)d_descs, d_out);
+            const size_t at = proof.size();
+            proof.resize(at + off);
+            mark(11);
+            dev.d2h(proof.data() + at, d_out, (size_t)off * 4);
+            dev.sync();
+        }
+        stage_ms[6] = between(10, 11);
+        stats.ms_h2d = stage_ms[0]; stats.ms_ntt_main = stage_ms[1]; stats.ms_hash_main = stage_ms[2]; stats.ms_accum = stage_ms[3];
+        stats.ms_check = stage_ms[4]; stats.ms_deep = stage_ms[5]; stats.ms_fri = stage_ms[6];
+        stats.ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        stats.launches = dev.launches - launches_at_begin;
+        stats.ntt_main_bytes = 28ull * W * N;
+        seal_out = proof;
+    }
+
+    void witgen(uint32_t p, uint64_t trace_seed, uint64_t blind, uint32_t* globals_out) {
+        layout(p);
+        const size_t N = (size_t)1 << po2;
+        for (uint32_t i = 0; i < N_GLOBAL; i++) globals_out[i] = synth_value(trace_seed ^ 0x676C6F62ull, 0xFFFFu, i);
+        std::memcpy(globals, globals_out, sizeof globals);
+        const CircuitDev& cd = cir.cd;
+        dev.launch<GenCodeKernel, 256, 1>((unsigned)(((size_t)cd.w_code * N + 255) / 256), 1, 256, 0, tr[GROUP_CODE], cd.w_code, po2);
+        dev.launch<GenFreeKernel, 256, 1>((unsigned)(((size_t)cd.w_data * N + 255) / 256), 1, 256, 0, tr[GROUP_DATA], cd, po2, trace_seed, blind, globals_out[0]);
+        dev.launch<GenDerivedKernel, 256, 1>((unsigned)(((size_t)cd.n_free * N + 255) / 256), 1, 256, 0, tr[GROUP_DATA], (const uint32_t*)tr[GROUP_CODE], cd, po2);
+        dev.sync();
+        have_trace = true;
+    }
+
+    size_t seal_words(uint32_t p) const {
+        const size_t W = cir.n_regs(), T = cir.n_taps;
+        size_t n = (size_t)1 << p;
+        const MerkleShape m0((uint32_t)(4 * n));
+        size_t words = N_GLOBAL + 1 + 4 * 8 * m0.top_size + 4 * (T + CHECK_SIZE);
+        size_t per_query = W + CHECK_SIZE + 4 * m0.path_words();
+        while (n > FRI_MIN_DEGREE) {
+            const MerkleShape mr((uint32_t)(4 * n / FRI_FOLD));
+            words += 8 * mr.top_size;
+            per_query += 64 + mr.path_words();
+            n /= FRI_FOLD;
+        }
+        return words + 4 * n + QUERIES * per_query;
+    }
+};
+
+}  // namespace hf

@@ -1,0 +1,128 @@
+/*
+ * hfb200.h -- C ABI of the B200-native STARK segment prover (libhfb200.so).
+ *
+ * Drop-in boundary for the ONE hot path of element36-io/hyperfridge-r0: the call
+ *     let prover = default_prover();                       (/root/reference/host/src/main.rs:420)
+ *     prover.prove(env, HYPERFRIDGE_ELF)                   (/root/reference/host/src/main.rs:423)
+ * which, per segment, runs risc0-circuit-rv32im 4.0.4 `SegmentProver::prove(&Segment) -> Seal` on top of
+ * risc0-zkp 3.0.4's `Hal` / `CircuitHal` traits (/root/reference/Cargo.lock:3087-3223; crates not vendored).
+ * The library sits at that `SegmentProver` seam: trace columns in, seal (u32 words) out.
+ *
+ * Conventions (same as upstream's sys crates, risc0-sys `ffi_wrap`):
+ *   - every entry returns `const char*`: NULL = success, otherwise a malloc'd message that the caller
+ *     releases with hfb200_free_error().  No exceptions or aborts cross the ABI.
+ *   - matrices are column-major u32[w][N] BabyBear residues in MONTGOMERY form (R = 2^32), N = 2^po2.
+ *   - a context is single-owner: one host thread <-> one GPU <-> its stream.  Distinct contexts are
+ *     independent (one per GPU for multi-GPU operation; segments are independent, no collectives).
+ *   - the caller owns every host pointer for the duration of the call; the library owns device memory.
+ *   - there is NO CPU fallback: without a CUDA device hfb200_init fails.
+ */
+#ifndef HFB200_H
+#define HFB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hfb200_ctx hfb200_ctx;
+
+/* Circuit plug-in descriptor.  Replaces the generated rv32im circuit (taps + poly_fp + step_accum of
+ * risc0-circuit-rv32im[-sys], /root/reference/Cargo.lock:3087-3132), which is not obtainable here; the
+ * built-in plug-in is the declared stand-in "synth-rv32im-shape v1" (oracle/circuit.h). */
+typedef struct {
+    uint32_t w_code;  /* control columns  (>= 5)            default 16  */
+    uint32_t w_data;  /* data columns     (multiple of 4)   default 192 */
+    uint32_t w_accum; /* accum columns    (multiple of 4)   default 48  */
+    uint32_t flags;   /* reserved, 0 */
+} hfb200_circuit_desc;
+
+#define HFB200_N_GLOBAL 32u
+#define HFB200_DIGEST_WORDS 8u
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+/* Replaces `segment_prover(hashfn)` / HAL construction.  Allocates the device arena for segments up to
+ * 2^max_po2 cycles (12 <= max_po2 <= 22) and registers the circuit. */
+const char* hfb200_init(int device, uint32_t max_po2, const hfb200_circuit_desc* circuit, hfb200_ctx** out);
+void hfb200_destroy(hfb200_ctx* ctx);
+void hfb200_free_error(const char* msg);
+const char* hfb200_version(void);
+
+/* Pinned host memory for trace staging (plain pointers are accepted too, just slower over PCIe). */
+const char* hfb200_host_alloc(size_t bytes, void** out);
+void hfb200_host_free(void* p);
+
+/* ---- the segment prover (replaces SegmentProver::prove) ------------------------------------- */
+/* One-shot: host trace in, seal out.  `code` = control columns u32[w_code][N], `data` = witness columns
+ * u32[w_data][N] with their blinding rows already filled by the witness generator (upstream's
+ * WitnessGenerator does the same); `blind_seed` fixes the blinding noise of the accum group, which the
+ * library derives on the device (step_accum).  On success *seal_words = words written.  If seal_cap is too
+ * small an error is returned and *seal_words holds the required size. */
+const char* hfb200_prove_segment(hfb200_ctx* ctx, uint32_t po2, const uint32_t* globals /*[32]*/,
+                                 const uint32_t* code, const uint32_t* data, uint64_t blind_seed,
+                                 uint32_t* seal_out, size_t seal_cap, size_t* seal_words);
+
+/* Two-phase form: begin commits CODE and DATA and returns the accum mix
+ * (Fiat-Shamir) so an external step_accum can run; finish takes the accum columns (or NULL to let the
+ * built-in plug-in compute them on the device) and completes the seal. */
+const char* hfb200_segment_begin(hfb200_ctx* ctx, uint32_t po2, const uint32_t* globals, const uint32_t* code,
+                                 const uint32_t* data, uint64_t blind_seed, uint32_t* mix_out, size_t mix_cap, size_t* mix_words);
+const char* hfb200_segment_finish(hfb200_ctx* ctx, const uint32_t* accum_or_null, uint32_t* seal_out, size_t seal_cap, size_t* seal_words);
+
+/* Witness stand-in on the device (replaces preflight + WitnessGenerator for the synthetic circuit):
+ * fills the context's resident code/data columns; globals_out receives the 32 global words. */
+const char* hfb200_witgen_synth(hfb200_ctx* ctx, uint32_t po2, uint64_t trace_seed, uint64_t blind_seed, uint32_t* globals_out);
+/* Proves the resident trace (inputs already in HBM: the `value` leg of bench.py). The trace stays intact. */
+const char* hfb200_prove_resident(hfb200_ctx* ctx, uint64_t blind_seed, uint32_t* seal_out, size_t seal_cap, size_t* seal_words);
+/* Copies resident columns back (group: 0 accum, 1 code, 2 data), for parity tests of witgen/step_accum. */
+const char* hfb200_read_group(hfb200_ctx* ctx, uint32_t group, uint32_t* out, size_t cap_words);
+
+/* Seal length in words for (circuit, po2) -- what upstream's Vec<u32> seal would hold. */
+size_t hfb200_seal_words(const hfb200_ctx* ctx, uint32_t po2);
+
+/* ---- transcript checkpoints of the last proved segment (parity tests) ------------------------ */
+/* names: globals_hash code_root data_root accum_mix accum_root poly_mix check_root z hash_u deep_mix
+ *        final_poly_hash fri_root_<r> fri_mix_<r> fri_final_hash query_positions */
+const char* hfb200_checkpoint(hfb200_ctx* ctx, const char* name, uint32_t* out, size_t cap, size_t* n_words);
+
+/* ---- measurement ------------------------------------------------------------------------------ */
+typedef struct {
+    float ms_total;        /* whole segment, first kernel to seal bytes on host (CUDA events + host waits) */
+    float ms_h2d;          /* host->device trace copies (0 for resident)                                  */
+    float ms_ntt_main;     /* iNTT+zk_shift and expand+NTT (LDE) of code+data+accum columns               */
+    float ms_hash_main;    /* Poseidon2 leaf hashing + tree folds of code+data+accum                      */
+    float ms_accum;        /* step_accum                                                                  */
+    float ms_check;        /* eval_check + check-group commit                                             */
+    float ms_deep;         /* DEEP evaluations + quotient                                                 */
+    float ms_fri;          /* FRI rounds + query openings                                                 */
+    uint64_t launches;     /* kernels launched for the segment                                            */
+    uint64_t ntt_main_bytes; /* algorithmic bytes of ms_ntt_main: 28 * w * N (8 iNTT + 20 LDE)            */
+} hfb200_stats;
+const char* hfb200_last_stats(hfb200_ctx* ctx, hfb200_stats* out);
+uint64_t hfb200_total_launches(const hfb200_ctx* ctx);
+
+/* ---- HAL-level operators (second seam: risc0-zkp `Hal` methods), host buffers in/out ----------- */
+/* Hal::batch_interpolate_ntt (+ Hal::zk_shift when zk_shift != 0): natural-order evaluations ->
+ * bit-reversed coefficients, in place, `count` columns of n = 2^k. */
+const char* hfb200_op_interpolate_ntt(hfb200_ctx* ctx, uint32_t* io, size_t count, size_t n, int zk_shift);
+/* Hal::batch_expand_into_evaluate_ntt(out, in, count, expand_bits): bit-reversed coefficients ->
+ * natural-order evaluations on the 2^expand_bits larger domain (expand_bits in {0, 2}). */
+const char* hfb200_op_expand_ntt(hfb200_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, size_t n_in, uint32_t expand_bits);
+/* The fused production path of commit_group: trace columns -> LDE evaluations (no coefficient round trip). */
+const char* hfb200_op_lde(hfb200_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, size_t n_in);
+/* Hal::hash_rows + Hal::hash_fold: full Merkle tree (heap layout, 2*rows digests) of a column-major matrix. */
+const char* hfb200_op_merkle(hfb200_ctx* ctx, const uint32_t* matrix, size_t rows, size_t cols, uint32_t* nodes_out);
+/* poseidon2_mix on `n` independent 24-word states. */
+const char* hfb200_op_poseidon2(hfb200_ctx* ctx, uint32_t* states, size_t n);
+/* Hal::fri_fold: 4 x n bit-reversed coefficient columns -> 4 x n/16. mix = one Fp4. */
+const char* hfb200_op_fri_fold(hfb200_ctx* ctx, uint32_t* out, const uint32_t* in, size_t n, const uint32_t* mix4);
+/* Device-only timing of the main-group NTT/LDE pipeline on resident synthetic columns (roofline probe):
+ * runs the fused trace->LDE pipeline over `count` columns of 2^po2 `iters` times, returns avg ms. */
+const char* hfb200_bench_lde(hfb200_ctx* ctx, uint32_t po2, uint32_t count, uint32_t iters, float* ms_avg);
+const char* hfb200_bench_merkle(hfb200_ctx* ctx, uint32_t po2, uint32_t count, uint32_t iters, float* ms_avg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HFB200_H */
