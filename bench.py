@@ -1,0 +1,296 @@
+#!/usr/bin/env python3
+"""bench.py -- po2=20 segments/second (and camt53 end-to-end proof seconds) of the B200 segment prover.
+
+  python bench.py --gpus N --steps K --warmup W            (N=1 directly; N>1 under torchrun, one rank per GPU)
+  python bench.py --impl reference --steps K --warmup W    (the CPU baseline arm, see below)
+
+A "step" is one pass of the hot path over one batch = ONE synthetic rv32im-shaped segment of 2^po2 cycles
+(BASELINE.json configs[1]: circuit "synth-rv32im-shape v1", W = 16+192+48 = 256 columns) per GPU.  Segments are
+independent, so N GPUs prove N segments per step with no collective on the data path (weak scaling); NCCL is used
+only for the timing barrier and the max-over-ranks reduction.
+
+  value : segments/s with the trace already resident in HBM when the timed region starts (hfb200_prove_resident)
+  e2e   : the same metric through the reference-facing C-ABI call hfb200_prove_segment with HOST (pinned) trace
+          buffers: host->device copy of code+data columns and device->host seal inside the timed region
+  roofline : the NTT/LDE pipeline (iNTT+zk_shift and x4 expand+NTT of all 256 columns; 9 launches per segment),
+             algorithmic bytes 28*W*N over its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline : the CPU oracle (the only CPU implementation of this path that exists here: upstream's Rust crates
+             are not vendored / buildable) on a bounded sample, scaled linearly in cycles to po2=20
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "po2=20 segments/sec (synthetic rv32im-shaped segment, W=256); camt53 proof seconds = 37 segments / value"
+UNIT = "segments/s"
+WIDTHS = (16, 192, 48)
+CAMT53_SEGMENTS = 37  # /root/reference/docs/runtime.md:50 (segment_count of the test camt53 proof)
+TRACE_SEED = 0x48595046
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_sample_po2(steps, warmup):
+    # ~7.5 s per po2=16 W=256 segment on 8 cores; keep the whole reference run within a few minutes
+    total = max(1, steps + warmup)
+    for po2, est in ((16, 8.0), (15, 4.0), (14, 2.0), (13, 1.0)):
+        if total * est <= 150:
+            return po2
+    return 12
+
+
+def run_oracle_sample(po2, repeats=1):
+    """Times the CPU oracle (all host threads, OpenMP) proving one W=256 segment of 2^po2 cycles."""
+    import oracle
+    cir = oracle.Circuit(*WIDTHS)
+    code = cir.gen_code(po2)
+    g = cir.gen_globals(TRACE_SEED)
+    data = cir.gen_data(po2, code, g, TRACE_SEED, 1)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        cir.prove(po2, g, code, data, 1)
+        times.append(time.perf_counter() - t0)
+    cores = oracle.lib().orc_num_threads()
+    return times, cores
+
+
+def reference_arm(args):
+    """`--impl reference`: the reference's CPU implementation of the path on the box's host cores.  The real one
+    (risc0 3.0.5 Rust crates) cannot be built here, so this is the oracle port (kind = "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    po2 = oracle_sample_po2(args.steps, args.warmup)
+    run_oracle_sample(po2, max(0, args.warmup)) if args.warmup else None
+    t0 = time.perf_counter()
+    times, cores = run_oracle_sample(po2, args.steps)
+    wall = time.perf_counter() - t0
+    per = sum(times) / len(times)
+    scale = float(1 << (20 - po2))
+    value = 1.0 / (per * scale)
+    sample = "oracle CPU restatement (kind=port), %d threads, one W=256 segment of 2^%d cycles per step, scaled x%d linearly in cycles to po2=20" % (cores, po2, int(scale))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (BabyBear mod p)", "data": "synthetic",
+            "config": {"workload": "configs[1]: single synthetic rv32im-shaped segment, po2=20, W=256 (16 code + 192 data + 48 accum)", "sample_po2": po2,
+                       "camt53_proof_seconds": CAMT53_SEGMENTS / value, "camt53_segments": CAMT53_SEGMENTS},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": wall}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--po2", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+    import hfb200_loader
+    pkg = hfb200_loader.load()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the prover has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    po2 = args.po2
+    N = 1 << po2
+    W = sum(WIDTHS)
+    ctx = pkg.Context(device=local_rank, max_po2=po2, circuit=WIDTHS)
+    # per-rank segment: seed = f(global seed, rank) -> every GPU proves a different segment
+    seg_seed = TRACE_SEED + 1000003 * rank
+    g = ctx.witgen_synth(po2, seg_seed, 1 + rank)
+
+    # ---------------- value: resident trace ----------------
+    for i in range(args.warmup):
+        seal = ctx.prove_resident(1 + rank)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.total_launches()
+    stage = {}
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        seal = ctx.prove_resident(1 + rank + 17 * i)  # new accum blinding each step: no cached outputs
+        st = ctx.last_stats()
+        dev_ms += st["ms_device"]
+        for k, v in st.items():
+            stage[k] = stage.get(k, 0.0) + float(v)
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = ctx.total_launches() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    wall = max_over_ranks(wall)
+    dev_ms = max_over_ranks(dev_ms)
+    launches_all = int(sum_over_ranks(float(launches)))
+    ms_per_step = wall * 1e3 / args.steps
+    value = world * args.steps / wall
+    seal_words = int(len(seal))
+
+    # ---------------- e2e: host buffers through the C ABI ----------------
+    e2e = None
+    if not args.no_e2e:
+        code_h = ctx.host_alloc((WIDTHS[0], N))
+        data_h = ctx.host_alloc((WIDTHS[1], N))
+        code_h[...] = ctx.read_group(1)
+        data_h[...] = ctx.read_group(2)
+        for i in range(2):
+            ctx.prove_segment(po2, g, code_h, data_h, 1 + rank)
+        barrier()
+        t0 = time.perf_counter()
+        h2d_ms = 0.0
+        for i in range(args.steps):
+            seal_h = ctx.prove_segment(po2, g, code_h, data_h, 1 + rank + 17 * i)
+            h2d_ms += ctx.last_stats()["ms_h2d"]
+        barrier()
+        wall_e = max_over_ranks(time.perf_counter() - t0)
+        e2e_value = world * args.steps / wall_e
+        e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((WIDTHS[0] + WIDTHS[1]) * N * 4 + 128 + 4 * WIDTHS[2]),
+               "d2h_bytes_per_step": int(len(seal_h) * 4), "ms_per_step": wall_e * 1e3 / args.steps, "ms_h2d_per_step": h2d_ms / args.steps,
+               "camt53_proof_seconds": CAMT53_SEGMENTS / e2e_value, "host_memory": "pinned (hfb200_host_alloc)"}
+        ctx.host_free(code_h)
+        ctx.host_free(data_h)
+
+    # ---------------- roofline of the NTT/LDE pipeline ----------------
+    peak, peak_src = measured_hbm_peak()
+    ntt_ms = stage["ms_ntt_main"] / args.steps
+    ntt_bytes = 28.0 * W * N
+    achieved = ntt_bytes / (ntt_ms * 1e-3) / 1e9 if ntt_ms > 0 else 0.0
+    roofline = {"kernel": "NTT/LDE pipeline of the 3 main groups: StridedKernel(DIF) + MiddleKernel(fused iNTT.zk_shift.expand.NTT chunk stage) + StridedKernel(DIT), 9 launches/segment",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes": ntt_bytes, "ms": ntt_ms, "peak_source": peak_src,
+                "note": "traffic by design = 60*W*N bytes (8 + 20 + 32 per element over the three passes); ncu dram bytes go under profiles/"}
+    # Poseidon2 (integer-ALU bound, no HBM roofline): permutations/s
+    perms = 4 * N * sum((w + 15) // 16 for w in WIDTHS) + 3 * 4 * N
+    hash_ms = stage["ms_hash_main"] / args.steps
+    poseidon = {"kernel": "HashRowsKernel + HashFoldKernel (Poseidon2 t=24) over the 3 main trees", "bound": "integer ALU", "permutations": perms,
+                "ms": hash_ms, "gperm_per_s": perms / (hash_ms * 1e-3) / 1e9 if hash_ms > 0 else 0.0}
+
+    # ---------------- CPU baseline (rank 0, N=1 only, bounded sample) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        spo2 = 16
+        times, cores = run_oracle_sample(spo2, 1)
+        scale = float(1 << (po2 - spo2))
+        cpu_value = 1.0 / (times[0] * scale)
+        cpu = {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "oracle CPU restatement, %d threads: one W=256 segment of 2^%d cycles (%.2f s), scaled x%d linearly in cycles to po2=%d" % (cores, spo2, times[0], int(scale), po2)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "ms_per_step_device_events": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u32 (BabyBear mod p, Montgomery)", "data": "synthetic",
+                "config": {"workload": "configs[1]: single synthetic rv32im-shaped segment per GPU per step, po2=%d, W=256 (16 code + 192 data + 48 accum), circuit synth-rv32im-shape v1" % po2,
+                           "po2": po2, "segments_per_step": world, "parallelism": "segments sharded across %d GPU(s), no collectives" % world,
+                           "cache": "inputs (1 GiB trace, 4 GiB LDE) are larger than L2; no flush needed", "seal_words": seal_words,
+                           "camt53_segments": CAMT53_SEGMENTS, "camt53_proof_seconds": CAMT53_SEGMENTS / value},
+                "stages_ms_per_step": {k: v / args.steps for k, v in stage.items() if k.startswith("ms_")},
+                "roofline": roofline, "poseidon2": poseidon, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": launches_all, "clocks": clocks}
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -33,7 +33,7 @@ class CircuitDesc(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_ntt_main", C.c_float), ("ms_hash_main", C.c_float),
+    _fields_ = [("ms_total", C.c_float), ("ms_device", C.c_float), ("ms_h2d", C.c_float), ("ms_ntt_main", C.c_float), ("ms_hash_main", C.c_float),
                 ("ms_accum", C.c_float), ("ms_check", C.c_float), ("ms_deep", C.c_float), ("ms_fri", C.c_float),
                 ("launches", C.c_uint64), ("ntt_main_bytes", C.c_uint64)]
 
@@ -200,6 +200,20 @@ class Context:
             except Hfb200Error:
                 pass
         return out
+
+    def host_alloc(self, shape):
+        """Pinned host memory (cudaHostAlloc) viewed as a uint32 numpy array; freed with host_free(arr)."""
+        n = int(np.prod(shape))
+        p = C.c_void_p()
+        self._check(self.lib.hfb200_host_alloc(n * 4, C.byref(p)))
+        arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(n,)).reshape(shape)
+        self._pinned = getattr(self, "_pinned", {})
+        self._pinned[arr.ctypes.data] = p
+        return arr
+
+    def host_free(self, arr):
+        p = self._pinned.pop(arr.ctypes.data)
+        self.lib.hfb200_host_free(p)
 
     def last_stats(self):
         s = Stats()

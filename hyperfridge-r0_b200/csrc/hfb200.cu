@@ -143,7 +143,7 @@ const char* hfb200_last_stats(hfb200_ctx* ctx, hfb200_stats* out) {
     API_TRY
     if (!ctx || !out) throw Err("hfb200_last_stats: NULL argument");
     const Stats& s = ctx->p.stats;
-    out->ms_total = s.ms_total; out->ms_h2d = s.ms_h2d; out->ms_ntt_main = s.ms_ntt_main; out->ms_hash_main = s.ms_hash_main;
+    out->ms_total = s.ms_total; out->ms_device = s.ms_device; out->ms_h2d = s.ms_h2d; out->ms_ntt_main = s.ms_ntt_main; out->ms_hash_main = s.ms_hash_main;
     out->ms_accum = s.ms_accum; out->ms_check = s.ms_check; out->ms_deep = s.ms_deep; out->ms_fri = s.ms_fri;
     out->launches = s.launches; out->ntt_main_bytes = s.ntt_main_bytes;
     API_CATCH

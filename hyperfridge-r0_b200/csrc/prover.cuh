@@ -39,7 +39,7 @@ struct Arena {
 };
 
 struct Stats {
-    float ms_total = 0, ms_h2d = 0, ms_ntt_main = 0, ms_hash_main = 0, ms_accum = 0, ms_check = 0, ms_deep = 0, ms_fri = 0;
+    float ms_total = 0, ms_device = 0, ms_h2d = 0, ms_ntt_main = 0, ms_hash_main = 0, ms_accum = 0, ms_check = 0, ms_deep = 0, ms_fri = 0;
     uint64_t launches = 0, ntt_main_bytes = 0;
 };
 
@@ -434,6 +434,7 @@ struct Prover {
         stage_ms[6] = between(10, 11);
         stats.ms_h2d = stage_ms[0]; stats.ms_ntt_main = stage_ms[1]; stats.ms_hash_main = stage_ms[2]; stats.ms_accum = stage_ms[3];
         stats.ms_check = stage_ms[4]; stats.ms_deep = stage_ms[5]; stats.ms_fri = stage_ms[6];
+        stats.ms_device = between(0, 11);
         stats.ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
         stats.launches = dev.launches - launches_at_begin;
         stats.ntt_main_bytes = 28ull * W * N;

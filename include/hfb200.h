@@ -88,7 +88,8 @@ const char* hfb200_checkpoint(hfb200_ctx* ctx, const char* name, uint32_t* out, 
 
 /* ---- measurement ------------------------------------------------------------------------------ */
 typedef struct {
-    float ms_total;        /* whole segment, first kernel to seal bytes on host (CUDA events + host waits) */
+    float ms_total;        /* whole segment, host wall clock from entry to seal bytes on host                 */
+    float ms_device;       /* CUDA-event time, first enqueue to last kernel, on the context's stream          */
     float ms_h2d;          /* host->device trace copies (0 for resident)                                  */
     float ms_ntt_main;     /* iNTT+zk_shift and expand+NTT (LDE) of code+data+accum columns               */
     float ms_hash_main;    /* Poseidon2 leaf hashing + tree folds of code+data+accum                      */

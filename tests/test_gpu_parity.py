@@ -1,0 +1,155 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle (bit-exact: all
+arithmetic on this path is integer mod p) and, at BASELINE.json's full size (po2 = 20), through size-independent
+properties (verifier acceptance, linearity of the LDE, determinism, seal-length model)."""
+import json
+import os
+import numpy as np
+import pytest
+from conftest import SMALL, DEFAULT, TRACE_SEED, make_segment, rand_elems
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = 2013265921
+
+
+@pytest.fixture(scope="module")
+def ctx(pkg, gpu_lib):
+    c = pkg.Context(0, 16, DEFAULT, lib=gpu_lib)
+    assert "sm_100a" in c.version
+    yield c
+    c.close()
+
+
+def test_poseidon2_permutation(ctx, orc):
+    st = rand_elems(np.random.default_rng(0), (1000, 24))
+    st[0] = 0
+    got = ctx.op_poseidon2(st)
+    exp = np.stack([orc.poseidon2_mix(s) for s in st])
+    assert (got == exp).all()
+
+
+@pytest.mark.parametrize("lg", [1, 4, 10, 11, 12, 14, 16, 18, 20])
+def test_ntt_ops(ctx, orc, lg):
+    ncols = 3 if lg < 20 else 2
+    x = rand_elems(np.random.default_rng(lg), (ncols, 1 << lg))
+    x[0, :] = np.uint32(P - 1)  # extreme values
+    coeffs = orc.interpolate_ntt(x)
+    shifted = orc.zk_shift(coeffs)
+    assert (ctx.op_interpolate_ntt(x, False) == coeffs).all()
+    assert (ctx.op_interpolate_ntt(x, True) == shifted).all()
+    assert (ctx.op_expand_ntt(x, 2) == orc.expand_ntt(x, 2)).all()
+    assert (ctx.op_expand_ntt(x, 0) == orc.expand_ntt(x, 0)).all()
+    assert (ctx.op_lde(x) == orc.expand_ntt(shifted, 2)).all()
+
+
+def test_ntt_size_22_inverse(ctx, orc):
+    # the check polynomial of a po2 = 20 segment is interpolated over 2^22 points
+    x = rand_elems(np.random.default_rng(22), (1, 1 << 22))
+    assert (ctx.op_interpolate_ntt(x, False) == orc.interpolate_ntt(x)).all()
+
+
+@pytest.mark.parametrize("rows,cols", [(2, 1), (16, 3), (64, 16), (1024, 17), (4096, 64), (1 << 16, 48), (1 << 14, 272)])
+def test_merkle(ctx, orc, rows, cols):
+    m = rand_elems(np.random.default_rng(rows + cols), (cols, rows))
+    _, nodes = orc.merkle(m, True)
+    assert (ctx.op_merkle(m)[1:] == nodes[1:]).all()
+
+
+def test_fri_fold_matches_definition(ctx, orc):
+    rng = np.random.default_rng(7)
+    n = 1 << 12
+    x = rand_elems(rng, (4, n))
+    mix = rand_elems(rng, 4)
+    got = ctx.op_fri_fold(x, mix)
+    # definition on natural-order coefficients: out_m = sum_i mix^i c[16 m + i]; buffers are bit-reversed
+    L = orc.lib()
+
+    def e4mul(a, b):
+        out = np.zeros(4, np.uint32)
+        a = np.ascontiguousarray(a, np.uint32); b = np.ascontiguousarray(b, np.uint32)
+        L.orc_fp4_mul(a.ctypes.data, b.ctypes.data, out.ctypes.data)
+        return out
+    nat = orc.bit_reverse(x)
+    outnat = orc.bit_reverse(got)
+    one = np.array([orc.encode([1])[0], 0, 0, 0], np.uint32)
+    for m in (0, 1, 17, n // 16 - 1):
+        tot = np.zeros(4, np.uint64)
+        cur = one
+        for i in range(16):
+            tot = (tot + e4mul(cur, nat[:, 16 * m + i]).astype(np.uint64)) % P
+            cur = e4mul(cur, mix)
+        assert (outnat[:, m] == tot.astype(np.uint32)).all()
+
+
+@pytest.mark.parametrize("widths,po2", [(SMALL, 12), (SMALL, 13), (DEFAULT, 12), (DEFAULT, 14), (DEFAULT, 16)])
+def test_segment_seal_bit_exact(pkg, gpu_lib, orc, widths, po2, monkeypatch):
+    monkeypatch.setenv("HFB200_DEBUG_CHECKPOINTS", "1")
+    cir, g, code, data = make_segment(orc, widths, po2)
+    oseal, ocps, _ = cir.prove(po2, g, code, data, 1)
+    with pkg.Context(0, po2, widths, lib=gpu_lib) as c:
+        assert (c.witgen_synth(po2, TRACE_SEED, 1) == g).all()
+        assert (c.read_group(1) == code).all() and (c.read_group(2) == data).all()
+        seal_res = c.prove_resident(1)                      # inputs resident in HBM
+        cps = c.checkpoints()
+        for k, v in ocps.items():
+            assert (cps[k] == v).all(), "checkpoint %s differs" % k
+        assert len(seal_res) == c.seal_words(po2) == len(oseal)
+        assert (seal_res == oseal).all()
+        assert (c.read_group(0) == cir.step_accum(po2, data, ocps["accum_mix"], 1)).all()
+        seal_host = c.prove_segment(po2, g, code, data, 1)  # host buffers through the C ABI
+        assert (seal_host == oseal).all()
+        mix = c.segment_begin(po2, g, code, data, 1)        # two-phase, external accum
+        assert (mix == ocps["accum_mix"]).all()
+        assert (c.segment_finish(cir.step_accum(po2, data, mix, 1)) == oseal).all()
+        assert cir.verify(seal_res, ocps["code_root"]) == po2
+        st = c.last_stats()
+        assert st["launches"] > 20 and st["ms_total"] > 0
+
+
+def test_golden_fixture(pkg, gpu_lib, monkeypatch):
+    monkeypatch.setenv("HFB200_DEBUG_CHECKPOINTS", "1")
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_small.json")))["segment"]
+    with pkg.Context(0, gold["po2"], tuple(gold["widths"]), lib=gpu_lib) as c:
+        c.witgen_synth(gold["po2"], gold["trace_seed"], gold["blind_seed"])
+        seal = c.prove_resident(gold["blind_seed"])
+        assert len(seal) == gold["seal_words"]
+        cps = c.checkpoints()
+        for k, v in gold["checkpoints"].items():
+            assert cps[k].tolist() == v, k
+
+
+def test_tampered_gpu_seal_rejected(pkg, gpu_lib, orc):
+    with pkg.Context(0, 12, SMALL, lib=gpu_lib) as c:
+        c.witgen_synth(12, TRACE_SEED, 1)
+        seal = c.prove_resident(1)
+        cir = orc.Circuit(*SMALL)
+        cid = cir.control_id(12)
+        assert cir.verify(seal, cid) == 12
+        for pos in (3, 40, len(seal) // 2, len(seal) - 5):
+            bad = seal.copy(); bad[pos] ^= 1
+            with pytest.raises(RuntimeError):
+                cir.verify(bad, cid)
+
+
+def test_full_size_po2_20_properties(pkg, gpu_lib, orc):
+    """BASELINE.json's full size: too slow for a seal-vs-oracle comparison (the oracle needs minutes), so check
+    size-independent properties instead."""
+    po2 = 20
+    with pkg.Context(0, po2, DEFAULT, lib=gpu_lib) as c:
+        c.witgen_synth(po2, TRACE_SEED, 1)
+        seal = c.prove_resident(1)
+        cir = orc.Circuit(*DEFAULT)
+        assert len(seal) == c.seal_words(po2) == cir.seal_words_model(po2)
+        assert (c.prove_resident(1) == seal).all()            # deterministic
+        assert cir.verify(seal, c.checkpoint("code_root")) == po2  # the independent verifier accepts
+        assert (cir.control_id(po2) == c.checkpoint("code_root")).all()
+        # linearity of the fused trace -> LDE pipeline, and LDE of a constant column
+        rng = np.random.default_rng(20)
+        x = rand_elems(rng, (2, 1 << po2))
+        s = ((x[0].astype(np.uint64) + x[1]) % P).astype(np.uint32)
+        const = np.full(1 << po2, 12345, np.uint32)
+        out = c.op_lde(np.stack([x[0], x[1], s, const]))
+        assert (((out[0].astype(np.uint64) + out[1]) % P).astype(np.uint32) == out[2]).all()
+        assert (out[3] == 12345).all()
+        # inverse o forward round trip at 2^20
+        assert (c.op_expand_ntt(c.op_interpolate_ntt(x, False), 0) == x).all()
