@@ -249,8 +249,8 @@ struct Prover {
         if (accum_h) dev.h2d(tr[GROUP_ACCUM], accum_h, (size_t)cd.w_accum * N * 4);
         else step_accum();
         mark(6);
+        commit_group(GROUP_ACCUM, "accum_root", 6, 7, 8);  // ends with a stream sync: events 5..8 are complete
         stage_ms[3] = between(5, 6);
-        commit_group(GROUP_ACCUM, "accum_root", 6, 7, 8);
         stage_ms[1] += between(6, 7);
         stage_ms[2] += between(7, 8);
 
