@@ -20,14 +20,43 @@
 namespace hf {
 
 struct KCtx {
-    int tid, nt;            // thread index / threads per block
+    int tid, nt;              // thread index / threads per block (or per unit, see unit_ctx)
     unsigned bx, by, gx, gy;  // block index / grid size
+    int bar_id = 0;           // 0: whole-CTA barrier; k > 0: named barrier k over `nt` threads (a "unit")
     HD void sync() const {
 #ifdef __CUDA_ARCH__
-        __syncthreads();
+        if (bar_id) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nt) : "memory");
+        else __syncthreads();
 #endif
     }
 };
+
+// A CTA may be split into independent "units" of UT threads (each with its own named barrier) that work on
+// different columns but share per-CTA tables.  Device: unit = tid / UT, one pass.  Emulator (nt = 1): the units
+// are simply visited one after the other.
+HD int unit_first(const KCtx& cx, int UT) {
+#ifdef __CUDA_ARCH__
+    return cx.tid / UT;
+#else
+    (void)cx; (void)UT; return 0;
+#endif
+}
+HD int unit_step(const KCtx& cx, int UT) {
+#ifdef __CUDA_ARCH__
+    return cx.nt / UT;
+#else
+    (void)cx; (void)UT; return 1;
+#endif
+}
+HD KCtx unit_ctx(const KCtx& cx, int unit, int UT) {
+#ifdef __CUDA_ARCH__
+    KCtx u{cx.tid % UT, UT, cx.bx, cx.by, cx.gx, cx.gy, unit + 1};
+#else
+    (void)unit; (void)UT;
+    KCtx u{0, 1, cx.bx, cx.by, cx.gx, cx.gy, 0};
+#endif
+    return u;
+}
 
 struct Err : std::runtime_error { using std::runtime_error::runtime_error; };
 

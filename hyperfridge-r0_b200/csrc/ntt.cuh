@@ -86,8 +86,7 @@ HD void ntt_round_dyn(const KCtx& cx, uint32_t* s, const uint32_t* tw, int k, in
         case 1: ntt_round<1, INV>(cx, s, tw, k, c, l0); break;
         case 2: ntt_round<2, INV>(cx, s, tw, k, c, l0); break;
         case 3: ntt_round<3, INV>(cx, s, tw, k, c, l0); break;
-        case 4: ntt_round<4, INV>(cx, s, tw, k, c, l0); break;
-        default: ntt_round<5, INV>(cx, s, tw, k, c, l0); break;
+        default: ntt_round<4, INV>(cx, s, tw, k, c, l0); break;
     }
 }
 
@@ -210,61 +209,326 @@ struct MiddleKernel {
     }
 };
 
-struct StrArgs {
-    const uint32_t* in;
-    uint32_t* out;                   // may alias `in`
-    uint64_t in_stride, out_stride;  // column strides (words)
-    uint32_t ncols;
-    int a, b, c;  // rows hi < 2^b at stride 2^a words; tile = 2^b x 2^c
-    int inv, rmax;
-    RootTables rt;
+// =====================================================================================================
+// v2 kernels: the first round of every stage reads straight from global memory into registers and the last
+// round writes straight back (no staging pass, many loads in flight per thread), at most 16 values per
+// thread, and the chunk-stage CTA is split into 64-thread units that share the per-chunk twiddle tables.
+// =====================================================================================================
+struct SmemIO {
+    uint32_t* s; int c;
+    HD uint32_t ld(uint32_t pos, uint32_t batch) const { return s[padi((pos << c) + batch)]; }
+    HD void st(uint32_t pos, uint32_t batch, uint32_t v) const { s[padi((pos << c) + batch)] = v; }
+};
+struct GlobStridedIO {  // element (pos, batch) of a strided tile: row pos at stride 2^a words, column batch
+    const uint32_t* src; uint32_t* dst; int a;
+    HD uint32_t ld(uint32_t pos, uint32_t batch) const { return src[((uint64_t)pos << a) + batch]; }
+    HD void st(uint32_t pos, uint32_t batch, uint32_t v) const { dst[((uint64_t)pos << a) + batch] = v; }
 };
 
-// grid.x = any (grid-stride over ncols * 2^(a-c) tiles).
-struct StridedKernel {
+template <int R, bool INV, typename LD, typename ST>
+HD void round_io(const KCtx& cx, const uint32_t* tw, int k, int c, int l0, const LD& L, const ST& S) {
+    const uint32_t items = 1u << (k - R + c);
+    const uint32_t cmask = (1u << c) - 1u, lmask = (1u << l0) - 1u;
+    for (uint32_t it = cx.tid; it < items; it += cx.nt) {
+        const uint32_t batch = it & cmask, t = it >> c;
+        const uint32_t low = t & lmask, high = t >> l0;
+        const uint32_t base = (high << (l0 + R)) | low;
+        uint32_t v[1 << R];
+#pragma unroll
+        for (int j = 0; j < (1 << R); j++) v[j] = L.ld(base + ((uint32_t)j << l0), batch);
+        if (!INV) {
+#pragma unroll
+            for (int q = 1; q <= R; q++) {
+                const int h = 1 << (q - 1);
+#pragma unroll
+                for (int j = 0; j < (1 << R); j++) {
+                    if (j & h) continue;
+                    const uint32_t w = tw[(low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q)];
+                    const uint32_t x = fmul(v[j + h], w);
+                    v[j + h] = fsub(v[j], x);
+                    v[j] = fadd(v[j], x);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = R; q >= 1; q--) {
+                const int h = 1 << (q - 1);
+#pragma unroll
+                for (int j = 0; j < (1 << R); j++) {
+                    if (j & h) continue;
+                    const uint32_t w = tw[(low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q)];
+                    const uint32_t a = v[j], b = v[j + h];
+                    v[j] = fadd(a, b);
+                    v[j + h] = fmul(fsub(a, b), w);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < (1 << R); j++) S.st(base + ((uint32_t)j << l0), batch, v[j]);
+    }
+}
+template <bool INV, typename LD, typename ST>
+HD void round_io_dyn(const KCtx& cx, const uint32_t* tw, int k, int c, int l0, int R, const LD& L, const ST& S) {
+    switch (R) {
+        case 1: round_io<1, INV>(cx, tw, k, c, l0, L, S); break;
+        case 2: round_io<2, INV>(cx, tw, k, c, l0, L, S); break;
+        case 3: round_io<3, INV>(cx, tw, k, c, l0, L, S); break;
+        default: round_io<4, INV>(cx, tw, k, c, l0, L, S); break;
+    }
+}
+
+struct Str2Args {
+    const uint32_t* in;
+    uint32_t* out;                   // may alias `in`
+    uint64_t in_stride, out_stride;
+    uint32_t ncols;
+    int a, b, c, inv;
+    int nr, R[4];
+    RootTables rt;
+};
+struct StridedKernel2 {
     static constexpr bool kBarrier = true;
-    HD static void run(const KCtx& cx, uint32_t* sm, StrArgs p) {
+    template <bool INV>
+    HD static void tile(const KCtx& cx, const Str2Args& p, uint32_t* s, const uint32_t* tw, const uint32_t* src, uint32_t* dst) {
+        const GlobStridedIO G{src, dst, p.a};
+        const SmemIO S{s, p.c};
+        int done = 0;
+        for (int r = 0; r < p.nr; r++) {
+            const int R = p.R[r];
+            const int l0 = INV ? (p.b - done - R) : done;
+            const bool first = r == 0, last = r == p.nr - 1;
+            if (first && last) round_io_dyn<INV>(cx, tw, p.b, p.c, l0, R, G, G);
+            else if (first) round_io_dyn<INV>(cx, tw, p.b, p.c, l0, R, G, S);
+            else if (last) round_io_dyn<INV>(cx, tw, p.b, p.c, l0, R, S, G);
+            else round_io_dyn<INV>(cx, tw, p.b, p.c, l0, R, S, S);
+            if (!last) cx.sync();
+            done += R;
+        }
+        if (p.nr > 1) cx.sync();  // the tile buffer is reused by the next tile
+    }
+    HD static void run(const KCtx& cx, uint32_t* sm, Str2Args p) {
         uint32_t* s = sm;
         uint32_t* tw = sm + padded_words(1u << (p.b + p.c));
-        const uint32_t half = p.b > 0 ? 1u << (p.b - 1) : 1u;
+        const uint32_t half = 1u << (p.b - 1);
         for (uint32_t i = cx.tid; i < half; i += cx.nt)
             tw[i] = p.inv ? tab_pow(p.rt.i_lo, p.rt.i_hi, i << (24 - p.b)) : tab_pow(p.rt.f_lo, p.rt.f_hi, i << (24 - p.b));
         cx.sync();
         const uint32_t tiles_per_col = 1u << (p.a - p.c);
         const uint64_t total = (uint64_t)p.ncols * tiles_per_col;
-        const uint32_t cmask = (1u << p.c) - 1u;
-        for (uint64_t tile = cx.bx; tile < total; tile += cx.gx) {
-            const uint32_t col = (uint32_t)(tile >> (p.a - p.c));
-            const uint32_t lo0 = ((uint32_t)tile & (tiles_per_col - 1u)) << p.c;
+        for (uint64_t t = cx.bx; t < total; t += cx.gx) {
+            const uint32_t col = (uint32_t)(t >> (p.a - p.c));
+            const uint32_t lo0 = ((uint32_t)t & (tiles_per_col - 1u)) << p.c;
             const uint32_t* src = p.in + (uint64_t)col * p.in_stride + lo0;
             uint32_t* dst = p.out + (uint64_t)col * p.out_stride + lo0;
-            if (p.c >= 2) {
-                const uint32_t n4 = 1u << (p.b + p.c - 2), c4 = p.c - 2, m4 = (1u << c4) - 1u;
-                for (uint32_t i4 = cx.tid; i4 < n4; i4 += cx.nt) {
-                    const uint32_t h = i4 >> c4, l = (i4 & m4) << 2;
-                    const uint4 v = *reinterpret_cast<const uint4*>(src + ((uint64_t)h << p.a) + l);
-                    const uint32_t o = (h << p.c) + l;
-                    s[padi(o)] = v.x; s[padi(o + 1)] = v.y; s[padi(o + 2)] = v.z; s[padi(o + 3)] = v.w;
+            if (p.inv) tile<true>(cx, p, s, tw, src, dst); else tile<false>(cx, p, s, tw, src, dst);
+        }
+    }
+};
+
+static constexpr int MID_UT = 64;  // threads per unit of the chunk-stage kernel
+
+struct Mid2Args {
+    const uint32_t* in;
+    uint32_t* out;
+    uint64_t in_stride, out_stride;
+    uint32_t ncols, cols_per_block;
+    int n, a, b, e;
+    uint32_t flags;
+    uint32_t n_inv;
+    int units, alias;
+    int nri, Ri[4];  // inverse rounds, top level first; the last one (RF levels) runs in registers
+    int nrf, Rf[4];  // forward rounds; the first one (RF levels) runs in registers, fused with the inverse tail
+    RootTables rt;
+};
+struct Mid2Layout {
+    uint32_t twI, twF, G3, Gs, G2, unit0, unit_words, A, B, total;
+    HD Mid2Layout(const Mid2Args& p) {
+        uint32_t o = 0;
+        const bool intt = p.flags & MID_INTT, fwd = p.flags & MID_FWD, fly = p.flags & MID_GFLY;
+        twI = o; if (intt) o += (p.a > 0 ? 1u << (p.a - 1) : 1u);
+        twF = o; if (fwd) o += 1u << (p.a + p.e - 1);
+        G3 = o; if (intt && p.b > 0 && !fly) o += 1u << p.a;
+        Gs = o; if (intt && !fly) o += 1u << p.a;
+        G2 = o; if (fwd && p.b > 0 && !fly) o += 1u << (p.a + p.e);
+        unit0 = o;
+        uint32_t u = 0;
+        A = u; if (intt && !(fwd && p.alias)) u += padded_words(1u << p.a);
+        B = u; if (fwd) u += padded_words(1u << (p.a + p.e));
+        unit_words = u;
+        total = o + u * (uint32_t)p.units;
+    }
+};
+
+struct MiddleKernel2 {
+    static constexpr bool kBarrier = true;
+    HD static uint32_t g3(const Mid2Args& p, uint32_t rb, uint32_t i) { return tab_pow(p.rt.i_lo, p.rt.i_hi, (rb * i) << (24 - p.n)); }
+    HD static uint32_t gs(const Mid2Args& p, uint32_t rb, uint32_t i) {
+        uint32_t g = p.n_inv;
+        if (p.flags & MID_SHIFT) g = fmul(g, tab_pow(p.rt.p3_lo, p.rt.p3_hi, (brev(i, p.a) << p.b) + rb));
+        return g;
+    }
+    HD static uint32_t g2(const Mid2Args& p, uint32_t rb, uint32_t i) { return tab_pow(p.rt.f_lo, p.rt.f_hi, (rb * i) << (24 - p.n - p.e)); }
+
+    struct SrcIO {  // chunk element from global, times the inter-stage twiddle w^-(rev(hi) lo)
+        const uint32_t* src; const uint32_t* G3; const uint32_t *lo, *hi; uint32_t rb; int shift; int mode;  // 0 none, 1 table, 2 fly
+        HD uint32_t ld(uint32_t pos, uint32_t) const {
+            uint32_t v = src[pos];
+            if (mode == 1) v = fmul(v, G3[pos]); else if (mode == 2) v = fmul(v, tab_pow(lo, hi, (rb * pos) << shift));
+            return v;
+        }
+        HD void st(uint32_t, uint32_t, uint32_t) const {}
+    };
+    struct DstIO {  // LDE chunk element to global, times the inter-stage twiddle w^(rev(hi) lo')
+        uint32_t* dst; const uint32_t* G2; const uint32_t *lo, *hi; uint32_t rb; int shift; int mode;
+        HD uint32_t ld(uint32_t, uint32_t) const { return 0; }
+        HD void st(uint32_t pos, uint32_t, uint32_t v) const {
+            if (mode == 1) v = fmul(v, G2[pos]); else if (mode == 2) v = fmul(v, tab_pow(lo, hi, (rb * pos) << shift));
+            dst[pos] = v;
+        }
+    };
+
+    // The register-resident tail of the inverse transform (last RF levels, scale by n^-1 3^j) fused with the
+    // register-resident head of the forward transform (replicate x 2^e, first RF levels) for one item of 2^RF
+    // consecutive coefficients.
+    template <int RF>
+    HD static void tail_load(uint32_t* v, uint32_t base, bool from_global, const SrcIO& G, const uint32_t* A) {
+#pragma unroll
+        for (int j = 0; j < (1 << RF); j++) v[j] = from_global ? G.ld(base + j, 0) : A[padi(base + j)];
+    }
+    template <int RF>
+    HD static void tail_compute_store(uint32_t* v, uint32_t base, const Mid2Args& p, uint32_t rb, const uint32_t* twI, const uint32_t* twF,
+                                      const uint32_t* Gs, uint32_t* B, uint32_t* dst_coef, const DstIO& D) {
+        const bool intt = p.flags & MID_INTT, fwd = p.flags & MID_FWD, fly = p.flags & MID_GFLY;
+        if (intt) {
+#pragma unroll
+            for (int q = RF; q >= 1; q--) {
+                const int h = 1 << (q - 1);
+#pragma unroll
+                for (int j = 0; j < (1 << RF); j++) {
+                    if (j & h) continue;
+                    const uint32_t w = twI[(uint32_t)(j & (h - 1)) << (p.a - q)];
+                    const uint32_t a = v[j], b = v[j + h];
+                    v[j] = fadd(a, b);
+                    v[j + h] = fmul(fsub(a, b), w);
                 }
-            } else {
-                for (uint32_t i = cx.tid; i < (1u << (p.b + p.c)); i += cx.nt) s[padi(i)] = src[((uint64_t)(i >> p.c) << p.a) + (i & cmask)];
             }
-            cx.sync();
-            if (p.inv) ntt_tile<true>(cx, s, tw, p.b, p.c, 0, p.rmax);
-            else ntt_tile<false>(cx, s, tw, p.b, p.c, 0, p.rmax);
-            if (p.c >= 2) {
-                const uint32_t n4 = 1u << (p.b + p.c - 2), c4 = p.c - 2, m4 = (1u << c4) - 1u;
-                for (uint32_t i4 = cx.tid; i4 < n4; i4 += cx.nt) {
-                    const uint32_t h = i4 >> c4, l = (i4 & m4) << 2;
-                    const uint32_t o = (h << p.c) + l;
-                    uint4 v;
-                    v.x = s[padi(o)]; v.y = s[padi(o + 1)]; v.z = s[padi(o + 2)]; v.w = s[padi(o + 3)];
-                    *reinterpret_cast<uint4*>(dst + ((uint64_t)h << p.a) + l) = v;
+#pragma unroll
+            for (int j = 0; j < (1 << RF); j++) v[j] = fmul(v[j], fly ? gs(p, rb, base + j) : Gs[base + j]);
+        }
+        if (!fwd) {
+#pragma unroll
+            for (int j = 0; j < (1 << RF); j++) dst_coef[base + j] = v[j];
+            return;
+        }
+        const int kf = p.a + p.e;
+        for (uint32_t r = 0; r < (1u << p.e); r++) {
+            uint32_t w[1 << RF];
+#pragma unroll
+            for (int j = 0; j < (1 << RF); j++) w[j] = v[j];
+#pragma unroll
+            for (int q = 1; q <= RF; q++) {
+                const int h = 1 << (q - 1);
+#pragma unroll
+                for (int j = 0; j < (1 << RF); j++) {
+                    if (j & h) continue;
+                    const uint32_t t = twF[(r + ((uint32_t)(j & (h - 1)) << p.e)) << (kf - p.e - q)];
+                    const uint32_t x = fmul(w[j + h], t);
+                    w[j + h] = fsub(w[j], x);
+                    w[j] = fadd(w[j], x);
                 }
-            } else {
-                for (uint32_t i = cx.tid; i < (1u << (p.b + p.c)); i += cx.nt) dst[((uint64_t)(i >> p.c) << p.a) + (i & cmask)] = s[padi(i)];
             }
-            cx.sync();
+            if (p.nrf > 1) {
+#pragma unroll
+                for (int j = 0; j < (1 << RF); j++) B[padi(((base + j) << p.e) + r)] = w[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < (1 << RF); j++) D.st(((base + j) << p.e) + r, 0, w[j]);
+            }
+        }
+    }
+    template <int RF>
+    HD static void tail(const KCtx& ux, const Mid2Args& p, uint32_t rb, bool from_global, const SrcIO& G, const uint32_t* A, const uint32_t* twI,
+                        const uint32_t* twF, const uint32_t* Gs, uint32_t* B, uint32_t* dst_coef, const DstIO& D) {
+        const uint32_t items = 1u << (p.a - RF);
+        if (p.alias && (p.flags & MID_INTT) && (p.flags & MID_FWD)) {
+            // A aliases B: every thread owns at most one item; all loads complete before any store
+            uint32_t v[1 << RF];
+            const uint32_t it = ux.tid;
+            if (it < items) tail_load<RF>(v, it << RF, from_global, G, A);
+            ux.sync();
+            if (it < items) tail_compute_store<RF>(v, it << RF, p, rb, twI, twF, Gs, B, dst_coef, D);
+        } else {
+            for (uint32_t it = ux.tid; it < items; it += ux.nt) {
+                uint32_t v[1 << RF];
+                tail_load<RF>(v, it << RF, from_global, G, A);
+                tail_compute_store<RF>(v, it << RF, p, rb, twI, twF, Gs, B, dst_coef, D);
+            }
+        }
+    }
+
+    HD static void run(const KCtx& cx, uint32_t* sm, Mid2Args p) {
+        const Mid2Layout L(p);
+        const bool intt = p.flags & MID_INTT, fwd = p.flags & MID_FWD, fly = p.flags & MID_GFLY;
+        const uint32_t hi = cx.bx, rb = brev(hi, p.b);
+        const uint32_t na = 1u << p.a, nf = 1u << (p.a + p.e);
+        uint32_t *twI = sm + L.twI, *twF = sm + L.twF, *G3 = sm + L.G3, *Gs = sm + L.Gs, *G2 = sm + L.G2;
+        if (intt) {
+            for (uint32_t i = cx.tid; i < (na >> 1); i += cx.nt) twI[i] = tab_pow(p.rt.i_lo, p.rt.i_hi, i << (24 - p.a));
+            if (!fly) {
+                if (p.b > 0) for (uint32_t i = cx.tid; i < na; i += cx.nt) G3[i] = g3(p, rb, i);
+                for (uint32_t i = cx.tid; i < na; i += cx.nt) Gs[i] = gs(p, rb, i);
+            }
+        }
+        if (fwd) {
+            for (uint32_t i = cx.tid; i < (nf >> 1); i += cx.nt) twF[i] = tab_pow(p.rt.f_lo, p.rt.f_hi, i << (24 - p.a - p.e));
+            if (!fly && p.b > 0) for (uint32_t i = cx.tid; i < nf; i += cx.nt) G2[i] = g2(p, rb, i);
+        }
+        cx.sync();
+        const int gmode = p.b == 0 ? 0 : (fly ? 2 : 1);
+        const int RF = intt ? p.Ri[p.nri - 1] : p.Rf[0];
+        const uint32_t col_end = (cx.by + 1) * p.cols_per_block < p.ncols ? (cx.by + 1) * p.cols_per_block : p.ncols;
+        for (int u = unit_first(cx, MID_UT); u < p.units; u += unit_step(cx, MID_UT)) {
+            const KCtx ux = unit_ctx(cx, u, MID_UT);
+            uint32_t* ubase = sm + L.unit0 + (uint32_t)u * L.unit_words;
+            uint32_t* B = ubase + L.B;
+            uint32_t* A = (fwd && p.alias) ? B : ubase + L.A;
+            for (uint32_t col = cx.by * p.cols_per_block + (uint32_t)u; col < col_end; col += (uint32_t)p.units) {
+                const SrcIO G{p.in + (uint64_t)col * p.in_stride + ((uint64_t)hi << p.a), G3, p.rt.i_lo, p.rt.i_hi, rb, 24 - p.n, intt ? gmode : 0};
+                const DstIO D{p.out + (uint64_t)col * p.out_stride + ((uint64_t)hi << (p.a + p.e)), G2, p.rt.f_lo, p.rt.f_hi, rb, 24 - p.n - p.e, gmode};
+                uint32_t* dst_coef = p.out + (uint64_t)col * p.out_stride + ((uint64_t)hi << p.a);
+                const SmemIO SA{A, 0}, SB{B, 0};
+                bool from_global = true;
+                if (intt) {
+                    int done = 0;
+                    for (int r = 0; r + 1 < p.nri; r++) {
+                        const int R = p.Ri[r], l0 = p.a - done - R;
+                        if (r == 0) round_io_dyn<true>(ux, twI, p.a, 0, l0, R, G, SA);
+                        else round_io_dyn<true>(ux, twI, p.a, 0, l0, R, SA, SA);
+                        ux.sync();
+                        done += R;
+                        from_global = false;
+                    }
+                }
+                switch (RF) {
+                    case 1: tail<1>(ux, p, rb, from_global, G, A, twI, twF, Gs, B, dst_coef, D); break;
+                    case 2: tail<2>(ux, p, rb, from_global, G, A, twI, twF, Gs, B, dst_coef, D); break;
+                    case 3: tail<3>(ux, p, rb, from_global, G, A, twI, twF, Gs, B, dst_coef, D); break;
+                    default: tail<4>(ux, p, rb, from_global, G, A, twI, twF, Gs, B, dst_coef, D); break;
+                }
+                if (fwd && p.nrf > 1) {
+                    ux.sync();
+                    int done = RF;
+                    for (int r = 1; r < p.nrf; r++) {
+                        const int R = p.Rf[r], l0 = p.e + done;
+                        const bool last = r == p.nrf - 1;
+                        if (last) round_io_dyn<false>(ux, twF, p.a + p.e, 0, l0, R, SB, D);
+                        else round_io_dyn<false>(ux, twF, p.a + p.e, 0, l0, R, SB, SB);
+                        if (!last) ux.sync();
+                        done += R;
+                    }
+                }
+                ux.sync();  // unit buffers are reused by the next column
+            }
         }
     }
 };
@@ -326,29 +590,76 @@ struct Ntt {
         return r < 2 ? 2 : (r > 5 ? 5 : r);
     }
 
+    // rounds of <= 4 levels, as even as possible
+    static int split_rounds(int L, int* R) {
+        if (L <= 0) return 0;
+        const int nr = (L + 3) / 4;
+        for (int r = 0; r < nr; r++) R[r] = L / nr + (r < L % nr ? 1 : 0);
+        return nr;
+    }
+
     void strided(const uint32_t* in, uint64_t in_stride, uint32_t* out, uint64_t out_stride, uint32_t ncols, int a, int b, int c, bool inv) {
         if (b == 0) { if (in != out) throw Err("ntt: strided pass with b = 0 must be in place"); return; }
-        StrArgs p{in, out, in_stride, out_stride, ncols, a, b, c, inv ? 1 : 0, pick_rmax(b, c, str_threads), rt};
-        if (p.rmax > b) p.rmax = b;
-        const size_t smem = (size_t)(padded_words(1u << (b + c)) + (1u << (b > 0 ? b - 1 : 0))) * 4;
+        Str2Args p{};
+        p.in = in; p.out = out; p.in_stride = in_stride; p.out_stride = out_stride; p.ncols = ncols;
+        p.a = a; p.b = b; p.c = c; p.inv = inv ? 1 : 0; p.rt = rt;
+        p.nr = split_rounds(b, p.R);
+        const size_t smem = (size_t)(padded_words(1u << (b + c)) + (1u << (b - 1))) * 4;
         const uint64_t tiles = (uint64_t)ncols << (a - c);
-        const unsigned ctas_per_sm = (unsigned)(200 * 1024 / (smem + 1024)) ? (unsigned)(200 * 1024 / (smem + 1024)) : 1u;
-        uint64_t grid = (uint64_t)dev->sm_count * (ctas_per_sm > 8 ? 8 : ctas_per_sm);
+        unsigned per_sm = (unsigned)((220 * 1024) / (smem + 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 4) per_sm = 4;
+        uint64_t grid = (uint64_t)dev->sm_count * per_sm;
         if (grid > tiles) grid = tiles;
-        dev->launch<StridedKernel, 256, 1>((unsigned)grid, 1, str_threads > 256 ? 256 : str_threads, smem, p);
+        dev->launch<StridedKernel2, 256, 2>((unsigned)grid, 1, 256, smem, p);
     }
 
     void middle(const uint32_t* in, uint64_t in_stride, uint32_t* out, uint64_t out_stride, uint32_t ncols, int n, int a, int e, uint32_t flags) {
+        if (a < 5) { middle_small(in, in_stride, out, out_stride, ncols, n, a, e, flags); return; }
+        Mid2Args p{};
+        p.in = in; p.out = out; p.in_stride = in_stride; p.out_stride = out_stride; p.ncols = ncols;
+        p.n = n; p.a = a; p.b = n - a; p.e = e; p.flags = flags;
+        if (a + e > 12) p.flags |= MID_GFLY;
+        p.n_inv = finv(to_mont((uint32_t)((1ull << n) % P)));
+        p.rt = rt;
+        const bool intt = flags & MID_INTT, fwd = flags & MID_FWD;
+        const int RF = a < 4 ? a : 4;
+        if (intt) { p.nri = split_rounds(a - RF, p.Ri); p.Ri[p.nri++] = RF; }
+        if (fwd) { p.Rf[0] = RF; p.nrf = 1 + split_rounds(a - RF, p.Rf + 1); }
+        // A may alias B when every thread of a unit owns at most one register-tail item
+#ifdef HFB200_EMU
+        p.alias = 0;
+#else
+        p.alias = (intt && fwd && (1 << (a - RF)) <= MID_UT) ? 1 : 0;
+#endif
+        const size_t budget = 100 * 1024;  // two CTAs per SM
+        int units = 4;
+        for (;; units >>= 1) {
+            p.units = units;
+            if ((size_t)Mid2Layout(p).total * 4 <= budget || units == 1) break;
+        }
+        const uint64_t chunks = 1ull << p.b;
+        uint32_t groups = (uint32_t)((2ull * dev->sm_count + chunks - 1) / chunks);
+        if (groups < 1) groups = 1;
+        uint32_t max_groups = (ncols + (uint32_t)p.units - 1) / (uint32_t)p.units;
+        if (groups > max_groups) groups = max_groups;
+        p.cols_per_block = (ncols + groups - 1) / groups;
+        groups = (ncols + p.cols_per_block - 1) / p.cols_per_block;
+        dev->launch<MiddleKernel2, 256, 2>((unsigned)chunks, groups, p.units * MID_UT, (size_t)Mid2Layout(p).total * 4, p);
+    }
+
+    void middle_small(const uint32_t* in, uint64_t in_stride, uint32_t* out, uint64_t out_stride, uint32_t ncols, int n, int a, int e, uint32_t flags) {
         MidArgs p{};
         p.in = in; p.out = out; p.in_stride = in_stride; p.out_stride = out_stride; p.ncols = ncols;
         p.n = n; p.a = a; p.b = n - a; p.e = e; p.flags = flags;
         if (a + e > 12) p.flags |= MID_GFLY;
-        const int threads = mid_threads > 256 ? 256 : mid_threads;
+        const int threads = 64;
         p.rmax_inv = pick_rmax(a, 0, threads); if (p.rmax_inv > a) p.rmax_inv = a > 0 ? a : 1;
         p.rmax_fwd = pick_rmax(a + e, 0, threads); if (p.rmax_fwd > a) p.rmax_fwd = a > 0 ? a : 1;
+        if (p.rmax_inv > 4) p.rmax_inv = 4;
+        if (p.rmax_fwd > 4) p.rmax_fwd = 4;
         p.n_inv = finv(to_mont((uint32_t)((1ull << n) % P)));
         p.rt = rt;
-        // enough column groups to fill the machine ~4x, but keep per-CTA table setup amortised
         const uint64_t chunks = 1ull << p.b;
         uint32_t groups = (uint32_t)((4ull * dev->sm_count + chunks - 1) / chunks);
         if (groups < 1) groups = 1;
@@ -356,7 +667,7 @@ struct Ntt {
         p.cols_per_block = (ncols + groups - 1) / groups;
         groups = (ncols + p.cols_per_block - 1) / p.cols_per_block;
         const MidLayout L(p);
-        dev->launch<MiddleKernel, 256, 1>((unsigned)chunks, groups, threads, (size_t)L.total * 4, p);
+        dev->launch<MiddleKernel, 64, 1>((unsigned)chunks, groups, threads, (size_t)L.total * 4, p);
     }
 
     // Hal::batch_interpolate_ntt (+ zk_shift): natural evaluations -> bit-reversed coefficients.
