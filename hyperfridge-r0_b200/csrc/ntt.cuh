@@ -214,28 +214,51 @@ struct MiddleKernel {
 // round writes straight back (no staging pass, many loads in flight per thread), at most 16 values per
 // thread, and the chunk-stage CTA is split into 64-thread units that share the per-chunk twiddle tables.
 // =====================================================================================================
+// IO functors of a radix round.  An element is addressed either by (pos, batch) or, when the round's stride maps
+// to a constant index step ("affine"), by base index + j * step -- with compile-time sizes the steps become
+// immediate offsets of the load/store instructions.
 struct SmemIO {
-    uint32_t* s; int c;
-    HD uint32_t ld(uint32_t pos, uint32_t batch) const { return s[padi((pos << c) + batch)]; }
-    HD void st(uint32_t pos, uint32_t batch, uint32_t v) const { s[padi((pos << c) + batch)] = v; }
+    uint32_t* s;
+    HD uint32_t base(uint32_t pos, uint32_t batch, int c) const { return padi((pos << c) + batch); }
+    HD uint32_t step(int l0, int c) const { const uint32_t S = 1u << (l0 + c); return S + (S >> 5); }
+    HD bool affine(int l0, int c) const { return l0 + c >= 5; }
+    HD uint32_t ld_i(uint32_t i) const { return s[i]; }
+    HD void st_i(uint32_t i, uint32_t v) const { s[i] = v; }
 };
+template <int A>
 struct GlobStridedIO {  // element (pos, batch) of a strided tile: row pos at stride 2^a words, column batch
-    const uint32_t* src; uint32_t* dst; int a;
-    HD uint32_t ld(uint32_t pos, uint32_t batch) const { return src[((uint64_t)pos << a) + batch]; }
-    HD void st(uint32_t pos, uint32_t batch, uint32_t v) const { dst[((uint64_t)pos << a) + batch] = v; }
+    const uint32_t* src; uint32_t* dst; int a_;
+    HD int a() const { return A >= 0 ? A : a_; }
+    HD uint32_t base(uint32_t pos, uint32_t batch, int) const { return (pos << a()) + batch; }
+    HD uint32_t step(int l0, int) const { return 1u << (l0 + a()); }
+    HD bool affine(int, int) const { return true; }
+    HD uint32_t ld_i(uint32_t i) const { return src[i]; }
+    HD void st_i(uint32_t i, uint32_t v) const { dst[i] = v; }
 };
 
-template <int R, bool INV, typename LD, typename ST>
-HD void round_io(const KCtx& cx, const uint32_t* tw, int k, int c, int l0, const LD& L, const ST& S) {
+// One radix-2^R round over levels l0+1..l0+R of a [2^k][2^c] tile.  K, C, L0 >= 0 fix the sizes at compile time
+// (-1 = runtime).  With L0 == 0 the twiddle exponents are compile-time and the unit twiddles (15 of the 32
+// butterflies of a radix-16 round) are skipped.
+template <int R, bool INV, int K, int C, int L0, typename LD, typename ST>
+HD void round_t(const KCtx& cx, const uint32_t* tw, int k_, int c_, int l0_, const LD& L, const ST& S) {
+    const int k = K >= 0 ? K : k_, c = C >= 0 ? C : c_, l0 = L0 >= 0 ? L0 : l0_;
     const uint32_t items = 1u << (k - R + c);
     const uint32_t cmask = (1u << c) - 1u, lmask = (1u << l0) - 1u;
+    const bool laff = L.affine(l0, c), saff = S.affine(l0, c);
+    const uint32_t lstep = L.step(l0, c), sstep = S.step(l0, c);
     for (uint32_t it = cx.tid; it < items; it += cx.nt) {
         const uint32_t batch = it & cmask, t = it >> c;
         const uint32_t low = t & lmask, high = t >> l0;
         const uint32_t base = (high << (l0 + R)) | low;
         uint32_t v[1 << R];
+        if (laff) {
+            const uint32_t i0 = L.base(base, batch, c);
 #pragma unroll
-        for (int j = 0; j < (1 << R); j++) v[j] = L.ld(base + ((uint32_t)j << l0), batch);
+            for (int j = 0; j < (1 << R); j++) v[j] = L.ld_i(i0 + (uint32_t)j * lstep);
+        } else {
+#pragma unroll
+            for (int j = 0; j < (1 << R); j++) v[j] = L.ld_i(L.base(base + ((uint32_t)j << l0), batch, c));
+        }
         if (!INV) {
 #pragma unroll
             for (int q = 1; q <= R; q++) {
@@ -243,8 +266,8 @@ HD void round_io(const KCtx& cx, const uint32_t* tw, int k, int c, int l0, const
 #pragma unroll
                 for (int j = 0; j < (1 << R); j++) {
                     if (j & h) continue;
-                    const uint32_t w = tw[(low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q)];
-                    const uint32_t x = fmul(v[j + h], w);
+                    uint32_t x = v[j + h];
+                    if (!(L0 == 0 && (j & (h - 1)) == 0)) x = fmul(x, tw[(low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q)]);
                     v[j + h] = fsub(v[j], x);
                     v[j] = fadd(v[j], x);
                 }
@@ -256,24 +279,31 @@ HD void round_io(const KCtx& cx, const uint32_t* tw, int k, int c, int l0, const
 #pragma unroll
                 for (int j = 0; j < (1 << R); j++) {
                     if (j & h) continue;
-                    const uint32_t w = tw[(low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q)];
                     const uint32_t a = v[j], b = v[j + h];
                     v[j] = fadd(a, b);
-                    v[j + h] = fmul(fsub(a, b), w);
+                    uint32_t d = fsub(a, b);
+                    if (!(L0 == 0 && (j & (h - 1)) == 0)) d = fmul(d, tw[(low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q)]);
+                    v[j + h] = d;
                 }
             }
         }
+        if (saff) {
+            const uint32_t i0 = S.base(base, batch, c);
 #pragma unroll
-        for (int j = 0; j < (1 << R); j++) S.st(base + ((uint32_t)j << l0), batch, v[j]);
+            for (int j = 0; j < (1 << R); j++) S.st_i(i0 + (uint32_t)j * sstep, v[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < (1 << R); j++) S.st_i(S.base(base + ((uint32_t)j << l0), batch, c), v[j]);
+        }
     }
 }
 template <bool INV, typename LD, typename ST>
 HD void round_io_dyn(const KCtx& cx, const uint32_t* tw, int k, int c, int l0, int R, const LD& L, const ST& S) {
     switch (R) {
-        case 1: round_io<1, INV>(cx, tw, k, c, l0, L, S); break;
-        case 2: round_io<2, INV>(cx, tw, k, c, l0, L, S); break;
-        case 3: round_io<3, INV>(cx, tw, k, c, l0, L, S); break;
-        default: round_io<4, INV>(cx, tw, k, c, l0, L, S); break;
+        case 1: round_t<1, INV, -1, -1, -1>(cx, tw, k, c, l0, L, S); break;
+        case 2: round_t<2, INV, -1, -1, -1>(cx, tw, k, c, l0, L, S); break;
+        case 3: round_t<3, INV, -1, -1, -1>(cx, tw, k, c, l0, L, S); break;
+        default: round_t<4, INV, -1, -1, -1>(cx, tw, k, c, l0, L, S); break;
     }
 }
 
@@ -286,12 +316,28 @@ struct Str2Args {
     int nr, R[4];
     RootTables rt;
 };
+// SB/SC/SA >= 0: sizes fixed at compile time (hot po2 configurations); -1: generic.
+template <int SB, int SC, int SA>
 struct StridedKernel2 {
     static constexpr bool kBarrier = true;
     template <bool INV>
     HD static void tile(const KCtx& cx, const Str2Args& p, uint32_t* s, const uint32_t* tw, const uint32_t* src, uint32_t* dst) {
-        const GlobStridedIO G{src, dst, p.a};
-        const SmemIO S{s, p.c};
+        const GlobStridedIO<SA> G{src, dst, p.a};
+        const SmemIO S{s};
+        if constexpr (SB >= 6) {
+            // fixed schedule: SB = R0 + R1 + R2 with R0 = 4 on the global-facing first round
+            constexpr int R0 = 4, R1 = (SB - 4 + 1) / 2, R2 = SB - 4 - R1;
+            if (INV) {
+                round_t<R0, true, SB, SC, SB - R0>(cx, tw, SB, SC, SB - R0, G, S); cx.sync();
+                round_t<R1, true, SB, SC, R2>(cx, tw, SB, SC, R2, S, S); cx.sync();
+                round_t<(R2 > 0 ? R2 : 1), true, SB, SC, 0>(cx, tw, SB, SC, 0, S, G);
+            } else {
+                round_t<R0, false, SB, SC, 0>(cx, tw, SB, SC, 0, G, S); cx.sync();
+                round_t<R1, false, SB, SC, R0>(cx, tw, SB, SC, R0, S, S); cx.sync();
+                round_t<(R2 > 0 ? R2 : 1), false, SB, SC, R0 + R1>(cx, tw, SB, SC, R0 + R1, S, G);
+            }
+            cx.sync();
+        } else {
         int done = 0;
         for (int r = 0; r < p.nr; r++) {
             const int R = p.R[r];
@@ -305,6 +351,7 @@ struct StridedKernel2 {
             done += R;
         }
         if (p.nr > 1) cx.sync();  // the tile buffer is reused by the next tile
+        }
     }
     HD static void run(const KCtx& cx, uint32_t* sm, Str2Args p) {
         uint32_t* s = sm;
@@ -359,8 +406,12 @@ struct Mid2Layout {
     }
 };
 
+// MA/ME >= 0: chunk size / expand bits fixed at compile time (the main-group configuration a = 10, e = 2).
+template <int MA, int ME>
 struct MiddleKernel2 {
     static constexpr bool kBarrier = true;
+    HD static int A_(const Mid2Args& p) { return MA >= 0 ? MA : p.a; }
+    HD static int E_(const Mid2Args& p) { return ME >= 0 ? ME : p.e; }
     HD static uint32_t g3(const Mid2Args& p, uint32_t rb, uint32_t i) { return tab_pow(p.rt.i_lo, p.rt.i_hi, (rb * i) << (24 - p.n)); }
     HD static uint32_t gs(const Mid2Args& p, uint32_t rb, uint32_t i) {
         uint32_t g = p.n_inv;
@@ -371,17 +422,23 @@ struct MiddleKernel2 {
 
     struct SrcIO {  // chunk element from global, times the inter-stage twiddle w^-(rev(hi) lo)
         const uint32_t* src; const uint32_t* G3; const uint32_t *lo, *hi; uint32_t rb; int shift; int mode;  // 0 none, 1 table, 2 fly
-        HD uint32_t ld(uint32_t pos, uint32_t) const {
+        HD uint32_t base(uint32_t pos, uint32_t, int) const { return pos; }
+        HD uint32_t step(int l0, int) const { return 1u << l0; }
+        HD bool affine(int, int) const { return true; }
+        HD uint32_t ld_i(uint32_t pos) const {
             uint32_t v = src[pos];
             if (mode == 1) v = fmul(v, G3[pos]); else if (mode == 2) v = fmul(v, tab_pow(lo, hi, (rb * pos) << shift));
             return v;
         }
-        HD void st(uint32_t, uint32_t, uint32_t) const {}
+        HD void st_i(uint32_t, uint32_t) const {}
     };
     struct DstIO {  // LDE chunk element to global, times the inter-stage twiddle w^(rev(hi) lo')
         uint32_t* dst; const uint32_t* G2; const uint32_t *lo, *hi; uint32_t rb; int shift; int mode;
-        HD uint32_t ld(uint32_t, uint32_t) const { return 0; }
-        HD void st(uint32_t pos, uint32_t, uint32_t v) const {
+        HD uint32_t base(uint32_t pos, uint32_t, int) const { return pos; }
+        HD uint32_t step(int l0, int) const { return 1u << l0; }
+        HD bool affine(int, int) const { return true; }
+        HD uint32_t ld_i(uint32_t) const { return 0; }
+        HD void st_i(uint32_t pos, uint32_t v) const {
             if (mode == 1) v = fmul(v, G2[pos]); else if (mode == 2) v = fmul(v, tab_pow(lo, hi, (rb * pos) << shift));
             dst[pos] = v;
         }
@@ -393,7 +450,7 @@ struct MiddleKernel2 {
     template <int RF>
     HD static void tail_load(uint32_t* v, uint32_t base, bool from_global, const SrcIO& G, const uint32_t* A) {
 #pragma unroll
-        for (int j = 0; j < (1 << RF); j++) v[j] = from_global ? G.ld(base + j, 0) : A[padi(base + j)];
+        for (int j = 0; j < (1 << RF); j++) v[j] = from_global ? G.ld_i(base + j) : A[padi(base + j)];
     }
     template <int RF>
     HD static void tail_compute_store(uint32_t* v, uint32_t base, const Mid2Args& p, uint32_t rb, const uint32_t* twI, const uint32_t* twF,
@@ -406,10 +463,11 @@ struct MiddleKernel2 {
 #pragma unroll
                 for (int j = 0; j < (1 << RF); j++) {
                     if (j & h) continue;
-                    const uint32_t w = twI[(uint32_t)(j & (h - 1)) << (p.a - q)];
                     const uint32_t a = v[j], b = v[j + h];
                     v[j] = fadd(a, b);
-                    v[j + h] = fmul(fsub(a, b), w);
+                    uint32_t d = fsub(a, b);
+                    if ((j & (h - 1)) != 0) d = fmul(d, twI[(uint32_t)(j & (h - 1)) << (A_(p) - q)]);
+                    v[j + h] = d;
                 }
             }
 #pragma unroll
@@ -420,36 +478,40 @@ struct MiddleKernel2 {
             for (int j = 0; j < (1 << RF); j++) dst_coef[base + j] = v[j];
             return;
         }
-        const int kf = p.a + p.e;
-        for (uint32_t r = 0; r < (1u << p.e); r++) {
-            uint32_t w[1 << RF];
+        head<RF, true>(v, base, 0, p, twF, B, D);
+        for (uint32_t r = 1; r < (1u << E_(p)); r++) head<RF, false>(v, base, r, p, twF, B, D);
+    }
+    // forward head for coset r: first RF levels of the x 2^e expanded chunk (levels e+1 .. e+RF)
+    template <int RF, bool RZ>
+    HD static void head(const uint32_t* v, uint32_t base, uint32_t r, const Mid2Args& p, const uint32_t* twF, uint32_t* B, const DstIO& D) {
+        const int e = E_(p), kf = A_(p) + e;
+        uint32_t w[1 << RF];
 #pragma unroll
-            for (int j = 0; j < (1 << RF); j++) w[j] = v[j];
+        for (int j = 0; j < (1 << RF); j++) w[j] = v[j];
 #pragma unroll
-            for (int q = 1; q <= RF; q++) {
-                const int h = 1 << (q - 1);
+        for (int q = 1; q <= RF; q++) {
+            const int h = 1 << (q - 1);
 #pragma unroll
-                for (int j = 0; j < (1 << RF); j++) {
-                    if (j & h) continue;
-                    const uint32_t t = twF[(r + ((uint32_t)(j & (h - 1)) << p.e)) << (kf - p.e - q)];
-                    const uint32_t x = fmul(w[j + h], t);
-                    w[j + h] = fsub(w[j], x);
-                    w[j] = fadd(w[j], x);
-                }
+            for (int j = 0; j < (1 << RF); j++) {
+                if (j & h) continue;
+                uint32_t x = w[j + h];
+                if (!(RZ && (j & (h - 1)) == 0)) x = fmul(x, twF[(r + ((uint32_t)(j & (h - 1)) << e)) << (kf - e - q)]);
+                w[j + h] = fsub(w[j], x);
+                w[j] = fadd(w[j], x);
             }
-            if (p.nrf > 1) {
+        }
+        if (p.nrf > 1) {
 #pragma unroll
-                for (int j = 0; j < (1 << RF); j++) B[padi(((base + j) << p.e) + r)] = w[j];
-            } else {
+            for (int j = 0; j < (1 << RF); j++) B[padi(((base + j) << e) + r)] = w[j];
+        } else {
 #pragma unroll
-                for (int j = 0; j < (1 << RF); j++) D.st(((base + j) << p.e) + r, 0, w[j]);
-            }
+            for (int j = 0; j < (1 << RF); j++) D.st_i(((base + j) << e) + r, w[j]);
         }
     }
     template <int RF>
     HD static void tail(const KCtx& ux, const Mid2Args& p, uint32_t rb, bool from_global, const SrcIO& G, const uint32_t* A, const uint32_t* twI,
                         const uint32_t* twF, const uint32_t* Gs, uint32_t* B, uint32_t* dst_coef, const DstIO& D) {
-        const uint32_t items = 1u << (p.a - RF);
+        const uint32_t items = 1u << (A_(p) - RF);
         if (p.alias && (p.flags & MID_INTT) && (p.flags & MID_FWD)) {
             // A aliases B: every thread owns at most one item; all loads complete before any store
             uint32_t v[1 << RF];
@@ -496,7 +558,15 @@ struct MiddleKernel2 {
                 const SrcIO G{p.in + (uint64_t)col * p.in_stride + ((uint64_t)hi << p.a), G3, p.rt.i_lo, p.rt.i_hi, rb, 24 - p.n, intt ? gmode : 0};
                 const DstIO D{p.out + (uint64_t)col * p.out_stride + ((uint64_t)hi << (p.a + p.e)), G2, p.rt.f_lo, p.rt.f_hi, rb, 24 - p.n - p.e, gmode};
                 uint32_t* dst_coef = p.out + (uint64_t)col * p.out_stride + ((uint64_t)hi << p.a);
-                const SmemIO SA{A, 0}, SB{B, 0};
+                const SmemIO SA{A}, SB{B};
+                if constexpr (MA == 10 && ME == 2) {  // host dispatches this instantiation only for the fused iNTT+LDE
+                    // main-group schedule, all sizes compile-time: DIF 3+3 (+4 in registers), DIT (4 in registers +) 3+3
+                    round_t<3, true, 10, 0, 7>(ux, twI, 10, 0, 7, G, SA); ux.sync();
+                    round_t<3, true, 10, 0, 4>(ux, twI, 10, 0, 4, SA, SA); ux.sync();
+                    tail<4>(ux, p, rb, false, G, A, twI, twF, Gs, B, dst_coef, D); ux.sync();
+                    round_t<3, false, 12, 0, 6>(ux, twF, 12, 0, 6, SB, SB); ux.sync();
+                    round_t<3, false, 12, 0, 9>(ux, twF, 12, 0, 9, SB, D);
+                } else {
                 bool from_global = true;
                 if (intt) {
                     int done = 0;
@@ -526,6 +596,7 @@ struct MiddleKernel2 {
                         if (!last) ux.sync();
                         done += R;
                     }
+                }
                 }
                 ux.sync();  // unit buffers are reused by the next column
             }
@@ -611,7 +682,16 @@ struct Ntt {
         if (per_sm > 4) per_sm = 4;
         uint64_t grid = (uint64_t)dev->sm_count * per_sm;
         if (grid > tiles) grid = tiles;
-        dev->launch<StridedKernel2, 256, 2>((unsigned)grid, 1, 256, smem, p);
+        const int key = b * 10000 + c * 100 + a;
+        switch (key) {
+            case 100410: dev->launch<StridedKernel2<10, 4, 10>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
+            case 100412: dev->launch<StridedKernel2<10, 4, 12>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
+            case 80510: dev->launch<StridedKernel2<8, 5, 10>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
+            case 80512: dev->launch<StridedKernel2<8, 5, 12>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
+            case 60510: dev->launch<StridedKernel2<6, 5, 10>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
+            case 60512: dev->launch<StridedKernel2<6, 5, 12>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
+            default: dev->launch<StridedKernel2<-1, -1, -1>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
+        }
     }
 
     void middle(const uint32_t* in, uint64_t in_stride, uint32_t* out, uint64_t out_stride, uint32_t ncols, int n, int a, int e, uint32_t flags) {
@@ -645,7 +725,8 @@ struct Ntt {
         if (groups > max_groups) groups = max_groups;
         p.cols_per_block = (ncols + groups - 1) / groups;
         groups = (ncols + p.cols_per_block - 1) / p.cols_per_block;
-        dev->launch<MiddleKernel2, 256, 2>((unsigned)chunks, groups, p.units * MID_UT, (size_t)Mid2Layout(p).total * 4, p);
+        if (a == 10 && e == 2 && intt && fwd) dev->launch<MiddleKernel2<10, 2>, 256, 2>((unsigned)chunks, groups, p.units * MID_UT, (size_t)Mid2Layout(p).total * 4, p);
+        else dev->launch<MiddleKernel2<-1, -1>, 256, 2>((unsigned)chunks, groups, p.units * MID_UT, (size_t)Mid2Layout(p).total * 4, p);
     }
 
     void middle_small(const uint32_t* in, uint64_t in_stride, uint32_t* out, uint64_t out_stride, uint32_t ncols, int n, int a, int e, uint32_t flags) {

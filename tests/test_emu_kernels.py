@@ -29,7 +29,7 @@ def test_poseidon2(ctx, orc):
     assert (ctx.op_poseidon2(st) == np.stack([orc.poseidon2_mix(s) for s in st])).all()
 
 
-@pytest.mark.parametrize("lg", [1, 2, 5, 10, 11, 12, 14])
+@pytest.mark.parametrize("lg", [1, 2, 5, 10, 11, 12, 14, 16, 18])
 def test_ntt_ops(ctx, orc, lg):
     x = rand_elems(np.random.default_rng(lg), (3, 1 << lg))
     coeffs = orc.interpolate_ntt(x)
