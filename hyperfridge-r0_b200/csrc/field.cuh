@@ -94,6 +94,13 @@ HD E4 e4_inv(const E4& a) {
     return r;
 }
 
+HD int clz32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
 HD uint32_t brev(uint32_t x, unsigned bits) {
 #ifdef __CUDA_ARCH__
     return bits == 0 ? 0u : (__brev(x) >> (32 - bits));

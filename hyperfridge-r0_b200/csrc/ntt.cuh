@@ -217,14 +217,18 @@ struct MiddleKernel {
 // IO functors of a radix round.  An element is addressed either by (pos, batch) or, when the round's stride maps
 // to a constant index step ("affine"), by base index + j * step -- with compile-time sizes the steps become
 // immediate offsets of the load/store instructions.
-struct SmemIO {
+template <int PS>
+HD uint32_t padx(uint32_t i) { return i + (i >> PS); }
+template <int PS = 5>
+struct SmemIOT {  // one pad word per 2^PS
     uint32_t* s;
-    HD uint32_t base(uint32_t pos, uint32_t batch, int c) const { return padi((pos << c) + batch); }
-    HD uint32_t step(int l0, int c) const { const uint32_t S = 1u << (l0 + c); return S + (S >> 5); }
-    HD bool affine(int l0, int c) const { return l0 + c >= 5; }
+    HD uint32_t base(uint32_t pos, uint32_t batch, int c) const { return padx<PS>((pos << c) + batch); }
+    HD uint32_t step(int l0, int c) const { const uint32_t S = 1u << (l0 + c); return S + (S >> PS); }
+    HD bool affine(int l0, int c) const { return l0 + c >= PS; }
     HD uint32_t ld_i(uint32_t i) const { return s[i]; }
     HD void st_i(uint32_t i, uint32_t v) const { s[i] = v; }
 };
+using SmemIO = SmemIOT<5>;
 template <int A>
 struct GlobStridedIO {  // element (pos, batch) of a strided tile: row pos at stride 2^a words, column batch
     const uint32_t* src; uint32_t* dst; int a_;
@@ -239,7 +243,10 @@ struct GlobStridedIO {  // element (pos, batch) of a strided tile: row pos at st
 // One radix-2^R round over levels l0+1..l0+R of a [2^k][2^c] tile.  K, C, L0 >= 0 fix the sizes at compile time
 // (-1 = runtime).  With L0 == 0 the twiddle exponents are compile-time and the unit twiddles (15 of the 32
 // butterflies of a radix-16 round) are skipped.
-template <int R, bool INV, int K, int C, int L0, typename LD, typename ST>
+// TWL: twiddle table layout. false: tw[i] = w_{2^k}^i (i < 2^(k-1)), level l reads stride 2^(k-l);  true: per-level
+// blocks tw[2^(l-1) + x] = w_{2^l}^x, so consecutive lanes read consecutive words (no bank conflicts when c = 0).
+// HF: lanes enumerate `high` first (only for c = 0); keeps rounds with l0 < 5 off the same banks.
+template <int R, bool INV, int K, int C, int L0, bool TWL = false, bool HF = false, typename LD, typename ST>
 HD void round_t(const KCtx& cx, const uint32_t* tw, int k_, int c_, int l0_, const LD& L, const ST& S) {
     const int k = K >= 0 ? K : k_, c = C >= 0 ? C : c_, l0 = L0 >= 0 ? L0 : l0_;
     const uint32_t items = 1u << (k - R + c);
@@ -248,7 +255,8 @@ HD void round_t(const KCtx& cx, const uint32_t* tw, int k_, int c_, int l0_, con
     const uint32_t lstep = L.step(l0, c), sstep = S.step(l0, c);
     for (uint32_t it = cx.tid; it < items; it += cx.nt) {
         const uint32_t batch = it & cmask, t = it >> c;
-        const uint32_t low = t & lmask, high = t >> l0;
+        const uint32_t nhigh_mask = (items >> (l0 + c)) - 1u;
+        const uint32_t low = HF ? (t >> (k - R - l0)) : (t & lmask), high = HF ? (t & nhigh_mask) : (t >> l0);
         const uint32_t base = (high << (l0 + R)) | low;
         uint32_t v[1 << R];
         if (laff) {
@@ -267,7 +275,7 @@ HD void round_t(const KCtx& cx, const uint32_t* tw, int k_, int c_, int l0_, con
                 for (int j = 0; j < (1 << R); j++) {
                     if (j & h) continue;
                     uint32_t x = v[j + h];
-                    if (!(L0 == 0 && (j & (h - 1)) == 0)) x = fmul(x, tw[(low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q)]);
+                    if (!(L0 == 0 && (j & (h - 1)) == 0)) x = fmul(x, TWL ? tw[(1u << (l0 + q - 1)) + ((uint32_t)(j & (h - 1)) << l0) + low] : tw[(low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q)]);
                     v[j + h] = fsub(v[j], x);
                     v[j] = fadd(v[j], x);
                 }
@@ -282,7 +290,7 @@ HD void round_t(const KCtx& cx, const uint32_t* tw, int k_, int c_, int l0_, con
                     const uint32_t a = v[j], b = v[j + h];
                     v[j] = fadd(a, b);
                     uint32_t d = fsub(a, b);
-                    if (!(L0 == 0 && (j & (h - 1)) == 0)) d = fmul(d, tw[(low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q)]);
+                    if (!(L0 == 0 && (j & (h - 1)) == 0)) d = fmul(d, TWL ? tw[(1u << (l0 + q - 1)) + ((uint32_t)(j & (h - 1)) << l0) + low] : tw[(low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q)]);
                     v[j + h] = d;
                 }
             }
@@ -297,13 +305,13 @@ HD void round_t(const KCtx& cx, const uint32_t* tw, int k_, int c_, int l0_, con
         }
     }
 }
-template <bool INV, typename LD, typename ST>
+template <bool INV, bool TWL = false, typename LD, typename ST>
 HD void round_io_dyn(const KCtx& cx, const uint32_t* tw, int k, int c, int l0, int R, const LD& L, const ST& S) {
     switch (R) {
-        case 1: round_t<1, INV, -1, -1, -1>(cx, tw, k, c, l0, L, S); break;
-        case 2: round_t<2, INV, -1, -1, -1>(cx, tw, k, c, l0, L, S); break;
-        case 3: round_t<3, INV, -1, -1, -1>(cx, tw, k, c, l0, L, S); break;
-        default: round_t<4, INV, -1, -1, -1>(cx, tw, k, c, l0, L, S); break;
+        case 1: round_t<1, INV, -1, -1, -1, TWL>(cx, tw, k, c, l0, L, S); break;
+        case 2: round_t<2, INV, -1, -1, -1, TWL>(cx, tw, k, c, l0, L, S); break;
+        case 3: round_t<3, INV, -1, -1, -1, TWL>(cx, tw, k, c, l0, L, S); break;
+        default: round_t<4, INV, -1, -1, -1, TWL>(cx, tw, k, c, l0, L, S); break;
     }
 }
 
@@ -392,8 +400,8 @@ struct Mid2Layout {
     HD Mid2Layout(const Mid2Args& p) {
         uint32_t o = 0;
         const bool intt = p.flags & MID_INTT, fwd = p.flags & MID_FWD, fly = p.flags & MID_GFLY;
-        twI = o; if (intt) o += (p.a > 0 ? 1u << (p.a - 1) : 1u);
-        twF = o; if (fwd) o += 1u << (p.a + p.e - 1);
+        twI = o; if (intt) o += 1u << p.a;          // per-level layout: tw[2^(l-1) + x] = w_{2^l}^-x
+        twF = o; if (fwd) o += 1u << (p.a + p.e);
         G3 = o; if (intt && p.b > 0 && !fly) o += 1u << p.a;
         Gs = o; if (intt && !fly) o += 1u << p.a;
         G2 = o; if (fwd && p.b > 0 && !fly) o += 1u << (p.a + p.e);
@@ -410,6 +418,7 @@ struct Mid2Layout {
 template <int MA, int ME>
 struct MiddleKernel2 {
     static constexpr bool kBarrier = true;
+    static constexpr int PSB = (MA == 10 && ME == 2) ? 6 : 5;  // pad shift of the forward buffer B
     HD static int A_(const Mid2Args& p) { return MA >= 0 ? MA : p.a; }
     HD static int E_(const Mid2Args& p) { return ME >= 0 ? ME : p.e; }
     HD static uint32_t g3(const Mid2Args& p, uint32_t rb, uint32_t i) { return tab_pow(p.rt.i_lo, p.rt.i_hi, (rb * i) << (24 - p.n)); }
@@ -466,7 +475,7 @@ struct MiddleKernel2 {
                     const uint32_t a = v[j], b = v[j + h];
                     v[j] = fadd(a, b);
                     uint32_t d = fsub(a, b);
-                    if ((j & (h - 1)) != 0) d = fmul(d, twI[(uint32_t)(j & (h - 1)) << (A_(p) - q)]);
+                    if ((j & (h - 1)) != 0) d = fmul(d, twI[(1u << (q - 1)) + (uint32_t)(j & (h - 1))]);
                     v[j + h] = d;
                 }
             }
@@ -495,14 +504,14 @@ struct MiddleKernel2 {
             for (int j = 0; j < (1 << RF); j++) {
                 if (j & h) continue;
                 uint32_t x = w[j + h];
-                if (!(RZ && (j & (h - 1)) == 0)) x = fmul(x, twF[(r + ((uint32_t)(j & (h - 1)) << e)) << (kf - e - q)]);
+                if (!(RZ && (j & (h - 1)) == 0)) x = fmul(x, twF[(1u << (e + q - 1)) + ((uint32_t)(j & (h - 1)) << e) + r]);
                 w[j + h] = fsub(w[j], x);
                 w[j] = fadd(w[j], x);
             }
         }
         if (p.nrf > 1) {
 #pragma unroll
-            for (int j = 0; j < (1 << RF); j++) B[padi(((base + j) << e) + r)] = w[j];
+            for (int j = 0; j < (1 << RF); j++) B[padx<PSB>(((base + j) << e) + r)] = w[j];
         } else {
 #pragma unroll
             for (int j = 0; j < (1 << RF); j++) D.st_i(((base + j) << e) + r, w[j]);
@@ -535,14 +544,23 @@ struct MiddleKernel2 {
         const uint32_t na = 1u << p.a, nf = 1u << (p.a + p.e);
         uint32_t *twI = sm + L.twI, *twF = sm + L.twF, *G3 = sm + L.G3, *Gs = sm + L.Gs, *G2 = sm + L.G2;
         if (intt) {
-            for (uint32_t i = cx.tid; i < (na >> 1); i += cx.nt) twI[i] = tab_pow(p.rt.i_lo, p.rt.i_hi, i << (24 - p.a));
+            // per-level blocks: index i in [2^(l-1), 2^l) holds w_{2^l}^-(i - 2^(l-1))
+            for (uint32_t i = cx.tid; i < na; i += cx.nt) {
+                uint32_t v = ONE;
+                if (i >= 1) { const int l = 32 - clz32(i); v = tab_pow(p.rt.i_lo, p.rt.i_hi, (i - (1u << (l - 1))) << (24 - l)); }
+                twI[i] = v;
+            }
             if (!fly) {
                 if (p.b > 0) for (uint32_t i = cx.tid; i < na; i += cx.nt) G3[i] = g3(p, rb, i);
                 for (uint32_t i = cx.tid; i < na; i += cx.nt) Gs[i] = gs(p, rb, i);
             }
         }
         if (fwd) {
-            for (uint32_t i = cx.tid; i < (nf >> 1); i += cx.nt) twF[i] = tab_pow(p.rt.f_lo, p.rt.f_hi, i << (24 - p.a - p.e));
+            for (uint32_t i = cx.tid; i < nf; i += cx.nt) {
+                uint32_t v = ONE;
+                if (i >= 1) { const int l = 32 - clz32(i); v = tab_pow(p.rt.f_lo, p.rt.f_hi, (i - (1u << (l - 1))) << (24 - l)); }
+                twF[i] = v;
+            }
             if (!fly && p.b > 0) for (uint32_t i = cx.tid; i < nf; i += cx.nt) G2[i] = g2(p, rb, i);
         }
         cx.sync();
@@ -561,19 +579,20 @@ struct MiddleKernel2 {
                 const SmemIO SA{A}, SB{B};
                 if constexpr (MA == 10 && ME == 2) {  // host dispatches this instantiation only for the fused iNTT+LDE
                     // main-group schedule, all sizes compile-time: DIF 3+3 (+4 in registers), DIT (4 in registers +) 3+3
-                    round_t<3, true, 10, 0, 7>(ux, twI, 10, 0, 7, G, SA); ux.sync();
-                    round_t<3, true, 10, 0, 4>(ux, twI, 10, 0, 4, SA, SA); ux.sync();
+                    const SmemIOT<PSB> SB6{B};
+                    round_t<3, true, 10, 0, 7, true>(ux, twI, 10, 0, 7, G, SA); ux.sync();
+                    round_t<3, true, 10, 0, 4, true, true>(ux, twI, 10, 0, 4, SA, SA); ux.sync();
                     tail<4>(ux, p, rb, false, G, A, twI, twF, Gs, B, dst_coef, D); ux.sync();
-                    round_t<3, false, 12, 0, 6>(ux, twF, 12, 0, 6, SB, SB); ux.sync();
-                    round_t<3, false, 12, 0, 9>(ux, twF, 12, 0, 9, SB, D);
+                    round_t<3, false, 12, 0, 6, true>(ux, twF, 12, 0, 6, SB6, SB6); ux.sync();
+                    round_t<3, false, 12, 0, 9, true>(ux, twF, 12, 0, 9, SB6, D);
                 } else {
                 bool from_global = true;
                 if (intt) {
                     int done = 0;
                     for (int r = 0; r + 1 < p.nri; r++) {
                         const int R = p.Ri[r], l0 = p.a - done - R;
-                        if (r == 0) round_io_dyn<true>(ux, twI, p.a, 0, l0, R, G, SA);
-                        else round_io_dyn<true>(ux, twI, p.a, 0, l0, R, SA, SA);
+                        if (r == 0) round_io_dyn<true, true>(ux, twI, p.a, 0, l0, R, G, SA);
+                        else round_io_dyn<true, true>(ux, twI, p.a, 0, l0, R, SA, SA);
                         ux.sync();
                         done += R;
                         from_global = false;
@@ -591,8 +610,8 @@ struct MiddleKernel2 {
                     for (int r = 1; r < p.nrf; r++) {
                         const int R = p.Rf[r], l0 = p.e + done;
                         const bool last = r == p.nrf - 1;
-                        if (last) round_io_dyn<false>(ux, twF, p.a + p.e, 0, l0, R, SB, D);
-                        else round_io_dyn<false>(ux, twF, p.a + p.e, 0, l0, R, SB, SB);
+                        if (last) round_io_dyn<false, true>(ux, twF, p.a + p.e, 0, l0, R, SB, D);
+                        else round_io_dyn<false, true>(ux, twF, p.a + p.e, 0, l0, R, SB, SB);
                         if (!last) ux.sync();
                         done += R;
                     }
@@ -712,7 +731,7 @@ struct Ntt {
 #else
         p.alias = (intt && fwd && (1 << (a - RF)) <= MID_UT) ? 1 : 0;
 #endif
-        const size_t budget = 100 * 1024;  // two CTAs per SM
+        const size_t budget = 112 * 1024;  // two CTAs per SM
         int units = 4;
         for (;; units >>= 1) {
             p.units = units;
