@@ -41,6 +41,22 @@ HD const P2Consts& p2c() {
 #endif
 }
 
+// Pipe steering experiment (B200): 32-bit integer multiplies run only on the heavy half of the FMA pipe, the binding
+// unit of this kernel (ncu: sm__pipe_fmaheavy_cycles_active ~92 %).  ptxas splits plain adds between the ALU pipe
+// (IADD3) and the FMA pipe (IMAD.IADD).  P2_FADD_ALU=1 pins them to the ALU pipe by writing the add as VIADDMNMX
+// (min(a + b, UINT_MAX)); measured on B200 this is 3.7 % SLOWER (28.9 -> 30.0 ms for the 192-column tree), i.e. both
+// pipes are already saturated together, so the default stays 0.
+#ifndef P2_FADD_ALU
+#define P2_FADD_ALU 0
+#endif
+HD uint32_t padd(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__) && P2_FADD_ALU
+    const uint32_t x = __viaddmin_u32(a, b, 0xFFFFFFFFu);
+    return __viaddmin_u32(x, 0u - P, x);
+#else
+    return fadd(a, b);
+#endif
+}
 HD uint32_t sbox7(uint32_t x) { uint32_t x2 = fmul(x, x), x3 = fmul(x2, x), x4 = fmul(x2, x2); return fmul(x3, x4); }
 
 // External layer: M4 on each 4-chunk (Poseidon2 add/double chain) then add the cross-chunk column sums.
@@ -48,25 +64,25 @@ HD void p2_m_ext(uint32_t* s) {
 #pragma unroll
     for (int c = 0; c < 24; c += 4) {
         uint32_t a = s[c], b = s[c + 1], cc = s[c + 2], d = s[c + 3];
-        uint32_t t0 = fadd(a, b), t1 = fadd(cc, d);
-        uint32_t t2 = fadd(fadd(b, b), t1), t3 = fadd(fadd(d, d), t0);
-        uint32_t t4 = fadd(t1, t1); t4 = fadd(fadd(t4, t4), t3);
-        uint32_t t5 = fadd(t0, t0); t5 = fadd(fadd(t5, t5), t2);
-        s[c] = fadd(t3, t5); s[c + 1] = t5; s[c + 2] = fadd(t2, t4); s[c + 3] = t4;
+        uint32_t t0 = padd(a, b), t1 = padd(cc, d);
+        uint32_t t2 = padd(padd(b, b), t1), t3 = padd(padd(d, d), t0);
+        uint32_t t4 = padd(t1, t1); t4 = padd(padd(t4, t4), t3);
+        uint32_t t5 = padd(t0, t0); t5 = padd(padd(t5, t5), t2);
+        s[c] = padd(t3, t5); s[c + 1] = t5; s[c + 2] = padd(t2, t4); s[c + 3] = t4;
     }
     uint32_t sum[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) sum[j] = fadd(fadd(fadd(s[j], s[4 + j]), fadd(s[8 + j], s[12 + j])), fadd(s[16 + j], s[20 + j]));
+    for (int j = 0; j < 4; j++) sum[j] = padd(padd(padd(s[j], s[4 + j]), padd(s[8 + j], s[12 + j])), padd(s[16 + j], s[20 + j]));
 #pragma unroll
-    for (int i = 0; i < 24; i++) s[i] = fadd(s[i], sum[i & 3]);
+    for (int i = 0; i < 24; i++) s[i] = padd(s[i], sum[i & 3]);
 }
 
 HD void p2_m_int(uint32_t* s, const P2Consts& k) {
     uint32_t sum = 0;
 #pragma unroll
-    for (int i = 0; i < 24; i++) sum = fadd(sum, s[i]);
+    for (int i = 0; i < 24; i++) sum = padd(sum, s[i]);
 #pragma unroll
-    for (int i = 0; i < 24; i++) s[i] = fadd(sum, fmul(k.diag[i], s[i]));
+    for (int i = 0; i < 24; i++) s[i] = padd(sum, fmul(k.diag[i], s[i]));
 }
 
 HD void p2_mix(uint32_t* s) {
@@ -75,18 +91,18 @@ HD void p2_mix(uint32_t* s) {
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
 #pragma unroll
-        for (int i = 0; i < 24; i++) s[i] = sbox7(fadd(s[i], k.rc_first[r * 24 + i]));
+        for (int i = 0; i < 24; i++) s[i] = sbox7(padd(s[i], k.rc_first[r * 24 + i]));
         p2_m_ext(s);
     }
 #pragma unroll 1
     for (int r = 0; r < 21; r++) {
-        s[0] = sbox7(fadd(s[0], k.rc_partial[r]));
+        s[0] = sbox7(padd(s[0], k.rc_partial[r]));
         p2_m_int(s, k);
     }
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
 #pragma unroll
-        for (int i = 0; i < 24; i++) s[i] = sbox7(fadd(s[i], k.rc_last[r * 24 + i]));
+        for (int i = 0; i < 24; i++) s[i] = sbox7(padd(s[i], k.rc_last[r * 24 + i]));
         p2_m_ext(s);
     }
 }
