@@ -4,4 +4,4 @@ The directory name is not a Python identifier; import it through `hfb200_loader.
 registers it as `hyperfridge_r0_b200`.
 """
 from .binding import (Context, Hfb200Error, load_library, LIB_PATH, EXPORTS, CircuitDesc, Stats, N_GLOBAL, P,  # noqa: F401
-                      CHECKPOINT_NAMES)
+                      CHECKPOINT_NAMES, Pool, SegmentJob)

@@ -21,6 +21,7 @@ EXPORTS = [
     "hfb200_prove_resident", "hfb200_read_group", "hfb200_seal_words", "hfb200_checkpoint", "hfb200_last_stats",
     "hfb200_total_launches", "hfb200_op_interpolate_ntt", "hfb200_op_expand_ntt", "hfb200_op_lde", "hfb200_op_merkle",
     "hfb200_op_poseidon2", "hfb200_op_fri_fold", "hfb200_bench_lde", "hfb200_bench_merkle",
+    "hfb200_pool_create", "hfb200_pool_prove", "hfb200_pool_destroy",
 ]
 
 
@@ -39,6 +40,12 @@ class Stats(C.Structure):
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class SegmentJob(C.Structure):
+    _fields_ = [("po2", C.c_uint32), ("globals", C.c_void_p), ("code", C.c_void_p), ("data", C.c_void_p), ("blind_seed", C.c_uint64),
+                ("seal_out", C.c_void_p), ("seal_cap", C.c_size_t), ("seal_words", C.c_size_t), ("error", C.c_void_p),
+                ("device", C.c_int), ("ms", C.c_float)]
 
 
 def load_library(path=None):
@@ -75,6 +82,9 @@ def load_library(path=None):
         "hfb200_op_fri_fold": (err, [vp, vp, vp, sz, vp]),
         "hfb200_bench_lde": (err, [vp, u32, u32, u32, C.POINTER(C.c_float)]),
         "hfb200_bench_merkle": (err, [vp, u32, u32, u32, C.POINTER(C.c_float)]),
+        "hfb200_pool_create": (err, [C.POINTER(C.c_int), C.c_int, C.c_int, u32, C.POINTER(CircuitDesc), C.POINTER(vp)]),
+        "hfb200_pool_prove": (err, [vp, C.POINTER(SegmentJob), sz]),
+        "hfb200_pool_destroy": (None, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -273,3 +283,60 @@ class Context:
         ms = C.c_float()
         self._check(self.lib.hfb200_bench_merkle(self._h, po2, count, iters, C.byref(ms)))
         return ms.value
+
+
+class Pool:
+    """hfb200_pool: worker contexts on several GPUs fed from one queue of independent segments (no collectives).
+    Mirrors the segment loop of upstream's `ProverImpl::prove_session`."""
+
+    def __init__(self, devices=(0,), contexts_per_device=1, max_po2=20, circuit=(16, 192, 48), lib=None):
+        self.lib = lib or load_library()
+        self.circuit = tuple(int(x) for x in circuit)
+        desc = CircuitDesc(self.circuit[0], self.circuit[1], self.circuit[2], 0)
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        self._h = None
+        e = self.lib.hfb200_pool_create(devs, len(devices), contexts_per_device, max_po2, C.byref(desc), C.byref(h))
+        self._raise(e)
+        self._h = h
+        self.workers = len(devices) * contexts_per_device
+
+    def _raise(self, e):
+        if e:
+            msg = C.cast(e, C.c_char_p).value.decode(errors="replace")
+            self.lib.hfb200_free_error(e)
+            raise Hfb200Error(msg)
+
+    def close(self):
+        if self._h:
+            self.lib.hfb200_pool_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def prove(self, jobs, seal_cap):
+        """jobs: list of (po2, globals, code, data, blind_seed) with numpy u32 arrays.  Returns (seals, devices, ms)."""
+        n = len(jobs)
+        arr = (SegmentJob * n)()
+        keep = []
+        seals = [np.empty(seal_cap, np.uint32) for _ in range(n)]
+        for i, (po2, g, code, data, seed) in enumerate(jobs):
+            g, code, data = _u32(g), _u32(code), _u32(data)
+            keep.append((g, code, data))
+            arr[i].po2, arr[i].blind_seed = po2, seed
+            arr[i].globals, arr[i].code, arr[i].data = g.ctypes.data, code.ctypes.data, data.ctypes.data
+            arr[i].seal_out, arr[i].seal_cap = seals[i].ctypes.data, seal_cap
+        e = self.lib.hfb200_pool_prove(self._h, arr, n)
+        errs = []
+        for i in range(n):
+            if arr[i].error:
+                errs.append(C.cast(arr[i].error, C.c_char_p).value.decode(errors="replace"))
+                self.lib.hfb200_free_error(arr[i].error)
+        self._raise(e)
+        if errs:
+            raise Hfb200Error(errs[0])
+        return [seals[i][:arr[i].seal_words] for i in range(n)], [arr[i].device for i in range(n)], [arr[i].ms for i in range(n)]

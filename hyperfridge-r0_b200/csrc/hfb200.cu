@@ -1,6 +1,10 @@
 // C ABI of libhfb200.so (see include/hfb200.h for the boundary contract and reference citations).
 #include "../../include/hfb200.h"
 #include "prover.cuh"
+#include <algorithm>
+#include <atomic>
+#include <memory>
+#include <thread>
 
 using namespace hf;
 
@@ -117,6 +121,7 @@ const char* hfb200_prove_resident(hfb200_ctx* ctx, uint64_t blind_seed, uint32_t
 const char* hfb200_read_group(hfb200_ctx* ctx, uint32_t group, uint32_t* out, size_t cap_words) {
     API_TRY
     if (!ctx || group > 2 || !ctx->p.tr[group]) throw Err("hfb200_read_group: bad argument");
+    ctx->p.bind();
     const size_t words = (size_t)ctx->p.cir.group_width((int)group) << ctx->p.po2;
     if (cap_words < words) throw Err("hfb200_read_group: buffer too small");
     ctx->p.dev.d2h(out, ctx->p.tr[group], words * 4);
@@ -150,6 +155,74 @@ const char* hfb200_last_stats(hfb200_ctx* ctx, hfb200_stats* out) {
 }
 uint64_t hfb200_total_launches(const hfb200_ctx* ctx) { return ctx ? ctx->p.dev.launches : 0; }
 
+// ---- multi-GPU pool ---------------------------------------------------------------------------------
+} // extern "C"
+struct hfb200_pool {
+    std::vector<std::unique_ptr<hfb200_ctx>> ctxs;
+    std::vector<int> device_of;
+};
+extern "C" {
+
+const char* hfb200_pool_create(const int* devices, int n_devices, int contexts_per_device, uint32_t max_po2,
+                               const hfb200_circuit_desc* c, hfb200_pool** out) {
+    API_TRY
+    if (!out || !devices || n_devices <= 0 || contexts_per_device <= 0) throw Err("hfb200_pool_create: bad argument");
+    *out = nullptr;
+    hfb200_circuit_desc d = c ? *c : hfb200_circuit_desc{16, 192, 48, 0};
+    std::unique_ptr<hfb200_pool> pool(new hfb200_pool());
+    // contexts are created on their worker threads' devices up front (cudaSetDevice is per thread, init is serial here)
+    for (int i = 0; i < n_devices; i++)
+        for (int s_ = 0; s_ < contexts_per_device; s_++) {
+            std::unique_ptr<hfb200_ctx> ctx(new hfb200_ctx());
+            ctx->p.init(devices[i], max_po2, d.w_code, d.w_data, d.w_accum);
+            pool->ctxs.push_back(std::move(ctx));
+            pool->device_of.push_back(devices[i]);
+        }
+    *out = pool.release();
+    API_CATCH
+}
+
+const char* hfb200_pool_prove(hfb200_pool* pool, hfb200_segment_job* jobs, size_t n_jobs) {
+    API_TRY
+    if (!pool || (!jobs && n_jobs)) throw Err("hfb200_pool_prove: bad argument");
+    std::vector<size_t> order(n_jobs);
+    for (size_t i = 0; i < n_jobs; i++) { order[i] = i; jobs[i].error = nullptr; jobs[i].seal_words = 0; jobs[i].device = -1; jobs[i].ms = 0; }
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return jobs[a].po2 > jobs[b].po2; });  // longest first
+    std::atomic<size_t> next{0};
+    auto worker = [&](size_t w) {
+        hfb200_ctx* ctx = pool->ctxs[w].get();
+#ifndef HFB200_EMU
+        cudaSetDevice(pool->device_of[w]);
+#endif
+        for (;;) {
+            const size_t k = next.fetch_add(1);
+            if (k >= n_jobs) break;
+            hfb200_segment_job& j = jobs[order[k]];
+            const auto t0 = std::chrono::steady_clock::now();
+            j.error = hfb200_prove_segment(ctx, j.po2, j.globals, j.code, j.data, j.blind_seed, j.seal_out, j.seal_cap, &j.seal_words);
+            j.device = pool->device_of[w];
+            j.ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        }
+    };
+    std::vector<std::thread> th;
+    for (size_t w = 0; w < pool->ctxs.size(); w++) th.emplace_back(worker, w);
+    for (auto& t : th) t.join();
+    for (size_t i = 0; i < n_jobs; i++)
+        if (jobs[i].error) return dup_err(std::string("job ") + std::to_string(i) + ": " + jobs[i].error);
+    API_CATCH
+}
+
+void hfb200_pool_destroy(hfb200_pool* pool) {
+    if (!pool) return;
+    for (size_t w = 0; w < pool->ctxs.size(); w++) {
+#ifndef HFB200_EMU
+        cudaSetDevice(pool->device_of[w]);
+#endif
+        try { pool->ctxs[w]->p.destroy(); } catch (...) {}
+    }
+    delete pool;
+}
+
 // ---- HAL-level operators ------------------------------------------------------------------------
 struct DevBuf {
     Dev& d; uint32_t* p;
@@ -159,6 +232,7 @@ struct DevBuf {
 
 const char* hfb200_op_interpolate_ntt(hfb200_ctx* ctx, uint32_t* io, size_t count, size_t n, int zk_shift) {
     API_TRY
+    ctx->p.bind();
     Dev& d = ctx->p.dev;
     const int lg = ilog2(n);
     if ((1ull << lg) != n || lg > 24 || count == 0) throw Err("op_interpolate_ntt: bad size");
@@ -171,6 +245,7 @@ const char* hfb200_op_interpolate_ntt(hfb200_ctx* ctx, uint32_t* io, size_t coun
 }
 const char* hfb200_op_expand_ntt(hfb200_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, size_t n_in, uint32_t expand_bits) {
     API_TRY
+    ctx->p.bind();
     Dev& d = ctx->p.dev;
     const int lg = ilog2(n_in);
     if ((1ull << lg) != n_in || lg + (int)expand_bits > 24 || (expand_bits != 0 && expand_bits != 2) || count == 0) throw Err("op_expand_ntt: bad size");
@@ -183,6 +258,7 @@ const char* hfb200_op_expand_ntt(hfb200_ctx* ctx, uint32_t* out, const uint32_t*
 }
 const char* hfb200_op_lde(hfb200_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, size_t n_in) {
     API_TRY
+    ctx->p.bind();
     Dev& d = ctx->p.dev;
     const int lg = ilog2(n_in);
     if ((1ull << lg) != n_in || lg > 22 || count == 0) throw Err("op_lde: bad size");
@@ -195,6 +271,7 @@ const char* hfb200_op_lde(hfb200_ctx* ctx, uint32_t* out, const uint32_t* in, si
 }
 const char* hfb200_op_merkle(hfb200_ctx* ctx, const uint32_t* matrix, size_t rows, size_t cols, uint32_t* nodes_out) {
     API_TRY
+    ctx->p.bind();
     Dev& d = ctx->p.dev;
     if ((1ull << ilog2(rows)) != rows || rows < 2 || cols == 0) throw Err("op_merkle: rows must be a power of two >= 2");
     DevBuf bm(d, rows * cols), bn(d, 2 * rows * 8);
@@ -207,6 +284,7 @@ const char* hfb200_op_merkle(hfb200_ctx* ctx, const uint32_t* matrix, size_t row
 }
 const char* hfb200_op_poseidon2(hfb200_ctx* ctx, uint32_t* states, size_t n) {
     API_TRY
+    ctx->p.bind();
     Dev& d = ctx->p.dev;
     DevBuf b(d, n * 24);
     d.h2d(b.p, states, n * 24 * 4);
@@ -217,6 +295,7 @@ const char* hfb200_op_poseidon2(hfb200_ctx* ctx, uint32_t* states, size_t n) {
 }
 const char* hfb200_op_fri_fold(hfb200_ctx* ctx, uint32_t* out, const uint32_t* in, size_t n, const uint32_t* mix4) {
     API_TRY
+    ctx->p.bind();
     Dev& d = ctx->p.dev;
     if (n < 16 || (n & 15)) throw Err("op_fri_fold: n must be a multiple of 16");
     DevBuf bi(d, 4 * n), bo(d, 4 * n / 16);
@@ -234,6 +313,7 @@ const char* hfb200_op_fri_fold(hfb200_ctx* ctx, uint32_t* out, const uint32_t* i
 const char* hfb200_bench_lde(hfb200_ctx* ctx, uint32_t po2, uint32_t count, uint32_t iters, float* ms_avg) {
     API_TRY
     Prover& p = ctx->p;
+    p.bind();
     p.layout(po2);
     if (count == 0 || count > p.cir.cd.w_data) throw Err("bench_lde: count must be in [1, w_data]");
     if (!p.have_trace) throw Err("bench_lde: call hfb200_witgen_synth first");
@@ -250,6 +330,7 @@ const char* hfb200_bench_lde(hfb200_ctx* ctx, uint32_t po2, uint32_t count, uint
 const char* hfb200_bench_merkle(hfb200_ctx* ctx, uint32_t po2, uint32_t count, uint32_t iters, float* ms_avg) {
     API_TRY
     Prover& p = ctx->p;
+    p.bind();
     p.layout(po2);
     if (count == 0 || count > p.cir.cd.w_data) throw Err("bench_merkle: count must be in [1, w_data]");
     const size_t D = (size_t)4 << po2;

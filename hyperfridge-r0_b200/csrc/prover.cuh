@@ -51,6 +51,7 @@ struct Prover {
     Merkle merkle;
     CircuitHost cir;
     uint32_t max_po2 = 0;
+    int device_id = 0;
     Arena arena;
     bool debug_checkpoints = false;
 
@@ -87,6 +88,7 @@ struct Prover {
         if (e != cudaSuccess || count == 0) throw Err(std::string("no CUDA device available (libhfb200 has no CPU fallback): ") + cudaGetErrorString(e));
         if (device < 0 || device >= count) throw Err("device index out of range");
         CUDA_CHECK(cudaSetDevice(device));
+        device_id = device;
         cudaDeviceProp prop;
         CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
         if (prop.major < 10) throw Err(std::string("libhfb200 is built for sm_100a only; found ") + prop.name);
@@ -121,6 +123,12 @@ struct Prover {
         return words * 4 + (64u << 20);
     }
 
+    // every API entry binds the calling host thread to this context's device (contexts may be driven from any thread)
+    void bind() {
+#ifndef HFB200_EMU
+        CUDA_CHECK(cudaSetDevice(device_id));
+#endif
+    }
     void mark(int i) {
 #ifndef HFB200_EMU
         CUDA_CHECK(cudaEventRecord(evs[i], dev.stream));
@@ -182,6 +190,7 @@ struct Prover {
     // ---- SegmentProver::prove, phase 1: header + CODE + DATA commits, returns the accum mix ----
     void begin(uint32_t p, const uint32_t* globals_h, const uint32_t* code_h, const uint32_t* data_h, uint64_t blind) {
         t_begin = std::chrono::steady_clock::now();
+        bind();
         layout(p);
         const size_t N = (size_t)1 << po2;
         arena.off = seg_mark;
@@ -240,6 +249,7 @@ struct Prover {
     void finish(const uint32_t* accum_h, std::vector<uint32_t>& seal_out) {
         if (!begun) throw Err("segment_finish without segment_begin");
         begun = false;
+        bind();
         const size_t N = (size_t)1 << po2, D = 4 * N;
         const CircuitDev& cd = cir.cd;
         const uint32_t W = cir.n_regs(), T = cir.n_taps;
@@ -450,6 +460,7 @@ struct Prover {
     }
 
     void witgen(uint32_t p, uint64_t trace_seed, uint64_t blind, uint32_t* globals_out) {
+        bind();
         layout(p);
         const size_t N = (size_t)1 << po2;
         for (uint32_t i = 0; i < N_GLOBAL; i++) globals_out[i] = synth_value(trace_seed ^ 0x676C6F62ull, 0xFFFFu, i);

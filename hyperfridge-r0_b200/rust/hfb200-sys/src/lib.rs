@@ -1,0 +1,70 @@
+//! Raw bindings of `include/hfb200.h`.  Error convention is the one of upstream's sys crates
+//! (`risc0_sys::ffi_wrap`): NULL = success, otherwise a malloc'd C string released with `hfb200_free_error`.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int};
+
+#[repr(C)]
+pub struct hfb200_ctx {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct hfb200_pool {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct hfb200_circuit_desc {
+    pub w_code: u32,
+    pub w_data: u32,
+    pub w_accum: u32,
+    pub flags: u32,
+}
+
+#[repr(C)]
+pub struct hfb200_segment_job {
+    pub po2: u32,
+    pub globals: *const u32,
+    pub code: *const u32,
+    pub data: *const u32,
+    pub blind_seed: u64,
+    pub seal_out: *mut u32,
+    pub seal_cap: usize,
+    pub seal_words: usize,
+    pub error: *const c_char,
+    pub device: c_int,
+    pub ms: f32,
+}
+
+extern "C" {
+    pub fn hfb200_init(device: c_int, max_po2: u32, circuit: *const hfb200_circuit_desc, out: *mut *mut hfb200_ctx) -> *const c_char;
+    pub fn hfb200_destroy(ctx: *mut hfb200_ctx);
+    pub fn hfb200_free_error(msg: *const c_char);
+    pub fn hfb200_seal_words(ctx: *const hfb200_ctx, po2: u32) -> usize;
+    pub fn hfb200_prove_segment(
+        ctx: *mut hfb200_ctx, po2: u32, globals: *const u32, code: *const u32, data: *const u32, blind_seed: u64,
+        seal_out: *mut u32, seal_cap: usize, seal_words: *mut usize,
+    ) -> *const c_char;
+    pub fn hfb200_segment_begin(
+        ctx: *mut hfb200_ctx, po2: u32, globals: *const u32, code: *const u32, data: *const u32, blind_seed: u64,
+        mix_out: *mut u32, mix_cap: usize, mix_words: *mut usize,
+    ) -> *const c_char;
+    pub fn hfb200_segment_finish(ctx: *mut hfb200_ctx, accum_or_null: *const u32, seal_out: *mut u32, seal_cap: usize, seal_words: *mut usize) -> *const c_char;
+    pub fn hfb200_pool_create(
+        devices: *const c_int, n_devices: c_int, contexts_per_device: c_int, max_po2: u32, circuit: *const hfb200_circuit_desc,
+        out: *mut *mut hfb200_pool,
+    ) -> *const c_char;
+    pub fn hfb200_pool_prove(pool: *mut hfb200_pool, jobs: *mut hfb200_segment_job, n_jobs: usize) -> *const c_char;
+    pub fn hfb200_pool_destroy(pool: *mut hfb200_pool);
+}
+
+/// Same contract as `risc0_sys::ffi_wrap`.
+pub fn ffi_wrap<F: FnOnce() -> *const c_char>(f: F) -> anyhow::Result<()> {
+    let e = f();
+    if e.is_null() {
+        return Ok(());
+    }
+    let msg = unsafe { std::ffi::CStr::from_ptr(e) }.to_string_lossy().into_owned();
+    unsafe { hfb200_free_error(e) };
+    Err(anyhow::anyhow!(msg))
+}

@@ -103,6 +103,30 @@ typedef struct {
 const char* hfb200_last_stats(hfb200_ctx* ctx, hfb200_stats* out);
 uint64_t hfb200_total_launches(const hfb200_ctx* ctx);
 
+/* ---- multi-GPU: a pool of contexts fed from one queue of independent segments --------------------------------- */
+/* Replaces the segment loop of upstream's `ProverImpl::prove_session` (sequential there).  One worker thread per
+ * (device, slot); whole segments are handed out longest-first (by po2); no collective, only seals return.  Seals depend
+ * on (trace, blind_seed) only, so the result is identical for any number of devices. */
+typedef struct hfb200_pool hfb200_pool;
+typedef struct {
+    uint32_t po2;
+    const uint32_t* globals; /* [32] */
+    const uint32_t* code;    /* u32[w_code][N]  host */
+    const uint32_t* data;    /* u32[w_data][N]  host */
+    uint64_t blind_seed;
+    uint32_t* seal_out;      /* caller buffer, seal_cap words */
+    size_t seal_cap;
+    size_t seal_words;       /* out */
+    const char* error;       /* out: NULL or malloc'd message (hfb200_free_error) */
+    int device;              /* out: device that proved the job */
+    float ms;                /* out: host wall time of the job */
+} hfb200_segment_job;
+const char* hfb200_pool_create(const int* devices, int n_devices, int contexts_per_device, uint32_t max_po2,
+                               const hfb200_circuit_desc* circuit, hfb200_pool** out);
+/* Proves all jobs; returns NULL when every job succeeded, else the first job's error (also left in jobs[i].error). */
+const char* hfb200_pool_prove(hfb200_pool* pool, hfb200_segment_job* jobs, size_t n_jobs);
+void hfb200_pool_destroy(hfb200_pool* pool);
+
 /* ---- HAL-level operators (second seam: risc0-zkp `Hal` methods), host buffers in/out ----------- */
 /* Hal::batch_interpolate_ntt (+ Hal::zk_shift when zk_shift != 0): natural-order evaluations ->
  * bit-reversed coefficients, in place, `count` columns of n = 2^k. */
