@@ -99,6 +99,12 @@ def oracle_sample_po2(steps, warmup):
 def run_oracle_sample(po2, repeats=1):
     """Times the CPU oracle (all host threads, OpenMP) proving one W=256 segment of 2^po2 cycles."""
     import oracle
+    # all host cores, regardless of OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    oracle.lib().orc_set_threads(ncpu)
     cir = oracle.Circuit(*WIDTHS)
     code = cir.gen_code(po2)
     g = cir.gen_globals(TRACE_SEED)
