@@ -287,7 +287,7 @@ def main():
         wall_e = max_over_ranks(time.perf_counter() - t0)
         e2e_value = world * F * args.steps / wall_e
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(F * ((WIDTHS[0] + WIDTHS[1]) * N * 4 + 128 + 4 * WIDTHS[2])),
-               "d2h_bytes_per_step": int(F * len(seal_h[0]) * 4), "ms_per_step": wall_e * 1e3 / args.steps, "ms_h2d_per_segment": h2d_ms[0] / args.steps,
+               "d2h_bytes_per_step": int(F * len(seal_h[0]) * 4), "ms_per_step": wall_e * 1e3 / args.steps, "ms_h2d_exposed_per_segment": h2d_ms[0] / args.steps,
                "camt53_proof_seconds": CAMT53_SEGMENTS / e2e_value, "host_memory": "pinned (hfb200_host_alloc)"}
         for c, (code_h, data_h) in zip(ctxs, hb):
             c.host_free(code_h)

@@ -76,6 +76,12 @@ struct Prover {
 #ifndef HFB200_EMU
     static constexpr int N_EV = 16;
     cudaEvent_t evs[N_EV] = {};
+    // host->device staging of the data columns runs on its own stream in H2D_CHUNKS column slices; the LDE of a slice
+    // starts as soon as its copy has landed, so the PCIe transfer hides behind the code commit and the data NTTs
+    static constexpr int H2D_CHUNKS = 4;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t chunk_ev[H2D_CHUNKS] = {};
+    cudaEvent_t copy_gate = nullptr;
 #endif
     float stage_ms[8] = {0};
 
@@ -95,6 +101,9 @@ struct Prover {
         dev.sm_count = prop.multiProcessorCount;
         CUDA_CHECK(cudaStreamCreateWithFlags(&dev.stream, cudaStreamNonBlocking));
         for (auto& ev_ : evs) CUDA_CHECK(cudaEventCreate(&ev_));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        for (auto& ev_ : chunk_ev) CUDA_CHECK(cudaEventCreateWithFlags(&ev_, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&copy_gate, cudaEventDisableTiming));
 #else
         (void)device;
 #endif
@@ -111,6 +120,9 @@ struct Prover {
         ntt.destroy();
 #ifndef HFB200_EMU
         for (auto& ev_ : evs) if (ev_) cudaEventDestroy(ev_);
+        for (auto& ev_ : chunk_ev) if (ev_) cudaEventDestroy(ev_);
+        if (copy_gate) cudaEventDestroy(copy_gate);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         if (dev.stream) cudaStreamDestroy(dev.stream);
 #endif
     }
@@ -201,7 +213,22 @@ struct Prover {
         std::memcpy(globals, globals_h, sizeof globals);
         for (uint32_t i = 0; i < N_GLOBAL; i++) if (globals[i] >= P) throw Err("globals: non-canonical field element");
         mark(0);
+        bool chunked = false;
         if (code_h) { dev.h2d(tr[GROUP_CODE], code_h, (size_t)cir.cd.w_code * N * 4); }
+#ifndef HFB200_EMU
+        if (data_h && cir.cd.w_data >= (uint32_t)H2D_CHUNKS) {
+            // the copy stream may not overwrite the data columns before everything already queued on the main
+            // stream (a previous segment's readers) has finished
+            CUDA_CHECK(cudaEventRecord(copy_gate, dev.stream));
+            CUDA_CHECK(cudaStreamWaitEvent(copy_stream, copy_gate, 0));
+            for (int k = 0; k < H2D_CHUNKS; k++) {
+                const uint32_t c0 = cir.cd.w_data * k / H2D_CHUNKS, c1 = cir.cd.w_data * (k + 1) / H2D_CHUNKS;
+                CUDA_CHECK(cudaMemcpyAsync(tr[GROUP_DATA] + (size_t)c0 * N, data_h + (size_t)c0 * N, (size_t)(c1 - c0) * N * 4, cudaMemcpyHostToDevice, copy_stream));
+                CUDA_CHECK(cudaEventRecord(chunk_ev[k], copy_stream));
+            }
+            chunked = true;
+        } else
+#endif
         if (data_h) { dev.h2d(tr[GROUP_DATA], data_h, (size_t)cir.cd.w_data * N * 4); }
         if (code_h && data_h) have_trace = true;
         if (!have_trace) throw Err("no trace: pass code/data or call hfb200_witgen_synth first");
@@ -212,7 +239,23 @@ struct Prover {
         proof.push_back(po2);
         cp_add("globals_hash", gh.w, 8);
         commit_group(GROUP_CODE, "code_root", 1, 2, 3);
-        commit_group(GROUP_DATA, "data_root", 3, 4, 5);
+        if (chunked) {
+#ifndef HFB200_EMU
+            const size_t D = 4 * N;
+            mark(3);
+            for (int k = 0; k < H2D_CHUNKS; k++) {
+                const uint32_t c0 = cir.cd.w_data * k / H2D_CHUNKS, c1 = cir.cd.w_data * (k + 1) / H2D_CHUNKS;
+                CUDA_CHECK(cudaStreamWaitEvent(dev.stream, chunk_ev[k], 0));
+                ntt.lde(tr[GROUP_DATA] + (size_t)c0 * N, N, ev[GROUP_DATA] + (size_t)c0 * D, D, scratch, c1 - c0, (int)po2);
+            }
+            mark(4);
+            merkle.build(ev[GROUP_DATA], D, (uint32_t)D, cir.cd.w_data, nodes[GROUP_DATA]);
+            mark(5);
+            commit_tree(Tree{ev[GROUP_DATA], D, (uint32_t)D, cir.cd.w_data, nodes[GROUP_DATA]}, "data_root");
+#endif
+        } else {
+            commit_group(GROUP_DATA, "data_root", 3, 4, 5);
+        }
         stage_ms[0] = between(0, 1);
         stage_ms[1] = between(1, 2) + between(3, 4);
         stage_ms[2] = between(2, 3) + between(4, 5);
