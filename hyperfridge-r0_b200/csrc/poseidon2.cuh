@@ -12,13 +12,18 @@ namespace hf {
 
 struct P2Consts {
     uint32_t rc_first[96], rc_partial[21], rc_last[96], diag[24];  // Montgomery form
+    uint32_t diag_std[24], diag_shoup[24];  // canonical d_i and floor(d_i * 2^32 / p): constant multiplier in Shoup form
 };
 
 static inline P2Consts p2_make_consts() {
     P2Consts c;
     for (int i = 0; i < 96; i++) { c.rc_first[i] = to_mont(P2_RC_FULL_FIRST[i]); c.rc_last[i] = to_mont(P2_RC_FULL_LAST[i]); }
     for (int i = 0; i < 21; i++) c.rc_partial[i] = to_mont(P2_RC_PARTIAL[i]);
-    for (int i = 0; i < 24; i++) c.diag[i] = to_mont(P2_M_INT_DIAG[i]);
+    for (int i = 0; i < 24; i++) {
+        c.diag[i] = to_mont(P2_M_INT_DIAG[i]);
+        c.diag_std[i] = P2_M_INT_DIAG[i];
+        c.diag_shoup[i] = (uint32_t)(((uint64_t)P2_M_INT_DIAG[i] << 32) / P);
+    }
     return c;
 }
 
@@ -57,7 +62,31 @@ HD uint32_t padd(uint32_t a, uint32_t b) {
     return fadd(a, b);
 #endif
 }
-HD uint32_t sbox7(uint32_t x) { uint32_t x2 = fmul(x, x), x3 = fmul(x2, x), x4 = fmul(x2, x2); return fmul(x3, x4); }
+// Montgomery product left in (0, 2p): one IADD3 instead of subtract + conditional correction.  Valid as ONE operand of a
+// following fmul/fmul_lazy whose other operand is canonical (2p * p < p * 2^32).
+HD uint32_t fmul_lazy(uint32_t a, uint32_t b) {
+    uint64_t o = (uint64_t)a * b;
+    uint32_t m = (uint32_t)o * P_INV;
+#ifdef __CUDA_ARCH__
+    uint32_t mp = __umulhi(m, P);
+#else
+    uint32_t mp = (uint32_t)(((uint64_t)m * P) >> 32);
+#endif
+    return (uint32_t)(o >> 32) - mp + P;
+}
+// x^7 with 4 multiplies; x4 stays lazy (it only meets the canonical x3).
+HD uint32_t sbox7(uint32_t x) { uint32_t x2 = fmul(x, x), x3 = fmul(x2, x), x4 = fmul_lazy(x2, x2); return fmul(x3, x4); }
+// x * d mod p for a constant d given as (d, d' = floor(d 2^32 / p)) -- Shoup: no 64-bit product, result already in [0, 2p).
+// x may be any residue representation (here Montgomery), d is the canonical constant.
+HD uint32_t fmul_const(uint32_t x, uint32_t d, uint32_t dp) {
+#ifdef __CUDA_ARCH__
+    const uint32_t q = __umulhi(x, dp);
+#else
+    const uint32_t q = (uint32_t)(((uint64_t)x * dp) >> 32);
+#endif
+    const uint32_t r = x * d - q * P;
+    return umin32(r, r - P);
+}
 
 // External layer: M4 on each 4-chunk (Poseidon2 add/double chain) then add the cross-chunk column sums.
 HD void p2_m_ext(uint32_t* s) {
@@ -82,7 +111,7 @@ HD void p2_m_int(uint32_t* s, const P2Consts& k) {
 #pragma unroll
     for (int i = 0; i < 24; i++) sum = padd(sum, s[i]);
 #pragma unroll
-    for (int i = 0; i < 24; i++) s[i] = padd(sum, fmul(k.diag[i], s[i]));
+    for (int i = 0; i < 24; i++) s[i] = padd(sum, fmul_const(s[i], k.diag_std[i], k.diag_shoup[i]));
 }
 
 HD void p2_mix(uint32_t* s) {
