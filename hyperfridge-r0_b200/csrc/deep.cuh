@@ -59,14 +59,23 @@ struct DotKernel {
         for (uint32_t it = cx.tid; it < DOT_T; it += cx.nt) {
             E4 acc[DOT_CPB][2];
             for (uint32_t c = 0; c < DOT_CPB; c++) { acc[c][0] = e4_zero(); acc[c][1] = e4_zero(); }
-            for (uint64_t r = row0 + it; r < row0 + DOT_RPB && r < n; r += DOT_T) {
+            // two rows per trip, all loads issued before the multiply-accumulate chains (memory-level parallelism)
+            for (uint64_t r = row0 + it; r < row0 + DOT_RPB && r < n; r += 2 * DOT_T) {
+                const uint64_t r2 = r + DOT_T;
+                const bool has2 = r2 < row0 + DOT_RPB && r2 < n;
                 const E4 w0 = Wt[r], w1 = Wt[(r + 1) & (n - 1)];
+                const E4 v0 = has2 ? Wt[r2] : e4_zero(), v1 = has2 ? Wt[(r2 + 1) & (n - 1)] : e4_zero();
+                uint32_t ta[DOT_CPB], tb[DOT_CPB];
 #pragma unroll
                 for (uint32_t c = 0; c < DOT_CPB; c++) {
-                    if (c0 + c >= ncols) break;
-                    const uint32_t t = cols[(uint64_t)(c0 + c) * col_stride + r];
-                    acc[c][0] = e4_add(acc[c][0], e4_scale(w0, t));
-                    if (c0 + c < n_back1) acc[c][1] = e4_add(acc[c][1], e4_scale(w1, t));
+                    const bool okc = c0 + c < ncols;
+                    ta[c] = okc ? cols[(uint64_t)(c0 + c) * col_stride + r] : 0u;
+                    tb[c] = (okc && has2) ? cols[(uint64_t)(c0 + c) * col_stride + r2] : 0u;
+                }
+#pragma unroll
+                for (uint32_t c = 0; c < DOT_CPB; c++) {
+                    acc[c][0] = e4_add(acc[c][0], e4_add(e4_scale(w0, ta[c]), e4_scale(v0, tb[c])));
+                    if (c0 + c < n_back1) acc[c][1] = e4_add(acc[c][1], e4_add(e4_scale(w1, ta[c]), e4_scale(v1, tb[c])));
                 }
             }
             for (uint32_t c = 0; c < DOT_CPB; c++) { red[(it * DOT_CPB + c) * 2] = acc[c][0]; red[(it * DOT_CPB + c) * 2 + 1] = acc[c][1]; }
