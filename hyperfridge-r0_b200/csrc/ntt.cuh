@@ -380,7 +380,7 @@ struct StridedKernel2 {
     }
 };
 
-static constexpr int MID_UT = 64;  // threads per unit of the chunk-stage kernel
+static constexpr int MID_UT = 64;  // threads per unit of the chunk-stage kernel for chunks up to 2^10 (larger chunks: 128 / 256)
 
 struct Mid2Args {
     const uint32_t* in;
@@ -390,7 +390,7 @@ struct Mid2Args {
     int n, a, b, e;
     uint32_t flags;
     uint32_t n_inv;
-    int units, alias;
+    int units, alias, ut;
     int nri, Ri[4];  // inverse rounds, top level first; the last one (RF levels) runs in registers
     int nrf, Rf[4];  // forward rounds; the first one (RF levels) runs in registers, fused with the inverse tail
     RootTables rt;
@@ -567,8 +567,8 @@ struct MiddleKernel2 {
         const int gmode = p.b == 0 ? 0 : (fly ? 2 : 1);
         const int RF = intt ? p.Ri[p.nri - 1] : p.Rf[0];
         const uint32_t col_end = (cx.by + 1) * p.cols_per_block < p.ncols ? (cx.by + 1) * p.cols_per_block : p.ncols;
-        for (int u = unit_first(cx, MID_UT); u < p.units; u += unit_step(cx, MID_UT)) {
-            const KCtx ux = unit_ctx(cx, u, MID_UT);
+        for (int u = unit_first(cx, p.ut); u < p.units; u += unit_step(cx, p.ut)) {
+            const KCtx ux = unit_ctx(cx, u, p.ut);
             uint32_t* ubase = sm + L.unit0 + (uint32_t)u * L.unit_words;
             uint32_t* B = ubase + L.B;
             uint32_t* A = (fwd && p.alias) ? B : ubase + L.A;
@@ -705,6 +705,13 @@ struct Ntt {
         switch (key) {
             case 100410: dev->launch<StridedKernel2<10, 4, 10>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
             case 100412: dev->launch<StridedKernel2<10, 4, 12>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
+            case 100411: dev->launch<StridedKernel2<10, 4, 11>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
+            case 100413: dev->launch<StridedKernel2<10, 4, 13>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
+            case 100414: dev->launch<StridedKernel2<10, 4, 14>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
+            case 90510: dev->launch<StridedKernel2<9, 5, 10>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
+            case 90512: dev->launch<StridedKernel2<9, 5, 12>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
+            case 70510: dev->launch<StridedKernel2<7, 5, 10>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
+            case 70512: dev->launch<StridedKernel2<7, 5, 12>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
             case 80510: dev->launch<StridedKernel2<8, 5, 10>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
             case 80512: dev->launch<StridedKernel2<8, 5, 12>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
             case 60510: dev->launch<StridedKernel2<6, 5, 10>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
@@ -729,10 +736,14 @@ struct Ntt {
 #ifdef HFB200_EMU
         p.alias = 0;
 #else
-        p.alias = (intt && fwd && (1 << (a - RF)) <= MID_UT) ? 1 : 0;
+        p.ut = a <= 10 ? MID_UT : (a == 11 ? 128 : 256);
+        p.alias = (intt && fwd && (1 << (a - RF)) <= p.ut) ? 1 : 0;
 #endif
-        const size_t budget = 112 * 1024;  // two CTAs per SM
-        int units = 4;
+#ifdef HFB200_EMU
+        p.ut = MID_UT;
+#endif
+        const size_t budget = a <= 10 ? 112 * 1024 : 200 * 1024;  // two CTAs per SM for the common chunk size
+        int units = 256 / p.ut;
         for (;; units >>= 1) {
             p.units = units;
             if ((size_t)Mid2Layout(p).total * 4 <= budget || units == 1) break;
@@ -744,8 +755,8 @@ struct Ntt {
         if (groups > max_groups) groups = max_groups;
         p.cols_per_block = (ncols + groups - 1) / groups;
         groups = (ncols + p.cols_per_block - 1) / p.cols_per_block;
-        if (a == 10 && e == 2 && intt && fwd) dev->launch<MiddleKernel2<10, 2>, 256, 2>((unsigned)chunks, groups, p.units * MID_UT, (size_t)Mid2Layout(p).total * 4, p);
-        else dev->launch<MiddleKernel2<-1, -1>, 256, 2>((unsigned)chunks, groups, p.units * MID_UT, (size_t)Mid2Layout(p).total * 4, p);
+        if (a == 10 && e == 2 && intt && fwd) dev->launch<MiddleKernel2<10, 2>, 256, 2>((unsigned)chunks, groups, p.units * p.ut, (size_t)Mid2Layout(p).total * 4, p);
+        else dev->launch<MiddleKernel2<-1, -1>, 256, 2>((unsigned)chunks, groups, p.units * p.ut, (size_t)Mid2Layout(p).total * 4, p);
     }
 
     void middle_small(const uint32_t* in, uint64_t in_stride, uint32_t* out, uint64_t out_stride, uint32_t ncols, int n, int a, int e, uint32_t flags) {

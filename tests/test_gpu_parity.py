@@ -153,3 +153,16 @@ def test_full_size_po2_20_properties(pkg, gpu_lib, orc):
         assert (out[3] == 12345).all()
         # inverse o forward round trip at 2^20
         assert (c.op_expand_ntt(c.op_interpolate_ntt(x, False), 0) == x).all()
+
+
+def test_po2_22_large_segment(pkg, gpu_lib, orc):
+    """BASELINE.json configs[4]: one po2 = 22 segment per GPU (29 GB arena).  Size-independent checks only."""
+    po2 = 22
+    with pkg.Context(0, po2, DEFAULT, lib=gpu_lib) as c:
+        c.witgen_synth(po2, TRACE_SEED, 1)
+        seal = c.prove_resident(1)
+        cir = orc.Circuit(*DEFAULT)
+        assert len(seal) == c.seal_words(po2) == cir.seal_words_model(po2)
+        assert cir.verify(seal, c.checkpoint("code_root")) == po2
+        st = c.last_stats()
+        print("po2=22 segment: %.1f ms (ntt %.1f, hash %.1f)" % (st["ms_total"], st["ms_ntt_main"], st["ms_hash_main"]))
