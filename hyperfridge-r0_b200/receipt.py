@@ -1,0 +1,97 @@
+"""Receipt wire format around the hot path -- host-side data classes only.
+
+Mirrors the serde-JSON shape the reference writes and reads:
+  * written by `serde_json::to_string(&receipt)` at /root/reference/host/src/main.rs:250-252,
+  * journal decoded at /root/reference/host/src/main.rs:258-267 (`receipt.journal.bytes`: u32-LE length, UTF-8 JSON,
+    zero padding to 4 bytes),
+  * read back by `serde_json::from_slice::<Receipt>` at /root/reference/verifier/src/main.rs:118-119.
+The two receipts shipped with the reference are dev-mode fakes (`{"inner":"Fake","journal":{"bytes":[...]}}`,
+/root/reference/data/test/test.xml-Receipt-test.json:1); `Receipt.from_json` accepts them, which pins the journal
+encoding against reference data.  The Composite form (`{"inner":{"Composite":{"segments":[{"seal":[..u32..],"index":..,
+"hashfn":"poseidon2",..}],..}}`) follows risc0-zkvm 3.0.5's `CompositeReceipt` / `SegmentReceipt` field names (crate not
+vendored: recollection); claims are carried opaquely.
+"""
+import json
+import struct
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+
+def encode_journal(text: str) -> bytes:
+    """risc0 serde encoding of one committed `String`: u32-LE byte length, the bytes, zero pad to a multiple of 4."""
+    raw = text.encode("utf-8")
+    pad = (-len(raw)) % 4
+    return struct.pack("<I", len(raw)) + raw + b"\x00" * pad
+
+
+def decode_journal(data: bytes) -> str:
+    if len(data) < 4:
+        raise ValueError("journal too short")
+    (n,) = struct.unpack("<I", data[:4])
+    if 4 + n > len(data):
+        raise ValueError("journal length prefix exceeds the payload")
+    return data[4:4 + n].decode("utf-8")
+
+
+@dataclass
+class Journal:
+    bytes_: bytes = b""
+
+    def decode(self) -> str:
+        return decode_journal(self.bytes_)
+
+    def to_obj(self):
+        return {"bytes": list(self.bytes_)}
+
+
+@dataclass
+class SegmentReceipt:
+    seal: List[int]
+    index: int
+    hashfn: str = "poseidon2"
+    verifier_parameters: List[int] = field(default_factory=lambda: [0] * 8)
+    claim: Optional[dict] = None
+
+    def to_obj(self):
+        return {"seal": [int(x) for x in self.seal], "index": self.index, "hashfn": self.hashfn,
+                "verifier_parameters": self.verifier_parameters, "claim": self.claim}
+
+
+@dataclass
+class CompositeReceipt:
+    segments: List[SegmentReceipt]
+    assumption_receipts: list = field(default_factory=list)
+    verifier_parameters: List[int] = field(default_factory=lambda: [0] * 8)
+
+    def to_obj(self):
+        return {"segments": [s.to_obj() for s in self.segments], "assumption_receipts": self.assumption_receipts,
+                "verifier_parameters": self.verifier_parameters}
+
+
+@dataclass
+class Receipt:
+    inner: object  # "Fake" | CompositeReceipt
+    journal: Journal
+    metadata: Optional[dict] = None
+
+    def to_json(self) -> str:
+        inner = self.inner if isinstance(self.inner, str) else {"Composite": self.inner.to_obj()}
+        obj = {"inner": inner, "journal": self.journal.to_obj()}
+        if self.metadata is not None:
+            obj["metadata"] = self.metadata
+        return json.dumps(obj, separators=(",", ":"))
+
+    @staticmethod
+    def from_json(text: str) -> "Receipt":
+        obj = json.loads(text)
+        journal = Journal(bytes(obj["journal"]["bytes"]))
+        inner = obj["inner"]
+        if isinstance(inner, dict) and "Composite" in inner:
+            c = inner["Composite"]
+            segs = [SegmentReceipt(s["seal"], s["index"], s.get("hashfn", "poseidon2"), s.get("verifier_parameters", [0] * 8), s.get("claim"))
+                    for s in c["segments"]]
+            inner = CompositeReceipt(segs, c.get("assumption_receipts", []), c.get("verifier_parameters", [0] * 8))
+        return Receipt(inner, journal, obj.get("metadata"))
+
+    def seal_bytes(self) -> int:
+        return 0 if isinstance(self.inner, str) else sum(4 * len(s.seal) for s in self.inner.segments)
