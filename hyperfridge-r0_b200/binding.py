@@ -116,6 +116,7 @@ class Context:
         desc = CircuitDesc(self.circuit[0], self.circuit[1], self.circuit[2], 0)
         h = C.c_void_p()
         self._h = None
+        self._po2 = max_po2
         self._check(self.lib.hfb200_init(device, max_po2, C.byref(desc), C.byref(h)))
         self._h = h
 

@@ -324,15 +324,8 @@ struct Prover {
             uint32_t y = three_n;
             for (int s = 0; s < 4; s++) { a.yinv[s] = finv(fsub(y, ONE)); y = fmul(y, w4); }
             a.po2 = po2; a.cd = cd;
-            static const int ec_mode = std::getenv("HFB200_EC") ? std::atoi(std::getenv("HFB200_EC")) : 0;
-            if (ec_mode == 1) {
-                a.rows_per_block = EC_ROWS;
-                const size_t ec_smem = ((size_t)nc + 2 * EC_ROWS) * sizeof(E4) + (size_t)W * EC_TS * 4;
-                dev.launch<EvalCheckKernelTile, 128, 3>((unsigned)(D / EC_ROWS), 1, 128, ec_smem, a);
-            } else {
-                a.rows_per_block = 128;
-                dev.launch<EvalCheckKernelDirect, 128, 1>((unsigned)((D + 127) / 128), 1, 128, (size_t)nc * sizeof(E4), a);
-            }
+            a.rows_per_block = 128;
+            dev.launch<EvalCheckKernel, 128, 1>((unsigned)((D + 127) / 128), 1, 128, (size_t)nc * sizeof(E4), a);
             dev.sync();  // mp must outlive the copy
         }
         // 4 polys of 4N evaluations -> coefficients (no zk_shift); bit-reversed order makes them 16 polys of N

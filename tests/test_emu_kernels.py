@@ -94,3 +94,24 @@ def test_error_paths(pkg, emu_lib):
             c.prove_resident(1)  # no resident trace yet
         with pytest.raises(pkg.Hfb200Error):
             c.witgen_synth(13, 1, 1)  # above max_po2
+
+
+def test_abi_buffer_contract(pkg, emu_lib, orc):
+    """Seal buffer too small -> error and the required size; mix buffer too small -> error; NULL trace -> error."""
+    import ctypes as C
+    cir, g, code, data = make_segment(orc, SMALL, 12)
+    with pkg.Context(0, 12, SMALL, lib=emu_lib) as c:
+        need = c.seal_words(12)
+        seal = np.zeros(16, np.uint32)
+        got = C.c_size_t()
+        e = emu_lib.hfb200_prove_segment(c._h, 12, g.ctypes.data, code.ctypes.data, data.ctypes.data, 1, seal.ctypes.data, seal.size, C.byref(got))
+        assert e and b"too small" in C.cast(e, C.c_char_p).value and got.value == need
+        emu_lib.hfb200_free_error(e)
+        e = emu_lib.hfb200_prove_segment(c._h, 12, g.ctypes.data, None, data.ctypes.data, 1, seal.ctypes.data, seal.size, C.byref(got))
+        assert e and b"NULL" in C.cast(e, C.c_char_p).value
+        emu_lib.hfb200_free_error(e)
+        bad = g.copy(); bad[3] = 0xFFFFFFFF  # INVALID marker is never a valid input
+        with pytest.raises(pkg.Hfb200Error, match="non-canonical"):
+            c.prove_segment(12, bad, code, data, 1)
+        with pytest.raises(pkg.Hfb200Error):
+            c.segment_finish(None)  # finish without begin
