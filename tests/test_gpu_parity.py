@@ -166,3 +166,32 @@ def test_po2_22_large_segment(pkg, gpu_lib, orc):
         assert cir.verify(seal, c.checkpoint("code_root")) == po2
         st = c.last_stats()
         print("po2=22 segment: %.1f ms (ntt %.1f, hash %.1f)" % (st["ms_total"], st["ms_ntt_main"], st["ms_hash_main"]))
+
+
+def test_pool_and_concurrent_contexts_on_gpu(pkg, gpu_lib, orc):
+    """hfb200_pool on real devices (every visible GPU, two contexts each) and two contexts driven from two host
+    threads: seals equal the oracle's regardless of which device / context proved them."""
+    import threading
+    import torch
+    ndev = max(1, torch.cuda.device_count())
+    jobs, expect = [], []
+    for i, po2 in enumerate([12, 13, 12, 13, 12, 12]):
+        cir, g, code, data = make_segment(orc, SMALL, po2, trace_seed=300 + i)
+        jobs.append((po2, g, code, data, 40 + i))
+        expect.append(cir.prove(po2, g, code, data, 40 + i)[0])
+    with pkg.Pool(devices=tuple(range(ndev)), contexts_per_device=2, max_po2=13, circuit=SMALL, lib=gpu_lib) as pool:
+        seals, devs, ms = pool.prove(jobs, 40000)
+        assert all(len(a) == len(b) and (a == b).all() for a, b in zip(seals, expect))
+        assert set(devs) <= set(range(ndev))
+    ctxs = [pkg.Context(0, 13, SMALL, lib=gpu_lib) for _ in range(2)]
+    out = [None, None]
+
+    def work(k):
+        po2, g, code, data, seed = jobs[k]
+        for _ in range(3):
+            out[k] = ctxs[k].prove_segment(po2, g, code, data, seed)
+    th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert (out[0] == expect[0]).all() and (out[1] == expect[1]).all()
+    [c.close() for c in ctxs]
