@@ -41,6 +41,20 @@ HD uint32_t fpow(uint32_t b, uint64_t e) {
 }
 HD uint32_t finv(uint32_t a) { return fpow(a, P - 2); }
 
+// x * d mod p for a constant d known as (d, d' = floor(d 2^32 / p)) in CANONICAL form -- Shoup's method: one high
+// multiply + two low multiplies, no 64-bit product, no separate subtraction.  x may be in any residue representation
+// (Montgomery here): the result is in the same representation.  Canonical output.
+HD uint32_t fmul_shoup(uint32_t x, uint32_t d, uint32_t dp) {
+#ifdef __CUDA_ARCH__
+    const uint32_t q = __umulhi(x, dp);
+#else
+    const uint32_t q = (uint32_t)(((uint64_t)x * dp) >> 32);
+#endif
+    const uint32_t r = x * d - q * P;
+    return umin32(r, r - P);
+}
+HD uint32_t shoup_quot(uint32_t d) { return (uint32_t)(((uint64_t)d << 32) / P); }
+
 struct __align__(16) E4 { uint32_t c[4]; };
 
 HD E4 e4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { E4 r; r.c[0] = a; r.c[1] = b; r.c[2] = c; r.c[3] = d; return r; }

@@ -246,7 +246,8 @@ struct GlobStridedIO {  // element (pos, batch) of a strided tile: row pos at st
 // TWL: twiddle table layout. false: tw[i] = w_{2^k}^i (i < 2^(k-1)), level l reads stride 2^(k-l);  true: per-level
 // blocks tw[2^(l-1) + x] = w_{2^l}^x, so consecutive lanes read consecutive words (no bank conflicts when c = 0).
 // HF: lanes enumerate `high` first (only for c = 0); keeps rounds with l0 < 5 off the same banks.
-template <int R, bool INV, int K, int C, int L0, bool TWL = false, bool HF = false, typename LD, typename ST>
+// SHP: the table holds canonical (w, w' = floor(w 2^32 / p)) pairs at tw[2 i], tw[2 i + 1] and multiplies use Shoup's form.
+template <int R, bool INV, int K, int C, int L0, bool TWL = false, bool HF = false, bool SHP = false, typename LD, typename ST>
 HD void round_t(const KCtx& cx, const uint32_t* tw, int k_, int c_, int l0_, const LD& L, const ST& S) {
     const int k = K >= 0 ? K : k_, c = C >= 0 ? C : c_, l0 = L0 >= 0 ? L0 : l0_;
     const uint32_t items = 1u << (k - R + c);
@@ -275,7 +276,10 @@ HD void round_t(const KCtx& cx, const uint32_t* tw, int k_, int c_, int l0_, con
                 for (int j = 0; j < (1 << R); j++) {
                     if (j & h) continue;
                     uint32_t x = v[j + h];
-                    if (!(L0 == 0 && (j & (h - 1)) == 0)) x = fmul(x, TWL ? tw[(1u << (l0 + q - 1)) + ((uint32_t)(j & (h - 1)) << l0) + low] : tw[(low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q)]);
+                    if (!(L0 == 0 && (j & (h - 1)) == 0)) {
+                        const uint32_t ti = TWL ? (1u << (l0 + q - 1)) + ((uint32_t)(j & (h - 1)) << l0) + low : (low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q);
+                        x = SHP ? fmul_shoup(x, tw[2 * ti], tw[2 * ti + 1]) : fmul(x, tw[ti]);
+                    }
                     v[j + h] = fsub(v[j], x);
                     v[j] = fadd(v[j], x);
                 }
@@ -290,7 +294,10 @@ HD void round_t(const KCtx& cx, const uint32_t* tw, int k_, int c_, int l0_, con
                     const uint32_t a = v[j], b = v[j + h];
                     v[j] = fadd(a, b);
                     uint32_t d = fsub(a, b);
-                    if (!(L0 == 0 && (j & (h - 1)) == 0)) d = fmul(d, TWL ? tw[(1u << (l0 + q - 1)) + ((uint32_t)(j & (h - 1)) << l0) + low] : tw[(low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q)]);
+                    if (!(L0 == 0 && (j & (h - 1)) == 0)) {
+                        const uint32_t ti = TWL ? (1u << (l0 + q - 1)) + ((uint32_t)(j & (h - 1)) << l0) + low : (low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q);
+                        d = SHP ? fmul_shoup(d, tw[2 * ti], tw[2 * ti + 1]) : fmul(d, tw[ti]);
+                    }
                     v[j + h] = d;
                 }
             }
@@ -336,13 +343,13 @@ struct StridedKernel2 {
             // fixed schedule: SB = R0 + R1 + R2 with R0 = 4 on the global-facing first round
             constexpr int R0 = 4, R1 = (SB - 4 + 1) / 2, R2 = SB - 4 - R1;
             if (INV) {
-                round_t<R0, true, SB, SC, SB - R0>(cx, tw, SB, SC, SB - R0, G, S); cx.sync();
-                round_t<R1, true, SB, SC, R2>(cx, tw, SB, SC, R2, S, S); cx.sync();
-                round_t<(R2 > 0 ? R2 : 1), true, SB, SC, 0>(cx, tw, SB, SC, 0, S, G);
+                round_t<R0, true, SB, SC, SB - R0, false, false, true>(cx, tw, SB, SC, SB - R0, G, S); cx.sync();
+                round_t<R1, true, SB, SC, R2, false, false, true>(cx, tw, SB, SC, R2, S, S); cx.sync();
+                round_t<(R2 > 0 ? R2 : 1), true, SB, SC, 0, false, false, true>(cx, tw, SB, SC, 0, S, G);
             } else {
-                round_t<R0, false, SB, SC, 0>(cx, tw, SB, SC, 0, G, S); cx.sync();
-                round_t<R1, false, SB, SC, R0>(cx, tw, SB, SC, R0, S, S); cx.sync();
-                round_t<(R2 > 0 ? R2 : 1), false, SB, SC, R0 + R1>(cx, tw, SB, SC, R0 + R1, S, G);
+                round_t<R0, false, SB, SC, 0, false, false, true>(cx, tw, SB, SC, 0, G, S); cx.sync();
+                round_t<R1, false, SB, SC, R0, false, false, true>(cx, tw, SB, SC, R0, S, S); cx.sync();
+                round_t<(R2 > 0 ? R2 : 1), false, SB, SC, R0 + R1, false, false, true>(cx, tw, SB, SC, R0 + R1, S, G);
             }
             cx.sync();
         } else {
@@ -365,8 +372,11 @@ struct StridedKernel2 {
         uint32_t* s = sm;
         uint32_t* tw = sm + padded_words(1u << (p.b + p.c));
         const uint32_t half = 1u << (p.b - 1);
-        for (uint32_t i = cx.tid; i < half; i += cx.nt)
-            tw[i] = p.inv ? tab_pow(p.rt.i_lo, p.rt.i_hi, i << (24 - p.b)) : tab_pow(p.rt.f_lo, p.rt.f_hi, i << (24 - p.b));
+        for (uint32_t i = cx.tid; i < half; i += cx.nt) {
+            const uint32_t w = p.inv ? tab_pow(p.rt.i_lo, p.rt.i_hi, i << (24 - p.b)) : tab_pow(p.rt.f_lo, p.rt.f_hi, i << (24 - p.b));
+            if (SB >= 6) { const uint32_t ws = from_mont(w); tw[2 * i] = ws; tw[2 * i + 1] = shoup_quot(ws); }  // Shoup pairs
+            else tw[i] = w;
+        }
         cx.sync();
         const uint32_t tiles_per_col = 1u << (p.a - p.c);
         const uint64_t total = (uint64_t)p.ncols * tiles_per_col;
@@ -694,7 +704,7 @@ struct Ntt {
         p.in = in; p.out = out; p.in_stride = in_stride; p.out_stride = out_stride; p.ncols = ncols;
         p.a = a; p.b = b; p.c = c; p.inv = inv ? 1 : 0; p.rt = rt;
         p.nr = split_rounds(b, p.R);
-        const size_t smem = (size_t)(padded_words(1u << (b + c)) + (1u << (b - 1))) * 4;
+        const size_t smem = (size_t)(padded_words(1u << (b + c)) + (1u << b)) * 4;  // tile + twiddle (w, w') pairs
         const uint64_t tiles = (uint64_t)ncols << (a - c);
         unsigned per_sm = (unsigned)((220 * 1024) / (smem + 1024));
         if (per_sm < 1) per_sm = 1;
