@@ -298,10 +298,16 @@ def main():
     ntt_ms = stage["ms_ntt_main"] / args.steps
     ntt_bytes = 28.0 * W * N
     achieved = ntt_bytes / (ntt_ms * 1e-3) / 1e9 if ntt_ms > 0 else 0.0
+    traffic = None
+    try:  # measured DRAM bytes per trace element of the three NTT/LDE kernels (one ncu --set full capture, profiles/)
+        with open(os.path.join(ROOT, "profiles", "r1_ntt_traffic.json")) as f:
+            traffic = float(json.load(f)["bytes_per_trace_element"]) * W * N
+    except Exception:
+        pass
     roofline = {"kernel": "NTT/LDE pipeline of the 3 main groups: StridedKernel(DIF) + MiddleKernel(fused iNTT.zk_shift.expand.NTT chunk stage) + StridedKernel(DIT), 9 launches/segment",
-                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes": ntt_bytes, "ms": ntt_ms, "peak_source": peak_src,
-                "note": "traffic by design = 60*W*N bytes (8 + 20 + 32 per element over the three passes); ncu dram bytes go under profiles/"}
+                "note": "traffic = dram__bytes_read+write of the 3 kernels from ncu (profiles/r1_ntt_traffic.json) scaled to W*N elements; by design 60*W*N (8+20+32 B per element over the three passes) vs 28*W*N algorithmic; the binding unit is the integer-multiply pipe, not HBM (DESIGN.md section 5)"}
     # Poseidon2 (integer-ALU bound, no HBM roofline): permutations/s
     perms = 4 * N * sum((w + 15) // 16 for w in WIDTHS) + 3 * 4 * N
     hash_ms = stage["ms_hash_main"] / args.steps
