@@ -115,3 +115,15 @@ def test_abi_buffer_contract(pkg, emu_lib, orc):
             c.prove_segment(12, bad, code, data, 1)
         with pytest.raises(pkg.Hfb200Error):
             c.segment_finish(None)  # finish without begin
+
+
+@pytest.mark.parametrize("widths,po2", [((21, 40, 12), 12), ((5, 8, 4), 12), ((16, 200, 52), 12)])
+def test_odd_circuit_widths(pkg, emu_lib, orc, widths, po2):
+    """Ragged shapes: widths that are not multiples of the sponge rate (partial absorb blocks), the minimum circuit,
+    and column-group sizes that do not divide the per-block column counts of the NTT / dot kernels."""
+    cir, g, code, data = make_segment(orc, widths, po2)
+    oseal, ocps, _ = cir.prove(po2, g, code, data, 3)
+    with pkg.Context(0, po2, widths, lib=emu_lib) as c:
+        seal = c.prove_segment(po2, g, code, data, 3)
+        assert len(seal) == len(oseal) and (seal == oseal).all()
+        assert cir.verify(seal, ocps["code_root"]) == po2

@@ -28,9 +28,9 @@ def test_poseidon2_permutation(ctx, orc):
     assert (got == exp).all()
 
 
-@pytest.mark.parametrize("lg", [1, 4, 10, 11, 12, 14, 16, 18, 20])
+@pytest.mark.parametrize("lg", [1, 4, 10, 11, 12, 14, 15, 16, 17, 18, 19, 20, 21])
 def test_ntt_ops(ctx, orc, lg):
-    ncols = 3 if lg < 20 else 2
+    ncols = 3 if lg < 19 else 2
     x = rand_elems(np.random.default_rng(lg), (ncols, 1 << lg))
     x[0, :] = np.uint32(P - 1)  # extreme values
     coeffs = orc.interpolate_ntt(x)
@@ -81,7 +81,7 @@ def test_fri_fold_matches_definition(ctx, orc):
         assert (outnat[:, m] == tot.astype(np.uint32)).all()
 
 
-@pytest.mark.parametrize("widths,po2", [(SMALL, 12), (SMALL, 13), (DEFAULT, 12), (DEFAULT, 14), (DEFAULT, 16)])
+@pytest.mark.parametrize("widths,po2", [(SMALL, 12), (SMALL, 13), (SMALL, 15), (SMALL, 17), (DEFAULT, 12), (DEFAULT, 14), (DEFAULT, 16), (DEFAULT, 18)])
 def test_segment_seal_bit_exact(pkg, gpu_lib, orc, widths, po2, monkeypatch):
     monkeypatch.setenv("HFB200_DEBUG_CHECKPOINTS", "1")
     cir, g, code, data = make_segment(orc, widths, po2)
@@ -195,3 +195,14 @@ def test_pool_and_concurrent_contexts_on_gpu(pkg, gpu_lib, orc):
     [t.join() for t in th]
     assert (out[0] == expect[0]).all() and (out[1] == expect[1]).all()
     [c.close() for c in ctxs]
+
+
+@pytest.mark.parametrize("widths,po2", [((21, 40, 12), 13), ((5, 8, 4), 12), ((16, 200, 52), 14)])
+def test_odd_circuit_widths(pkg, gpu_lib, orc, widths, po2):
+    """Ragged shapes on the GPU: partial sponge blocks, the minimum circuit, non-divisible column groups."""
+    cir, g, code, data = make_segment(orc, widths, po2)
+    oseal, ocps, _ = cir.prove(po2, g, code, data, 3)
+    with pkg.Context(0, po2, widths, lib=gpu_lib) as c:
+        seal = c.prove_segment(po2, g, code, data, 3)
+        assert len(seal) == len(oseal) and (seal == oseal).all()
+        assert cir.verify(seal, ocps["code_root"]) == po2
