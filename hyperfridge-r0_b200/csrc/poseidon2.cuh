@@ -209,6 +209,95 @@ struct HashFoldTailKernel {
     }
 };
 
+// ---- warp-cooperative permutation for the small upper levels of a tree --------------------------------------------
+// With one thread per node a level of <= a few thousand nodes is pure latency (one permutation ~17 us, one launch per
+// level).  Here a WARP computes one node: lane L < 24 owns state cell L, the S-boxes run 24-wide, the linear layers use
+// shuffles (4-lane M4 groups, xor-butterfly column sums, warp all-reduce for the internal layer): ~3.5 us per node.
+// 4x more instructions per node than the thread version, so it is used only where latency, not throughput, binds.
+#ifdef __CUDA_ARCH__
+struct WarpConsts { uint32_t rcf[4], rcl[4], d, dp; };
+__device__ __forceinline__ WarpConsts wp2_consts(int lane) {
+    const P2Consts& k = p2c();
+    WarpConsts w;
+    const int l = lane < 24 ? lane : 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) { w.rcf[r] = lane < 24 ? k.rc_first[r * 24 + l] : 0u; w.rcl[r] = lane < 24 ? k.rc_last[r * 24 + l] : 0u; }
+    w.d = k.diag_std[l]; w.dp = k.diag_shoup[l];
+    return w;
+}
+__device__ __forceinline__ uint32_t wp2_m_ext(uint32_t x, int lane) {
+    const int q = lane & ~3;
+    const uint32_t a = __shfl_sync(0xffffffffu, x, q), b = __shfl_sync(0xffffffffu, x, q + 1);
+    const uint32_t c = __shfl_sync(0xffffffffu, x, q + 2), d = __shfl_sync(0xffffffffu, x, q + 3);
+    const uint32_t t0 = fadd(a, b), t1 = fadd(c, d);
+    const uint32_t t2 = fadd(fadd(b, b), t1), t3 = fadd(fadd(d, d), t0);
+    uint32_t t4 = fadd(t1, t1); t4 = fadd(fadd(t4, t4), t3);
+    uint32_t t5 = fadd(t0, t0); t5 = fadd(fadd(t5, t5), t2);
+    const int r = lane & 3;
+    const uint32_t out = r == 0 ? fadd(t3, t5) : r == 1 ? t5 : r == 2 ? fadd(t2, t4) : t4;
+    uint32_t s = out;
+    s = fadd(s, __shfl_xor_sync(0xffffffffu, s, 4));
+    s = fadd(s, __shfl_xor_sync(0xffffffffu, s, 8));
+    s = fadd(s, __shfl_xor_sync(0xffffffffu, s, 16));
+    return lane < 24 ? fadd(out, s) : 0u;
+}
+__device__ __forceinline__ uint32_t wp2_mix(uint32_t x, int lane, const WarpConsts& w) {
+    const P2Consts& k = p2c();
+    x = wp2_m_ext(x, lane);
+#pragma unroll
+    for (int r = 0; r < 4; r++) x = wp2_m_ext(sbox7(fadd(x, w.rcf[r])), lane);
+#pragma unroll 1
+    for (int r = 0; r < 21; r++) {
+        const uint32_t y = sbox7(fadd(x, k.rc_partial[r]));
+        if (lane == 0) x = y;
+        uint32_t s = x;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) s = fadd(s, __shfl_xor_sync(0xffffffffu, s, off));
+        x = lane < 24 ? fadd(s, fmul_const(x, w.d, w.dp)) : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) x = wp2_m_ext(sbox7(fadd(x, w.rcl[r])), lane);
+    return x;
+}
+__device__ __forceinline__ void wp2_hash_pair(uint32_t* nodes, uint64_t i, int lane, const WarpConsts& w) {
+    uint32_t x = lane < 16 ? nodes[2 * i * 8 + lane] : 0u;
+    x = wp2_mix(x, lane, w);
+    if (lane < 8) nodes[i * 8 + lane] = x;
+}
+#endif
+// one level, one warp per node (device only; the emulator build keeps the thread-per-node path)
+struct HashFoldWarpKernel {
+    static constexpr bool kBarrier = true;
+    HD static void run(const KCtx& cx, uint32_t*, uint32_t* nodes, uint32_t level_size) {
+#ifdef __CUDA_ARCH__
+        const int lane = cx.tid & 31;
+        const uint64_t wid = ((uint64_t)cx.bx * cx.nt + cx.tid) >> 5;
+        if (wid >= level_size) return;
+        const WarpConsts w = wp2_consts(lane);
+        wp2_hash_pair(nodes, (uint64_t)level_size + wid, lane, w);
+#else
+        (void)cx; (void)nodes; (void)level_size;
+#endif
+    }
+};
+// levels top, top/2, ..., 1 in one block of 32 warps
+struct HashFoldWarpTailKernel {
+    static constexpr bool kBarrier = true;
+    HD static void run(const KCtx& cx, uint32_t*, uint32_t* nodes, uint32_t top) {
+#ifdef __CUDA_ARCH__
+        const int lane = cx.tid & 31, warp = cx.tid >> 5, nwarps = cx.nt >> 5;
+        const WarpConsts w = wp2_consts(lane);
+        for (uint32_t level = top; level >= 1; level >>= 1) {
+            for (uint32_t t = warp; t < level; t += nwarps) wp2_hash_pair(nodes, (uint64_t)level + t, lane, w);
+            __threadfence_block();
+            __syncthreads();
+        }
+#else
+        (void)cx; (void)nodes; (void)top;
+#endif
+    }
+};
+
 // poseidon2_mix on n independent states (parity probe for the permutation itself).
 struct PermuteKernel {
     static constexpr bool kBarrier = false;
@@ -236,8 +325,15 @@ struct Merkle {
         const int T = 128;
         dev->launch<HashRowsKernel, 128, 1>((rows + T - 1) / T, 1, T, 0, matrix, col_stride, rows, cols, nodes);
         uint32_t level = rows / 2;
+#ifndef HFB200_EMU
+        // big levels: one thread per node (throughput); <= 4096 nodes: one warp per node (latency); <= 32: one block
+        for (; level > 4096; level >>= 1) dev->launch<HashFoldKernel, 128, 1>((level + T - 1) / T, 1, T, 0, nodes, level);
+        for (; level > 32; level >>= 1) dev->launch<HashFoldWarpKernel, 256, 1>((level * 32 + 255) / 256, 1, 256, 0, nodes, level);
+        if (level >= 1) dev->launch<HashFoldWarpTailKernel, 1024, 1>(1, 1, 1024, 0, nodes, level);
+#else
         for (; level >= 512; level >>= 1) dev->launch<HashFoldKernel, 128, 1>((level + T - 1) / T, 1, T, 0, nodes, level);
         if (level >= 1) dev->launch<HashFoldTailKernel, 256, 1>(1, 1, 256, 0, nodes, level);
+#endif
     }
 };
 
