@@ -191,7 +191,9 @@ struct EvalCheckKernel {
         const CircuitDev& cd = p.cd;
         const uint32_t nc = cd.n_constraints();
         E4* mp = reinterpret_cast<E4*>(sm);
-        for (uint32_t i = cx.tid; i < nc; i += cx.nt) mp[i] = p.mixpow[i];
+        uint16_t* spk = reinterpret_cast<uint16_t*>(mp + nc);  // column picks staged in shared memory: the operand addresses
+        for (uint32_t i = cx.tid; i < nc; i += cx.nt) mp[i] = p.mixpow[i];       // no longer wait on a global load
+        for (uint32_t i = cx.tid; i < 6 * cd.n_free; i += cx.nt) spk[i] = cd.picks[i];
         cx.sync();
         const uint64_t domain = 4ull << p.po2, dmask = domain - 1;
         for (uint32_t rr = cx.tid; rr < p.rows_per_block; rr += cx.nt) {
@@ -201,8 +203,9 @@ struct EvalCheckKernel {
             const uint32_t active = p.ev_code[i], first = p.ev_code[domain + i];
             E4 tot = e4_zero();
             uint32_t j = 0;
+#pragma unroll 4
             for (uint32_t k = 0; k < cd.n_free; k++, j++) {
-                const uint16_t* pk = cd.picks + 6 * k;
+                const uint16_t* pk = spk + 6 * k;
                 const uint32_t e = derived_expr(k, p.ev_data[(uint64_t)pk[0] * domain + i], p.ev_data[(uint64_t)pk[1] * domain + i], p.ev_data[(uint64_t)pk[2] * domain + i],
                                                 p.ev_data[(uint64_t)pk[3] * domain + i], p.ev_data[(uint64_t)pk[4] * domain + ib], p.ev_code[(uint64_t)pk[5] * domain + i]);
                 const uint32_t cv = fmul(active, fsub(p.ev_data[(uint64_t)(cd.n_free + k) * domain + i], e));

@@ -325,7 +325,7 @@ struct Prover {
             for (int s = 0; s < 4; s++) { a.yinv[s] = finv(fsub(y, ONE)); y = fmul(y, w4); }
             a.po2 = po2; a.cd = cd;
             a.rows_per_block = 128;
-            dev.launch<EvalCheckKernel, 128, 1>((unsigned)((D + 127) / 128), 1, 128, (size_t)nc * sizeof(E4), a);
+            dev.launch<EvalCheckKernel, 128, 1>((unsigned)((D + 127) / 128), 1, 128, (size_t)nc * sizeof(E4) + (size_t)6 * cd.n_free * 2 + 16, a);
             dev.sync();  // mp must outlive the copy
         }
         // 4 polys of 4N evaluations -> coefficients (no zk_shift); bit-reversed order makes them 16 polys of N
