@@ -77,6 +77,19 @@ def lib():
         L.orc_prove_segment.argtypes = [C.c_uint32] * 3 + [C.c_uint, vp, vp, vp, C.c_uint64, C.POINTER(vp)]
         L.orc_verify_segment.argtypes = [C.c_uint32] * 3 + [vp, C.c_size_t, vp, vp]
         L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_circuit_new.restype = vp
+        L.orc_circuit_new.argtypes = [C.c_uint32] * 4
+        L.orc_circuit_free.argtypes = [vp]
+        L.orc_circuit_set_ir.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_uint32]
+        L.orc_h_n_taps.restype = C.c_size_t
+        L.orc_h_n_taps.argtypes = [vp]
+        L.orc_h_taps.argtypes = [vp, vp]
+        L.orc_h_gen_data.argtypes = [vp, C.c_uint, vp, vp, C.c_uint64, C.c_uint64, vp]
+        L.orc_h_control_id.argtypes = [vp, C.c_uint, vp]
+        L.orc_h_seal_words_model.restype = C.c_size_t
+        L.orc_h_seal_words_model.argtypes = [vp, C.c_uint]
+        L.orc_h_prove_segment.argtypes = [vp, C.c_uint, vp, vp, vp, C.c_uint64, C.POINTER(vp)]
+        L.orc_h_verify_segment.argtypes = [vp, vp, C.c_size_t, vp, vp]
         _lib = L
     return _lib
 
@@ -184,13 +197,42 @@ def merkle(matrix, want_nodes=False):
 
 
 class Circuit:
-    """The declared synthetic circuit 'synth-rv32im-shape v1' (oracle/circuit.h)."""
+    """The declared synthetic circuit 'synth-rv32im-shape' (oracle/circuit.h): v1 (variant=0) or v2 (variant=1, tap
+    sets {0},{0,1},{0,1,2}).  With `use_ir=True` the constraint polynomial is evaluated by interpreting the PolyStep
+    list built by oracle/synth_ir.py instead of the built-in formula (same field values, different code path)."""
 
-    def __init__(self, w_code=16, w_data=192, w_accum=48):
+    def __init__(self, w_code=16, w_data=192, w_accum=48, variant=0, use_ir=False):
         self.w = (w_code, w_data, w_accum)
+        self.variant = variant
+        self._h = lib().orc_circuit_new(w_code, w_data, w_accum, variant)
+        if not self._h:
+            raise RuntimeError(lib().orc_last_error().decode())
         nt, nm, nc = C.c_uint32(), C.c_uint32(), C.c_uint32()
         _check(lib().orc_circuit_info(*self.w, C.byref(nt), C.byref(nm), C.byref(nc)))
-        self.n_taps, self.n_mix, self.n_constraints = nt.value, nm.value, nc.value
+        self.n_mix, self.n_constraints = nm.value, nc.value
+        self.ir = None
+        if use_ir:
+            from . import synth_ir
+            self.ir = synth_ir.build(self.w, variant)
+            self.set_ir(self.ir["taps"], self.ir["steps"], self.ir["ret"])
+        self.n_taps = lib().orc_h_n_taps(self._h)
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().orc_circuit_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def set_ir(self, taps, steps, ret):
+        taps, steps = _u32(taps), _u32(steps)
+        _check(lib().orc_circuit_set_ir(self._h, _p(taps), taps.size // 3, _p(steps), steps.size // 4, ret))
+
+    def taps(self):
+        out = np.zeros((lib().orc_h_n_taps(self._h), 3), np.uint32)
+        lib().orc_h_taps(self._h, _p(out))
+        return out
 
     def gen_code(self, po2):
         out = np.zeros((self.w[0], 1 << po2), np.uint32)
@@ -204,7 +246,7 @@ class Circuit:
 
     def gen_data(self, po2, code, globals_, trace_seed, blind_seed):
         out = np.zeros((self.w[1], 1 << po2), np.uint32)
-        _check(lib().orc_gen_data(*self.w, po2, _p(code), _p(globals_), trace_seed, blind_seed, _p(out)))
+        _check(lib().orc_h_gen_data(self._h, po2, _p(code), _p(globals_), trace_seed, blind_seed, _p(out)))
         return out
 
     def step_accum(self, po2, data, mix, blind_seed):
@@ -215,17 +257,17 @@ class Circuit:
 
     def control_id(self, po2):
         out = np.zeros(8, np.uint32)
-        _check(lib().orc_control_id(*self.w, po2, _p(out)))
+        _check(lib().orc_h_control_id(self._h, po2, _p(out)))
         return out
 
     def seal_words_model(self, po2):
-        return lib().orc_seal_words_model(*self.w, po2)
+        return lib().orc_h_seal_words_model(self._h, po2)
 
     def prove(self, po2, globals_, code, data, blind_seed):
         """Returns (seal u32 array, checkpoints dict name -> u32 array (ordered), stage times dict)."""
         h = C.c_void_p()
         globals_, code, data = _u32(globals_), _u32(code), _u32(data)
-        _check(lib().orc_prove_segment(*self.w, po2, _p(globals_), _p(code), _p(data), blind_seed, C.byref(h)))
+        _check(lib().orc_h_prove_segment(self._h, po2, _p(globals_), _p(code), _p(data), blind_seed, C.byref(h)))
         try:
             n = lib().orc_proof_seal_words(h)
             seal = np.zeros(n, np.uint32)
@@ -246,5 +288,5 @@ class Circuit:
     def verify(self, seal, code_root):
         seal, code_root = _u32(seal), _u32(code_root)
         po2 = C.c_uint()
-        _check(lib().orc_verify_segment(*self.w, _p(seal), seal.size, _p(code_root), C.byref(po2)))
+        _check(lib().orc_h_verify_segment(self._h, _p(seal), seal.size, _p(code_root), C.byref(po2)))
         return po2.value

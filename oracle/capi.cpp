@@ -118,6 +118,57 @@ size_t orc_seal_words_model(uint32_t wc, uint32_t wd, uint32_t wa, unsigned po2)
     try { Circuit c(wc, wd, wa); return seal_words_model(c, po2); } catch (...) { return 0; }
 }
 
+// ---- handle-based circuit API (variants, user tap sets, constraint polynomial as PolyStep data) ----
+void* orc_circuit_new(uint32_t wc, uint32_t wd, uint32_t wa, uint32_t variant) {
+    try { return new Circuit(wc, wd, wa, variant); } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+void orc_circuit_free(void* h) { delete static_cast<Circuit*>(h); }
+// taps: n_taps triples (group, offset, back) sorted; steps: n_steps quads (op, a, b, c); ret: mix var holding the result
+int orc_circuit_set_ir(void* h, const uint32_t* taps, size_t n_taps, const uint32_t* steps, size_t n_steps, uint32_t ret) {
+    ORC_TRY
+    Circuit* c = static_cast<Circuit*>(h);
+    if (taps) {
+        std::vector<Tap> t(n_taps);
+        for (size_t i = 0; i < n_taps; i++) t[i] = Tap{taps[3 * i], taps[3 * i + 1], taps[3 * i + 2], 0};
+        c->set_taps(t);
+    }
+    std::vector<PolyStep> st(n_steps);
+    for (size_t i = 0; i < n_steps; i++) st[i] = PolyStep{steps[4 * i], steps[4 * i + 1], steps[4 * i + 2], steps[4 * i + 3]};
+    c->set_ir(st, ret);
+    ORC_CATCH
+}
+size_t orc_h_n_taps(void* h) { return static_cast<Circuit*>(h)->taps.size(); }
+void orc_h_taps(void* h, uint32_t* out) {
+    const Circuit* c = static_cast<Circuit*>(h);
+    for (size_t i = 0; i < c->taps.size(); i++) { out[3 * i] = c->taps[i].group; out[3 * i + 1] = c->taps[i].offset; out[3 * i + 2] = c->taps[i].back; }
+}
+int orc_h_gen_data(void* h, unsigned po2, const uint32_t* code, const uint32_t* globals, uint64_t trace_seed, uint64_t blind_seed, uint32_t* data) {
+    ORC_TRY
+    static_cast<Circuit*>(h)->gen_data(reinterpret_cast<Fp*>(data), reinterpret_cast<const Fp*>(code), reinterpret_cast<const Fp*>(globals), po2, trace_seed, blind_seed);
+    ORC_CATCH
+}
+int orc_h_control_id(void* h, unsigned po2, uint32_t* root_out) {
+    ORC_TRY Digest d = control_id(*static_cast<Circuit*>(h), po2); std::memcpy(root_out, d.w, 32); ORC_CATCH
+}
+size_t orc_h_seal_words_model(void* h, unsigned po2) {
+    try { return seal_words_model(*static_cast<Circuit*>(h), po2); } catch (...) { return 0; }
+}
+int orc_h_prove_segment(void* h, unsigned po2, const uint32_t* globals, const uint32_t* code, const uint32_t* data, uint64_t blind_seed, void** handle_out) {
+    ORC_TRY
+    ProofHandle* ph = new ProofHandle();
+    try {
+        ph->proof = prove_segment(*static_cast<Circuit*>(h), po2, reinterpret_cast<const Fp*>(globals), reinterpret_cast<const Fp*>(code),
+                                  reinterpret_cast<const Fp*>(data), blind_seed, &ph->times);
+    } catch (...) { delete ph; throw; }
+    *handle_out = ph;
+    ORC_CATCH
+}
+int orc_h_verify_segment(void* h, const uint32_t* seal, size_t seal_words, const uint32_t* code_root, unsigned* po2_out) {
+    ORC_TRY
+    verify_segment(*static_cast<Circuit*>(h), seal, seal_words, *reinterpret_cast<const Digest*>(code_root), po2_out);
+    ORC_CATCH
+}
+
 // ---- prove / verify ----
 int orc_prove_segment(uint32_t wc, uint32_t wd, uint32_t wa, unsigned po2, const uint32_t* globals, const uint32_t* code,
                       const uint32_t* data, uint64_t blind_seed, void** handle_out) {

@@ -13,6 +13,7 @@
 #pragma once
 #include <vector>
 #include <algorithm>
+#include <tuple>
 #include "merkle_iop.h"
 
 namespace orc {
@@ -42,6 +43,12 @@ static inline Fp blind_value(uint64_t seed, uint32_t group, uint32_t col, uint32
 }
 
 struct Tap { uint32_t group, offset, back, combo; };
+
+// Constraint polynomial as data: upstream's verifier-side representation `risc0_zkp::adapter::PolyExtStepDef`
+// (block of PolyExtStep { Const, Get, GetGlobal, Add, Sub, Mul, True, AndEqz, AndCond } + ret; recollection, crate not
+// vendored).  fp vars and mix vars live in two separate SSA index spaces, every step pushes one value.
+enum PolyOp : uint32_t { OP_CONST = 0, OP_GET = 1, OP_GET_GLOBAL = 2, OP_ADD = 3, OP_SUB = 4, OP_MUL = 5, OP_TRUE = 6, OP_AND_EQZ = 7, OP_AND_COND = 8 };
+struct PolyStep { uint32_t op, a, b, c; };
 struct Reg { uint32_t group, offset, combo, tap_begin, size; };
 
 struct Circuit {
@@ -51,6 +58,9 @@ struct Circuit {
     static constexpr uint32_t N_GLOBAL = 32;
     static constexpr uint32_t CODE_FIXED = 4;  // active, first, last, cycle
     uint64_t code_seed = 0x636F6465ull;
+    uint32_t variant = 0;              // 1 = "synth-rv32im-shape v2": the k%4==1 constraints tap P at back 2 (tap sets {0},{0,1},{0,1,2})
+    std::vector<PolyStep> ir;          // when non-empty, poly() interprets this instead of the built-in formula
+    uint32_t ir_ret = 0;
 
     std::vector<Tap> taps;             // sorted (group, offset, back)
     std::vector<Reg> regs;             // sorted (group, offset)
@@ -59,26 +69,51 @@ struct Circuit {
     uint32_t tot_combo_backs = 0;
     uint32_t group_tap_begin[NUM_GROUPS + 1];
 
-    Circuit(uint32_t wc, uint32_t wd, uint32_t wa) : w_code(wc), w_data(wd), w_accum(wa) {
-        if (wc < CODE_FIXED + 1 || wd < 8 || (wd & 3) || wa < 4 || (wa & 3)) throw std::runtime_error("circuit: unsupported widths");
+    Circuit(uint32_t wc, uint32_t wd, uint32_t wa, uint32_t variant_ = 0) : w_code(wc), w_data(wd), w_accum(wa), variant(variant_) {
+        if (wc < CODE_FIXED + 1 || wd < 8 || (wd & 3) || wa < 4 || (wa & 3) || variant_ > 1) throw std::runtime_error("circuit: unsupported widths");
         n_free = wd / 2; n_prev = n_free / 2; n_chains = wa / 4;
-        combos = {{0}, {0, 1}};
-        combo_begin = {0, 1, 3};
-        tot_combo_backs = 3;
-        auto add_reg = [&](uint32_t g, uint32_t off, bool two) {
-            Reg r{g, off, two ? 1u : 0u, (uint32_t)taps.size(), two ? 2u : 1u};
-            regs.push_back(r);
-            taps.push_back(Tap{g, off, 0, r.combo});
-            if (two) taps.push_back(Tap{g, off, 1, r.combo});
-        };
-        group_tap_begin[GROUP_ACCUM] = 0;
-        for (uint32_t c = 0; c < w_accum; c++) add_reg(GROUP_ACCUM, c, true);
-        group_tap_begin[GROUP_CODE] = (uint32_t)taps.size();
-        for (uint32_t c = 0; c < w_code; c++) add_reg(GROUP_CODE, c, false);
-        group_tap_begin[GROUP_DATA] = (uint32_t)taps.size();
-        for (uint32_t c = 0; c < w_data; c++) add_reg(GROUP_DATA, c, c < n_prev);
-        group_tap_begin[NUM_GROUPS] = (uint32_t)taps.size();
+        std::vector<Tap> t;
+        for (uint32_t c = 0; c < w_accum; c++) { t.push_back(Tap{GROUP_ACCUM, c, 0, 0}); t.push_back(Tap{GROUP_ACCUM, c, 1, 0}); }
+        for (uint32_t c = 0; c < w_code; c++) t.push_back(Tap{GROUP_CODE, c, 0, 0});
+        for (uint32_t c = 0; c < w_data; c++) {
+            t.push_back(Tap{GROUP_DATA, c, 0, 0});
+            if (c < n_prev) { t.push_back(Tap{GROUP_DATA, c, 1, 0}); if (variant) t.push_back(Tap{GROUP_DATA, c, 2, 0}); }
+        }
+        set_taps(t);
     }
+    // Rebuilds registers / combos from a tap list sorted by (group, offset, back) -- the shape of upstream's TapSet.
+    void set_taps(const std::vector<Tap>& user) {
+        taps = user; regs.clear(); combos.clear(); combo_begin.clear();
+        for (size_t i = 1; i < taps.size(); i++) {
+            const Tap &a = taps[i - 1], &b = taps[i];
+            if (std::make_tuple(a.group, a.offset, a.back) >= std::make_tuple(b.group, b.offset, b.back)) throw std::runtime_error("circuit: taps must be strictly sorted by (group, offset, back)");
+        }
+        std::vector<std::vector<uint32_t>> backsets;
+        for (size_t i = 0; i < taps.size();) {
+            if (taps[i].group >= NUM_GROUPS || taps[i].offset >= group_width(taps[i].group)) throw std::runtime_error("circuit: tap out of range");
+            size_t j = i; std::vector<uint32_t> b;
+            while (j < taps.size() && taps[j].group == taps[i].group && taps[j].offset == taps[i].offset) b.push_back(taps[j++].back);
+            regs.push_back(Reg{taps[i].group, taps[i].offset, 0, (uint32_t)i, (uint32_t)(j - i)});
+            backsets.push_back(b);
+            i = j;
+        }
+        combos = backsets;
+        std::sort(combos.begin(), combos.end());
+        combos.erase(std::unique(combos.begin(), combos.end()), combos.end());
+        combo_begin.push_back(0);
+        for (auto& c : combos) combo_begin.push_back(combo_begin.back() + (uint32_t)c.size());
+        tot_combo_backs = combo_begin.back();
+        for (size_t r = 0; r < regs.size(); r++) {
+            regs[r].combo = (uint32_t)(std::lower_bound(combos.begin(), combos.end(), backsets[r]) - combos.begin());
+            for (uint32_t k = 0; k < regs[r].size; k++) taps[regs[r].tap_begin + k].combo = regs[r].combo;
+        }
+        for (uint32_t g = 0; g <= NUM_GROUPS; g++) {
+            uint32_t k = 0;
+            while (k < taps.size() && taps[k].group < g) k++;
+            group_tap_begin[g] = k;
+        }
+    }
+    void set_ir(const std::vector<PolyStep>& steps, uint32_t ret) { ir = steps; ir_ret = ret; }
     uint32_t group_width(uint32_t g) const { return g == GROUP_ACCUM ? w_accum : g == GROUP_CODE ? w_code : w_data; }
     uint32_t n_constraints() const { return n_free + 4 * n_chains + 1; }
     uint32_t n_mix() const { return 4 * n_chains; }
@@ -97,7 +132,7 @@ struct Circuit {
     V derived_expr(uint32_t k, const V& A, const V& B, const V& C, const V& D, const V& Pp, const V& X) const {
         switch (k & 3) {
             case 0: return A * B + C;
-            case 1: return A * B * C + Pp;
+            case 1: return A * B * C + Pp;  // Pp = P at back 1 (variant 0) or back 2 (variant 1), chosen by the caller
             case 2: return (A + X) * B * C * D;
             default: return Pp * B + C * D + X;
         }
@@ -141,7 +176,8 @@ struct Circuit {
             Fp* out = data + (size_t)(n_free + k) * n;
             const Fp *A = data + (size_t)pick_a(k) * n, *B = data + (size_t)pick_b(k) * n, *C = data + (size_t)pick_c(k) * n;
             const Fp *D = data + (size_t)pick_d(k) * n, *Pp = data + (size_t)pick_p(k) * n, *X = code + (size_t)pick_x(k) * n;
-            for (size_t r = 0; r < act; r++) out[r] = derived_expr<Fp>((uint32_t)k, A[r], B[r], C[r], D[r], Pp[(r + n - 1) & (n - 1)], X[r]);
+            const size_t pb = (variant && (k & 3) == 1) ? 2 : 1;
+            for (size_t r = 0; r < act; r++) out[r] = derived_expr<Fp>((uint32_t)k, A[r], B[r], C[r], D[r], Pp[(r + n - pb) & (n - 1)], X[r]);
         }
     }
     // step_accum stand-in: chain r is the running product over active rows of (data[src_r] + mix_r).
@@ -166,14 +202,38 @@ struct Circuit {
     // ---- the constraint polynomial ----
     // V = Fp on the LDE domain (prover, `poly_fp`), V = Fp4 at the DEEP point z (verifier, `poly_ext`).
     // get(group, offset, back) returns the tapped value.  Result = sum_j poly_mix^j * constraint_j.
+    // Interpreter of the PolyStep list (MixState {tot, mul} semantics of upstream's PolyExtStep::step).
+    template <typename V, typename Get>
+    Fp4 poly_ir(const Fp4& poly_mix, const Fp* globals, const Fp* mix, Get get) const {
+        struct MixState { Fp4 tot, mul; };
+        std::vector<V> fp; fp.reserve(ir.size());
+        std::vector<MixState> ms;
+        for (const PolyStep& st : ir) {
+            switch (st.op) {
+                case OP_CONST: fp.push_back(V(Fp::from_u32(st.a))); break;
+                case OP_GET: { const Tap& t = taps.at(st.a); fp.push_back(get(t.group, t.offset, t.back)); break; }
+                case OP_GET_GLOBAL: fp.push_back(V(st.a == 0 ? globals[st.b] : mix[st.b])); break;
+                case OP_ADD: fp.push_back(fp.at(st.a) + fp.at(st.b)); break;
+                case OP_SUB: fp.push_back(fp.at(st.a) - fp.at(st.b)); break;
+                case OP_MUL: fp.push_back(fp.at(st.a) * fp.at(st.b)); break;
+                case OP_TRUE: ms.push_back(MixState{Fp4::zero(), Fp4::one()}); break;
+                case OP_AND_EQZ: { const MixState x = ms.at(st.a); ms.push_back(MixState{x.tot + x.mul * fp.at(st.b), x.mul * poly_mix}); break; }
+                case OP_AND_COND: { const MixState x = ms.at(st.a), in = ms.at(st.c); ms.push_back(MixState{x.tot + (in.tot * x.mul) * fp.at(st.b), x.mul * in.mul}); break; }
+                default: throw std::runtime_error("circuit: bad poly op");
+            }
+        }
+        return ms.at(ir_ret).tot;
+    }
+
     template <typename V, typename Get>
     Fp4 poly(const Fp4& poly_mix, const Fp* globals, const Fp* mix, Get get) const {
+        if (!ir.empty()) return poly_ir<V>(poly_mix, globals, mix, get);
         auto emb = [](Fp f) -> V { return V(f); };
         Fp4 tot = Fp4::zero(), cur = Fp4::one();
         V active = get(GROUP_CODE, 0, 0), first = get(GROUP_CODE, 1, 0);
         for (uint32_t k = 0; k < n_free; k++) {
             V e = derived_expr<V>(k, get(GROUP_DATA, pick_a(k), 0), get(GROUP_DATA, pick_b(k), 0), get(GROUP_DATA, pick_c(k), 0),
-                                  get(GROUP_DATA, pick_d(k), 0), get(GROUP_DATA, pick_p(k), 1), get(GROUP_CODE, pick_x(k), 0));
+                                  get(GROUP_DATA, pick_d(k), 0), get(GROUP_DATA, pick_p(k), (variant && (k & 3) == 1) ? 2 : 1), get(GROUP_CODE, pick_x(k), 0));
             V cv = active * (get(GROUP_DATA, n_free + k, 0) - e);
             tot += cur * cv; cur *= poly_mix;
         }

@@ -289,7 +289,14 @@ void verify_segment(const Circuit& cir, const uint32_t* seal, size_t seal_words,
             eval_u[r.tap_begin + i] = poly_eval(&coeff_u[r.tap_begin], r.size, x);
         }
     }
-    auto get = [&](uint32_t g, uint32_t off, uint32_t back) -> Fp4 { return eval_u[tap_of[g][off] + back]; };
+    std::vector<std::vector<uint32_t>> reg_size(NUM_GROUPS);
+    for (uint32_t g = 0; g < NUM_GROUPS; g++) reg_size[g].assign(cir.group_width(g), 0);
+    for (const Reg& r : cir.regs) reg_size[r.group][r.offset] = r.size;
+    auto get = [&](uint32_t g, uint32_t off, uint32_t back) -> Fp4 {
+        const uint32_t t0 = tap_of[g][off];
+        for (uint32_t k = 0; k < reg_size[g][off]; k++) if (cir.taps[t0 + k].back == back) return eval_u[t0 + k];
+        throw std::runtime_error("verify: constraint polynomial reads a tap that is not in the tap set");
+    };
     Fp4 result = cir.poly<Fp4>(poly_mix, globals, mix.data(), get);
     // check(z) from the 16 check polys evaluated at z^4: check_k(y) = sum_ch y^rev2(ch) * P_{k,ch}(y^4)
     Fp4 check = Fp4::zero();
