@@ -16,7 +16,7 @@ P = 2013265921
 
 # Every symbol include/hfb200.h declares (tests check that the built library exports all of them).
 EXPORTS = [
-    "hfb200_init", "hfb200_destroy", "hfb200_free_error", "hfb200_version", "hfb200_host_alloc", "hfb200_host_free",
+    "hfb200_init", "hfb200_init_ir", "hfb200_destroy", "hfb200_free_error", "hfb200_version", "hfb200_host_alloc", "hfb200_host_free",
     "hfb200_prove_segment", "hfb200_segment_begin", "hfb200_segment_finish", "hfb200_witgen_synth",
     "hfb200_prove_resident", "hfb200_read_group", "hfb200_seal_words", "hfb200_checkpoint", "hfb200_last_stats",
     "hfb200_total_launches", "hfb200_op_interpolate_ntt", "hfb200_op_expand_ntt", "hfb200_op_lde", "hfb200_op_merkle",
@@ -42,6 +42,11 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class CircuitIR(C.Structure):
+    _fields_ = [("w_code", C.c_uint32), ("w_data", C.c_uint32), ("w_accum", C.c_uint32), ("n_mix", C.c_uint32),
+                ("taps", C.c_void_p), ("n_taps", C.c_size_t), ("steps", C.c_void_p), ("n_steps", C.c_size_t), ("ret", C.c_uint32)]
+
+
 class SegmentJob(C.Structure):
     _fields_ = [("po2", C.c_uint32), ("globals", C.c_void_p), ("code", C.c_void_p), ("data", C.c_void_p), ("blind_seed", C.c_uint64),
                 ("seal_out", C.c_void_p), ("seal_cap", C.c_size_t), ("seal_words", C.c_size_t), ("error", C.c_void_p),
@@ -59,6 +64,7 @@ def load_library(path=None):
     err = C.c_void_p  # const char* that we must free ourselves
     sig = {
         "hfb200_init": (err, [C.c_int, u32, C.POINTER(CircuitDesc), C.POINTER(vp)]),
+        "hfb200_init_ir": (err, [C.c_int, u32, C.POINTER(CircuitIR), C.POINTER(vp)]),
         "hfb200_destroy": (None, [vp]),
         "hfb200_free_error": (None, [vp]),
         "hfb200_version": (C.c_char_p, []),
@@ -109,15 +115,22 @@ CHECKPOINT_NAMES = ["globals_hash", "code_root", "data_root", "accum_mix", "accu
 class Context:
     """One hfb200_ctx: one host thread <-> one GPU.  Mirrors upstream's `segment_prover(hashfn)` object."""
 
-    def __init__(self, device=0, max_po2=20, circuit=(16, 192, 48), lib=None):
+    def __init__(self, device=0, max_po2=20, circuit=(16, 192, 48), lib=None, ir=None):
+        """`ir`: optional data-defined circuit {"taps": u32[n,3], "steps": u32[m,4], "ret": int, "n_mix": int} (hfb200_init_ir)."""
         self.lib = lib or load_library()
         self.circuit = tuple(int(x) for x in circuit)
         self.max_po2 = max_po2
-        desc = CircuitDesc(self.circuit[0], self.circuit[1], self.circuit[2], 0)
         h = C.c_void_p()
         self._h = None
         self._po2 = max_po2
-        self._check(self.lib.hfb200_init(device, max_po2, C.byref(desc), C.byref(h)))
+        if ir is not None:
+            taps, steps = _u32(ir["taps"]), _u32(ir["steps"])
+            desc = CircuitIR(self.circuit[0], self.circuit[1], self.circuit[2], int(ir["n_mix"]), taps.ctypes.data, taps.size // 3,
+                             steps.ctypes.data, steps.size // 4, int(ir["ret"]))
+            self._check(self.lib.hfb200_init_ir(device, max_po2, C.byref(desc), C.byref(h)))
+        else:
+            desc = CircuitDesc(self.circuit[0], self.circuit[1], self.circuit[2], 0)
+            self._check(self.lib.hfb200_init(device, max_po2, C.byref(desc), C.byref(h)))
         self._h = h
 
     def _check(self, e):

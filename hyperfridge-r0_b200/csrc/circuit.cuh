@@ -11,6 +11,7 @@
 //   constraints (all gated by `active`, degree <= 5), mixed with successive powers of poly_mix:
 //     F derived, 4*n_chains accum components, 1 global tie  first*(f_0 - global_0)
 #pragma once
+#include <algorithm>
 #include "dev.cuh"
 
 namespace hf {
@@ -262,10 +263,248 @@ struct CircuitHost {
         n_taps = 2 * wa + wc + wd + cd.n_prev;
     }
     void destroy(Dev* dev) { dev->free(tab_mem); tab_mem = nullptr; }
+    // widths only (data-defined circuit: taps / constraints live in GenericCircuitHost)
+    uint32_t n_mix_data = 0;
+    bool builtin = true;
+    void init_widths(uint32_t wc, uint32_t wd, uint32_t wa, uint32_t n_taps_, uint32_t n_mix_) {
+        cd = CircuitDev{};
+        cd.w_code = wc; cd.w_data = wd; cd.w_accum = wa;
+        n_taps = n_taps_; n_mix_data = n_mix_; builtin = false;
+    }
     uint32_t group_width(int g) const { return g == GROUP_ACCUM ? cd.w_accum : g == GROUP_CODE ? cd.w_code : cd.w_data; }
     uint32_t group_back1(int g) const { return g == GROUP_ACCUM ? cd.w_accum : g == GROUP_CODE ? 0u : cd.n_prev; }
     uint32_t n_regs() const { return cd.w_accum + cd.w_code + cd.w_data; }
-    uint32_t n_mix() const { return 4 * cd.n_chains; }
+    uint32_t n_mix() const { return builtin ? 4 * cd.n_chains : n_mix_data; }
+};
+
+}  // namespace hf
+
+// =====================================================================================================================
+// Circuit as DATA: the plug-in form of SURVEY.md section 8b (`hfb200_circuit_register`): a tap table (upstream TapSet:
+// sorted (group, offset, back)) and the constraint polynomial as a step list in the shape of upstream's
+// `risc0_zkp::adapter::PolyExtStepDef` (Const / Get / GetGlobal / Add / Sub / Mul / True / AndEqz / AndCond).  Upstream
+// turns that IR into generated C++/CUDA for the prover; here the host compiles it once into a register-machine bytecode
+// (SSA values -> reusable slots by last-use analysis; the `mul` of every MixState is a static power of poly_mix, so only
+// `tot` lives at run time) and one interpreter kernel evaluates it per LDE row.  witgen / step_accum of a data-defined
+// circuit stay with the caller (two-phase API: segment_begin -> mix -> caller's accum -> segment_finish).
+// =====================================================================================================================
+namespace hf {
+
+enum : uint32_t { IR_CONST = 0, IR_GET = 1, IR_GET_GLOBAL = 2, IR_ADD = 3, IR_SUB = 4, IR_MUL = 5, IR_TRUE = 6, IR_AND_EQZ = 7, IR_AND_COND = 8 };
+struct IrStep { uint32_t op, a, b, c; };
+struct IrTap { uint32_t group, offset, back; };
+
+enum : uint16_t { BC_CONST = 0, BC_GET, BC_GETG, BC_ADD, BC_SUB, BC_MUL, BC_MTRUE, BC_MEQZ, BC_MCOND };
+struct BcIns { uint16_t op, dst; uint32_t a, b, c; };  // 16 bytes
+
+static constexpr uint32_t GEN_MAX_BACKS = 4;   // distinct `back` values over the whole tap set
+static constexpr uint32_t GEN_MAX_COMBOS = 8;  // distinct per-register back sets
+
+struct GenReg { uint32_t group, offset, combo, tap_begin, size; };
+
+struct GenericCircuitHost {
+    bool active = false;
+    uint32_t w[3] = {0, 0, 0};  // accum, code, data
+    uint32_t n_mix = 0;
+    std::vector<IrTap> taps;
+    std::vector<GenReg> regs;
+    std::vector<std::vector<uint32_t>> combos;
+    std::vector<uint32_t> combo_begin;
+    std::vector<uint32_t> backs;             // distinct back values, sorted (slot s <-> backs[s])
+    std::vector<BcIns> prog;
+    uint32_t n_fp_slots = 0, n_mix_slots = 0, ret_slot = 0, n_mixpow = 0;
+    // device copies
+    BcIns* d_prog = nullptr;
+    uint8_t* d_colmask[3] = {nullptr, nullptr, nullptr};  // per column: bit s set <=> tapped at backs[s]
+    uint8_t* d_regcombo = nullptr;                         // per register (taps order)
+    uint32_t* d_regcol = nullptr;                          // per register: group << 28 | offset
+
+    uint32_t back_slot(uint32_t back) const { for (uint32_t s = 0; s < backs.size(); s++) if (backs[s] == back) return s; throw Err("circuit: unknown back"); }
+
+    void init(Dev* dev, uint32_t wc, uint32_t wd, uint32_t wa, uint32_t n_mix_, const IrTap* tp, size_t n_taps, const IrStep* st, size_t n_steps, uint32_t ret) {
+        if (!tp || !st || n_taps == 0 || n_steps == 0) throw Err("circuit: empty tap table or step list");
+        w[GROUP_ACCUM] = wa; w[GROUP_CODE] = wc; w[GROUP_DATA] = wd; n_mix = n_mix_;
+        if (wc == 0 || wd == 0 || wa == 0 || wc > 65535 || wd > 65535 || wa > 65535) throw Err("circuit: bad group widths");
+        taps.assign(tp, tp + n_taps);
+        std::vector<std::vector<uint32_t>> backsets;
+        for (size_t i = 0; i < taps.size();) {
+            if (taps[i].group > 2 || taps[i].offset >= w[taps[i].group]) throw Err("circuit: tap out of range");
+            size_t j = i; std::vector<uint32_t> b;
+            while (j < taps.size() && taps[j].group == taps[i].group && taps[j].offset == taps[i].offset) {
+                if (j > i && taps[j].back <= taps[j - 1].back) throw Err("circuit: taps must be sorted by (group, offset, back)");
+                b.push_back(taps[j++].back);
+            }
+            if (j < taps.size() && (taps[j].group < taps[i].group || (taps[j].group == taps[i].group && taps[j].offset < taps[i].offset))) throw Err("circuit: taps must be sorted by (group, offset, back)");
+            if (b.size() > 4) throw Err("circuit: more than 4 taps on one register");
+            regs.push_back(GenReg{taps[i].group, taps[i].offset, 0, (uint32_t)i, (uint32_t)(j - i)});
+            backsets.push_back(b);
+            for (uint32_t x : b) if (std::find(backs.begin(), backs.end(), x) == backs.end()) backs.push_back(x);
+            i = j;
+        }
+        std::sort(backs.begin(), backs.end());
+        if (backs.size() > GEN_MAX_BACKS) throw Err("circuit: more than 4 distinct back values");
+        if (backs.back() >= 1024) throw Err("circuit: back too large");
+        combos = backsets;
+        std::sort(combos.begin(), combos.end());
+        combos.erase(std::unique(combos.begin(), combos.end()), combos.end());
+        if (combos.size() > GEN_MAX_COMBOS) throw Err("circuit: more than 8 distinct tap sets");
+        combo_begin.assign(1, 0);
+        for (auto& c : combos) combo_begin.push_back(combo_begin.back() + (uint32_t)c.size());
+        for (size_t r = 0; r < regs.size(); r++) regs[r].combo = (uint32_t)(std::lower_bound(combos.begin(), combos.end(), backsets[r]) - combos.begin());
+        compile(st, n_steps, ret);
+        // device tables
+        d_prog = (BcIns*)dev->alloc(prog.size() * sizeof(BcIns));
+        dev->h2d(d_prog, prog.data(), prog.size() * sizeof(BcIns));
+        for (int g = 0; g < 3; g++) {
+            std::vector<uint8_t> m(w[g], 0);
+            for (const IrTap& t : taps) if ((int)t.group == g) m[t.offset] |= (uint8_t)(1u << back_slot(t.back));
+            d_colmask[g] = (uint8_t*)dev->alloc(m.size());
+            dev->h2d(d_colmask[g], m.data(), m.size());
+        }
+        std::vector<uint8_t> rc(regs.size());
+        std::vector<uint32_t> rcol(regs.size());
+        for (size_t r = 0; r < regs.size(); r++) { rc[r] = (uint8_t)regs[r].combo; rcol[r] = (regs[r].group << 28) | regs[r].offset; }
+        d_regcombo = (uint8_t*)dev->alloc(rc.size());
+        dev->h2d(d_regcombo, rc.data(), rc.size());
+        d_regcol = (uint32_t*)dev->alloc(rcol.size() * 4);
+        dev->h2d(d_regcol, rcol.data(), rcol.size() * 4);
+        dev->sync();
+        active = true;
+    }
+    void destroy(Dev* dev) {
+        if (!active) return;
+        dev->free(d_prog); for (auto& p : d_colmask) dev->free(p);
+        dev->free(d_regcombo); dev->free(d_regcol);
+        active = false;
+    }
+
+    // SSA step list -> slot-allocated bytecode.
+    void compile(const IrStep* st, size_t n, uint32_t ret) {
+        std::vector<int> is_fp(n);                 // 1: pushes an fp var, 0: pushes a mix var
+        std::vector<uint32_t> fp_of, mix_of;       // var index -> step index
+        for (size_t i = 0; i < n; i++) {
+            if (st[i].op > IR_AND_COND) throw Err("circuit: bad poly op");
+            is_fp[i] = st[i].op <= IR_MUL;
+            (is_fp[i] ? fp_of : mix_of).push_back((uint32_t)i);
+        }
+        if (ret >= mix_of.size()) throw Err("circuit: ret is not a mix var");
+        auto chk_fp = [&](uint32_t v, size_t at) { if (v >= fp_of.size() || fp_of[v] >= at) throw Err("circuit: fp operand used before definition"); };
+        auto chk_mx = [&](uint32_t v, size_t at) { if (v >= mix_of.size() || mix_of[v] >= at) throw Err("circuit: mix operand used before definition"); };
+        std::vector<size_t> fp_last(fp_of.size(), 0), mix_last(mix_of.size(), 0);
+        std::vector<uint32_t> mix_exp(mix_of.size(), 0);
+        size_t nm = 0;
+        for (size_t i = 0; i < n; i++) {
+            const IrStep& s = st[i];
+            switch (s.op) {
+                case IR_ADD: case IR_SUB: case IR_MUL: chk_fp(s.a, i); chk_fp(s.b, i); fp_last[s.a] = i; fp_last[s.b] = i; break;
+                case IR_GET: if (s.a >= taps.size()) throw Err("circuit: Get of an unknown tap"); break;
+                case IR_GET_GLOBAL: if (s.a > 1 || s.b >= (s.a == 0 ? N_GLOBAL : n_mix)) throw Err("circuit: GetGlobal out of range"); break;
+                case IR_TRUE: mix_exp[nm++] = 0; break;
+                case IR_AND_EQZ: chk_mx(s.a, i); chk_fp(s.b, i); mix_last[s.a] = i; fp_last[s.b] = i; mix_exp[nm] = mix_exp[s.a] + 1; nm++; break;
+                case IR_AND_COND: chk_mx(s.a, i); chk_fp(s.b, i); chk_mx(s.c, i); mix_last[s.a] = i; mix_last[s.c] = i; fp_last[s.b] = i;
+                                  mix_exp[nm] = mix_exp[s.a] + mix_exp[s.c]; nm++; break;
+                default: break;
+            }
+        }
+        mix_last[ret] = n;  // live to the end
+        n_mixpow = 0;
+        for (uint32_t e : mix_exp) if (e + 1 > n_mixpow) n_mixpow = e + 1;
+        std::vector<uint32_t> fp_slot(fp_of.size()), mix_slot(mix_of.size());
+        std::vector<uint32_t> fp_free, mix_free;
+        uint32_t fp_hi = 0, mix_hi = 0, nf = 0; nm = 0;
+        auto take = [](std::vector<uint32_t>& fr, uint32_t& hi) { if (!fr.empty()) { uint32_t s = fr.back(); fr.pop_back(); return s; } return hi++; };
+        prog.clear();
+        for (size_t i = 0; i < n; i++) {
+            const IrStep& s = st[i];
+            BcIns ins{};
+            std::vector<uint32_t> rel_fp, rel_mix;
+            auto use_fp = [&](uint32_t v) { if (fp_last[v] == i) rel_fp.push_back(fp_slot[v]); return fp_slot[v]; };
+            auto use_mx = [&](uint32_t v) { if (mix_last[v] == i) rel_mix.push_back(mix_slot[v]); return mix_slot[v]; };
+            switch (s.op) {
+                case IR_CONST: ins.op = BC_CONST; ins.a = to_mont(s.a % P); break;
+                case IR_GET: ins.op = BC_GET; ins.a = taps[s.a].group; ins.b = taps[s.a].offset; ins.c = taps[s.a].back; break;
+                case IR_GET_GLOBAL: ins.op = BC_GETG; ins.a = s.a; ins.b = s.b; break;
+                case IR_ADD: ins.op = BC_ADD; ins.a = use_fp(s.a); ins.b = use_fp(s.b); break;
+                case IR_SUB: ins.op = BC_SUB; ins.a = use_fp(s.a); ins.b = use_fp(s.b); break;
+                case IR_MUL: ins.op = BC_MUL; ins.a = use_fp(s.a); ins.b = use_fp(s.b); break;
+                case IR_TRUE: ins.op = BC_MTRUE; break;
+                case IR_AND_EQZ: ins.op = BC_MEQZ; ins.a = use_mx(s.a); ins.b = use_fp(s.b); ins.c = mix_exp[s.a]; break;
+                case IR_AND_COND: ins.op = BC_MCOND; ins.a = use_mx(s.a); ins.b = use_fp(s.b) | (use_mx(s.c) << 16); ins.c = mix_exp[s.a]; break;
+            }
+            // operands whose last use is here are released BEFORE the destination is allocated (dst may reuse them:
+            // the interpreter reads all operands before it writes)
+            std::sort(rel_fp.begin(), rel_fp.end()); rel_fp.erase(std::unique(rel_fp.begin(), rel_fp.end()), rel_fp.end());
+            std::sort(rel_mix.begin(), rel_mix.end()); rel_mix.erase(std::unique(rel_mix.begin(), rel_mix.end()), rel_mix.end());
+            for (uint32_t x : rel_fp) fp_free.push_back(x);
+            for (uint32_t x : rel_mix) mix_free.push_back(x);
+            if (is_fp[i]) {
+                const uint32_t slot = take(fp_free, fp_hi);
+                fp_slot[nf] = slot; ins.dst = (uint16_t)slot;
+                if (fp_last[nf] == 0 || fp_last[nf] <= i) fp_free.push_back(slot);  // never used: slot is free again at once
+                nf++;
+            } else {
+                const uint32_t slot = take(mix_free, mix_hi);
+                mix_slot[nm] = slot; ins.dst = (uint16_t)slot;
+                if (mix_last[nm] <= i && nm != ret) mix_free.push_back(slot);
+                nm++;
+            }
+            if (fp_hi > 4096 || mix_hi > 4096) throw Err("circuit: too many live values");
+            prog.push_back(ins);
+        }
+        n_fp_slots = fp_hi ? fp_hi : 1; n_mix_slots = mix_hi ? mix_hi : 1; ret_slot = mix_slot[ret];
+    }
+};
+
+struct GenEvalArgs {
+    const uint32_t* ev[3];   // accum, code, data LDEs [w][domain]
+    uint32_t* check;         // [4][domain]
+    const BcIns* prog; uint32_t n_ins;
+    const E4* mixpow;        // poly_mix^k, k < n_mixpow (device)
+    const uint32_t* mix;     // accum mix (device)
+    const uint32_t* globals; // device copy of the 32 globals
+    uint32_t n_mix;
+    uint32_t yinv[4];
+    uint32_t po2, rows_per_block, n_fp_slots, n_mix_slots, ret_slot;
+};
+// One thread per LDE row; fp slots [slot][row] and mix slots in shared memory; the program is read uniformly.
+struct GenEvalCheckKernel {
+    static constexpr bool kBarrier = true;
+    HD static void run(const KCtx& cx, uint32_t* sm, GenEvalArgs p) {
+        const uint32_t R = p.rows_per_block;
+        E4* mslot = reinterpret_cast<E4*>(sm);                                   // [n_mix_slots][R]
+        uint32_t* fslot = reinterpret_cast<uint32_t*>(mslot + (size_t)p.n_mix_slots * R);  // [n_fp_slots][R]
+        uint32_t* gl = fslot + (size_t)p.n_fp_slots * R;                          // globals then mix
+        for (uint32_t i = cx.tid; i < N_GLOBAL; i += cx.nt) gl[i] = p.globals[i];
+        for (uint32_t i = cx.tid; i < p.n_mix; i += cx.nt) gl[N_GLOBAL + i] = p.mix[i];
+        cx.sync();
+        const uint64_t domain = 4ull << p.po2, dmask = domain - 1;
+        for (uint32_t rr = cx.tid; rr < R; rr += cx.nt) {
+            const uint64_t i = (uint64_t)cx.bx * R + rr;
+            if (i >= domain) break;
+            for (uint32_t pc = 0; pc < p.n_ins; pc++) {
+                const BcIns ins = p.prog[pc];
+                switch (ins.op) {
+                    case BC_CONST: fslot[ins.dst * R + rr] = ins.a; break;
+                    case BC_GET: fslot[ins.dst * R + rr] = p.ev[ins.a][(uint64_t)ins.b * domain + ((i + domain - 4ull * ins.c) & dmask)]; break;
+                    case BC_GETG: fslot[ins.dst * R + rr] = gl[ins.a == 0 ? ins.b : N_GLOBAL + ins.b]; break;
+                    case BC_ADD: fslot[ins.dst * R + rr] = fadd(fslot[ins.a * R + rr], fslot[ins.b * R + rr]); break;
+                    case BC_SUB: fslot[ins.dst * R + rr] = fsub(fslot[ins.a * R + rr], fslot[ins.b * R + rr]); break;
+                    case BC_MUL: fslot[ins.dst * R + rr] = fmul(fslot[ins.a * R + rr], fslot[ins.b * R + rr]); break;
+                    case BC_MTRUE: mslot[ins.dst * R + rr] = e4_zero(); break;
+                    case BC_MEQZ: mslot[ins.dst * R + rr] = e4_add(mslot[ins.a * R + rr], e4_scale(p.mixpow[ins.c], fslot[ins.b * R + rr])); break;
+                    default: {  // BC_MCOND: tot = x.tot + cond * inner.tot * mix^k
+                        const E4 inner = mslot[(ins.b >> 16) * R + rr];
+                        const uint32_t cond = fslot[(ins.b & 0xFFFFu) * R + rr];
+                        mslot[ins.dst * R + rr] = e4_add(mslot[ins.a * R + rr], e4_scale(e4_mul(inner, p.mixpow[ins.c]), cond));
+                        break;
+                    }
+                }
+            }
+            const E4 tot = mslot[p.ret_slot * R + rr];
+            const uint32_t yi = p.yinv[i & 3];
+            for (int k = 0; k < 4; k++) p.check[(uint64_t)k * domain + i] = fmul(tot.c[k], yi);
+        }
+    }
 };
 
 }  // namespace hf

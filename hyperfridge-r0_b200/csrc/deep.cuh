@@ -11,6 +11,7 @@
 // Field arithmetic is exact, so the seal is bit-identical to the coefficient-space formulation.
 #pragma once
 #include "ntt.cuh"
+#include "circuit.cuh"
 
 namespace hf {
 
@@ -215,6 +216,116 @@ struct OpenKernel {  // grid.x = descriptors
             const uint64_t i = ((uint64_t)d.idx + d.rows) >> s;
             o[w] = d.nodes[(i ^ 1) * 8 + (w & 7)];
         }
+    }
+};
+
+}  // namespace hf
+
+// ---- DEEP kernels for data-defined circuits: arbitrary tap sets (<= 4 distinct backs, <= 8 distinct back-sets) -------
+namespace hf {
+
+static constexpr uint32_t DOTG_T = 128;
+struct Backs4 { uint32_t nb; uint32_t back[GEN_MAX_BACKS]; };
+
+// partial[((col * nblk + blk) * 4) + s] = sum over the block's rows of cols[col][r] * Wt[(r + back[s]) mod n]
+// for every slot s whose bit is set in colmask[col].
+struct DotKernelG {
+    static constexpr bool kBarrier = true;
+    HD static void run(const KCtx& cx, uint32_t* sm, const uint32_t* cols, uint64_t col_stride, uint32_t ncols, const uint8_t* colmask, Backs4 bk,
+                       const E4* Wt, uint32_t po2, E4* partial) {
+        const uint64_t n = 1ull << po2;
+        const uint32_t nblk = cx.gx, c0 = cx.by * DOT_CPB;
+        const uint64_t row0 = (uint64_t)cx.bx * DOT_RPB;
+        E4* red = reinterpret_cast<E4*>(sm);  // [DOTG_T][DOT_CPB * 4]
+        for (uint32_t it = cx.tid; it < DOTG_T; it += cx.nt) {
+            E4 acc[DOT_CPB][GEN_MAX_BACKS];
+            uint32_t mask[DOT_CPB];
+            for (uint32_t c = 0; c < DOT_CPB; c++) {
+                mask[c] = c0 + c < ncols ? colmask[c0 + c] : 0u;
+                for (uint32_t s = 0; s < GEN_MAX_BACKS; s++) acc[c][s] = e4_zero();
+            }
+            for (uint64_t r = row0 + it; r < row0 + DOT_RPB && r < n; r += DOTG_T) {
+                E4 w[GEN_MAX_BACKS];
+#pragma unroll
+                for (uint32_t s = 0; s < GEN_MAX_BACKS; s++) w[s] = s < bk.nb ? Wt[(r + bk.back[s]) & (n - 1)] : e4_zero();
+#pragma unroll
+                for (uint32_t c = 0; c < DOT_CPB; c++) {
+                    if (c0 + c >= ncols) break;
+                    const uint32_t t = cols[(uint64_t)(c0 + c) * col_stride + r];
+#pragma unroll
+                    for (uint32_t s = 0; s < GEN_MAX_BACKS; s++)
+                        if ((mask[c] >> s) & 1u) acc[c][s] = e4_add(acc[c][s], e4_scale(w[s], t));
+                }
+            }
+            for (uint32_t c = 0; c < DOT_CPB; c++)
+                for (uint32_t s = 0; s < GEN_MAX_BACKS; s++) red[(it * DOT_CPB + c) * GEN_MAX_BACKS + s] = acc[c][s];
+        }
+        cx.sync();
+        const uint32_t K = DOT_CPB * GEN_MAX_BACKS;
+        for (uint32_t stride = DOTG_T / 2; stride >= 1; stride >>= 1) {
+            for (uint32_t w = cx.tid; w < stride * K; w += cx.nt) {
+                const uint32_t it = w / K, k = w % K;
+                red[it * K + k] = e4_add(red[it * K + k], red[(it + stride) * K + k]);
+            }
+            cx.sync();
+        }
+        for (uint32_t k = cx.tid; k < K; k += cx.nt) {
+            const uint32_t c = k / GEN_MAX_BACKS, s = k % GEN_MAX_BACKS;
+            if (c0 + c < ncols) partial[((uint64_t)(c0 + c) * nblk + cx.bx) * GEN_MAX_BACKS + s] = red[k];
+        }
+    }
+};
+struct DotReduceKernelG {  // out[col * 4 + s] = sum_blk partial[(col * nblk + blk) * 4 + s]
+    static constexpr bool kBarrier = false;
+    HD static void run(const KCtx& cx, uint32_t*, const E4* partial, uint32_t ncols, uint32_t nblk, E4* out) {
+        const uint64_t t = (uint64_t)cx.bx * cx.nt + cx.tid;
+        if (t >= (uint64_t)ncols * GEN_MAX_BACKS) return;
+        const uint32_t col = (uint32_t)(t / GEN_MAX_BACKS), s = (uint32_t)(t % GEN_MAX_BACKS);
+        E4 acc = e4_zero();
+        for (uint32_t k = 0; k < nblk; k++) acc = e4_add(acc, partial[((uint64_t)col * nblk + k) * GEN_MAX_BACKS + s]);
+        out[t] = acc;
+    }
+};
+
+struct DeepMixGArgs {
+    const uint32_t* tr[3];     // accum, code, data traces [w][n]
+    const uint32_t* regcol;    // registers sorted by combo: group << 28 | offset
+    const E4* regmix;          // their mix powers, same order
+    uint32_t combo_start[GEN_MAX_COMBOS + 1];
+    uint32_t n_combos;
+    uint32_t combo_nb[GEN_MAX_COMBOS];
+    uint32_t combo_back[GEN_MAX_COMBOS][GEN_MAX_BACKS];   // back values of the combo
+    uint32_t combo_fb[GEN_MAX_COMBOS][GEN_MAX_BACKS];     // -3 w^back (Montgomery): 1/(y_i - z w^-b) = fb * INV[(i + b) mod n]
+    E4 U[GEN_MAX_COMBOS][GEN_MAX_BACKS];                  // combo_u: U_c(y) = sum_k U[c][k] y^k
+    E4 Vc;
+    const uint32_t* S; const E4 *INV, *INV4; uint32_t* out;
+    uint32_t po2;
+    RootTables rt;
+};
+struct DeepMixKernelG {
+    static constexpr bool kBarrier = false;
+    HD static void run(const KCtx& cx, uint32_t*, DeepMixGArgs p) {
+        const uint64_t n = 1ull << p.po2;
+        const uint64_t i = (uint64_t)cx.bx * cx.nt + cx.tid;
+        if (i >= n) return;
+        const uint32_t w = tab_pow(p.rt.f_lo, p.rt.f_hi, (uint32_t)(i << (24 - p.po2)));
+        const uint32_t y = fmul(w, INV3);
+        E4 r = e4_zero();
+        for (uint32_t c = 0; c < p.n_combos; c++) {
+            E4 tot = e4_zero();
+            for (uint32_t k = p.combo_start[c]; k < p.combo_start[c + 1]; k++) {
+                const uint32_t rc = p.regcol[k];
+                tot = e4_add(tot, e4_scale(p.regmix[k], p.tr[rc >> 28][(uint64_t)(rc & 0x0FFFFFFFu) * n + i]));
+            }
+            E4 u = e4_zero();
+            for (uint32_t k = p.combo_nb[c]; k-- > 0;) u = e4_add(e4_scale(u, y), p.U[c][k]);
+            E4 q = e4_sub(tot, u);
+            for (uint32_t k = 0; k < p.combo_nb[c]; k++) q = e4_scale(e4_mul(q, p.INV[(i + p.combo_back[c][k]) & (n - 1)]), p.combo_fb[c][k]);
+            r = e4_add(r, q);
+        }
+        const E4 s = e4(p.S[i], p.S[n + i], p.S[2 * n + i], p.S[3 * n + i]);
+        r = e4_add(r, e4_mul(e4_sub(s, p.Vc), p.INV4[i]));
+        for (int k = 0; k < 4; k++) p.out[(uint64_t)k * n + i] = r.c[k];
     }
 };
 

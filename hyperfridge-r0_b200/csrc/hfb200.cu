@@ -48,6 +48,19 @@ const char* hfb200_init(int device, uint32_t max_po2, const hfb200_circuit_desc*
     *out = ctx;
     API_CATCH
 }
+const char* hfb200_init_ir(int device, uint32_t max_po2, const hfb200_circuit_ir* c, hfb200_ctx** out) {
+    API_TRY
+    if (!out || !c) throw Err("hfb200_init_ir: NULL argument");
+    *out = nullptr;
+    static_assert(sizeof(hfb200_tap) == sizeof(IrTap) && sizeof(hfb200_poly_step) == sizeof(IrStep), "IR layouts must match");
+    hfb200_ctx* ctx = new hfb200_ctx();
+    try {
+        ctx->p.init(device, max_po2, c->w_code, c->w_data, c->w_accum, reinterpret_cast<const IrTap*>(c->taps), c->n_taps,
+                    reinterpret_cast<const IrStep*>(c->steps), c->n_steps, c->ret, c->n_mix);
+    } catch (...) { delete ctx; throw; }
+    *out = ctx;
+    API_CATCH
+}
 void hfb200_destroy(hfb200_ctx* ctx) {
     if (!ctx) return;
     try { ctx->p.destroy(); } catch (...) {}

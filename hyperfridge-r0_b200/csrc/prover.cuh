@@ -50,6 +50,7 @@ struct Prover {
     Ntt ntt;
     Merkle merkle;
     CircuitHost cir;
+    GenericCircuitHost gen;  // active for data-defined circuits (hfb200_init_ir)
     uint32_t max_po2 = 0;
     int device_id = 0;
     Arena arena;
@@ -85,7 +86,8 @@ struct Prover {
 #endif
     float stage_ms[8] = {0};
 
-    void init(int device, uint32_t max_po2_, uint32_t wc, uint32_t wd, uint32_t wa) {
+    void init(int device, uint32_t max_po2_, uint32_t wc, uint32_t wd, uint32_t wa, const IrTap* taps = nullptr, size_t n_taps = 0,
+              const IrStep* steps = nullptr, size_t n_steps = 0, uint32_t ret = 0, uint32_t n_mix_ir = 0) {
         if (max_po2_ < 12 || max_po2_ > 22) throw Err("max_po2 must be in [12, 22]");
         max_po2 = max_po2_;
 #ifndef HFB200_EMU
@@ -109,13 +111,19 @@ struct Prover {
 #endif
         ntt.init(&dev);
         merkle.init(&dev);
-        cir.init(&dev, wc, wd, wa);
+        if (taps) {
+            gen.init(&dev, wc, wd, wa, n_mix_ir, taps, n_taps, steps, n_steps, ret);
+            cir.init_widths(wc, wd, wa, (uint32_t)gen.taps.size(), n_mix_ir);
+        } else {
+            cir.init(&dev, wc, wd, wa);
+        }
         arena.cap = arena_bytes(max_po2);
         arena.base = (uint8_t*)dev.alloc(arena.cap);
         if (const char* env = std::getenv("HFB200_DEBUG_CHECKPOINTS")) debug_checkpoints = std::atoi(env) != 0;
     }
     void destroy() {
         dev.free(arena.base);
+        gen.destroy(&dev);
         cir.destroy(&dev);
         ntt.destroy();
 #ifndef HFB200_EMU
@@ -131,7 +139,7 @@ struct Prover {
         const size_t N = (size_t)1 << p, W = cir.n_regs();
         // traces W*N, LDE (W+16)*4N, trees 4 * 2*4N*8, scratch wd*N, check 16N, E4 side arrays, FRI (< 40N), slack
         size_t words = W * N + (W + 16) * 4 * N + 4 * 64 * N + (size_t)cir.cd.w_data * N + 16 * N + 8 * 4 * N + 48 * N;
-        words += (W + 16) * ((N + DOT_RPB - 1) / DOT_RPB) * 8 + (1u << 20);
+        words += (W + 16) * ((N + DOT_RPB - 1) / DOT_RPB) * 16 + (1u << 20);
         return words * 4 + (64u << 20);
     }
 
@@ -288,6 +296,35 @@ struct Prover {
         arena.off = save;  // stream order makes reuse by later kernels safe
     }
 
+    void dot_group_g(const uint32_t* cols, uint32_t w, const uint8_t* colmask, const Backs4& bk, const E4* Wt, E4* out_dev) {
+        const size_t N = (size_t)1 << po2;
+        const uint32_t nblk = (uint32_t)((N + DOT_RPB - 1) / DOT_RPB);
+        const size_t save = arena.off;
+        E4* partial = arena.take<E4>((size_t)w * nblk * GEN_MAX_BACKS);
+        dev.launch<DotKernelG, 128, 1>(nblk, (w + DOT_CPB - 1) / DOT_CPB, DOTG_T, (size_t)DOTG_T * DOT_CPB * GEN_MAX_BACKS * sizeof(E4), cols, (uint64_t)N, w, colmask, bk, Wt, po2, partial);
+        dev.launch<DotReduceKernelG, 128, 1>((GEN_MAX_BACKS * w + 127) / 128, 1, 128, 0, (const E4*)partial, w, nblk, out_dev);
+        arena.off = save;
+    }
+    // coefficients (low to high) of the polynomial of degree < n through (xs[i], ys[i]), n <= 4
+    static void lagrange_e4(E4* out, const E4* xs, const E4* ys, uint32_t n) {
+        for (uint32_t i = 0; i < n; i++) out[i] = e4_zero();
+        for (uint32_t i = 0; i < n; i++) {
+            E4 b[5]; uint32_t nb = 1; b[0] = e4_one();
+            E4 den = e4_one();
+            for (uint32_t j = 0; j < n; j++) {
+                if (j == i) continue;
+                E4 nbuf[5];
+                for (uint32_t k = 0; k <= nb; k++) nbuf[k] = e4_zero();
+                for (uint32_t k = 0; k < nb; k++) { nbuf[k + 1] = e4_add(nbuf[k + 1], b[k]); nbuf[k] = e4_sub(nbuf[k], e4_mul(b[k], xs[j])); }
+                nb++;
+                for (uint32_t k = 0; k < nb; k++) b[k] = nbuf[k];
+                den = e4_mul(den, e4_sub(xs[i], xs[j]));
+            }
+            const E4 sc = e4_mul(ys[i], e4_inv(den));
+            for (uint32_t k = 0; k < nb; k++) out[k] = e4_add(out[k], e4_mul(b[k], sc));
+        }
+    }
+
     // ---- phase 2: ACCUM commit, check polynomial, DEEP, FRI, queries ----
     void finish(const uint32_t* accum_h, std::vector<uint32_t>& seal_out) {
         if (!begun) throw Err("segment_finish without segment_begin");
@@ -300,6 +337,7 @@ struct Prover {
         mark(5);
         dev.h2d(d_mix, mix.data(), mix.size() * 4);
         if (accum_h) dev.h2d(tr[GROUP_ACCUM], accum_h, (size_t)cd.w_accum * N * 4);
+        else if (gen.active) throw Err("data-defined circuit: step_accum is the caller's (pass the accum columns to hfb200_segment_finish)");
         else step_accum();
         mark(6);
         commit_group(GROUP_ACCUM, "accum_root", 6, 7, 8);  // ends with a stream sync: events 5..8 are complete
@@ -310,7 +348,34 @@ struct Prover {
         // ---- check polynomial ----
         const E4 poly_mix = rng.random_ext();
         cp_add("poly_mix", poly_mix);
+        uint32_t yinv4[4];
         {
+            const uint32_t three_n = fpow(THREE, N), w4 = rou_fwd(2);
+            uint32_t y = three_n;
+            for (int s = 0; s < 4; s++) { yinv4[s] = finv(fsub(y, ONE)); y = fmul(y, w4); }
+        }
+        if (gen.active) {
+            std::vector<E4> mp(gen.n_mixpow);
+            E4 cur = e4_one();
+            for (auto& m : mp) { m = cur; cur = e4_mul(cur, poly_mix); }
+            E4* d_mp = arena.take<E4>(mp.size());
+            dev.h2d(d_mp, mp.data(), mp.size() * sizeof(E4));
+            uint32_t* d_gl = arena.take<uint32_t>(N_GLOBAL);
+            dev.h2d(d_gl, globals, N_GLOBAL * 4);
+            GenEvalArgs a{};
+            a.ev[0] = ev[GROUP_ACCUM]; a.ev[1] = ev[GROUP_CODE]; a.ev[2] = ev[GROUP_DATA];
+            a.check = check; a.prog = gen.d_prog; a.n_ins = (uint32_t)gen.prog.size(); a.mixpow = d_mp; a.mix = d_mix; a.globals = d_gl;
+            a.n_mix = gen.n_mix; a.po2 = po2; a.n_fp_slots = gen.n_fp_slots; a.n_mix_slots = gen.n_mix_slots; a.ret_slot = gen.ret_slot;
+            for (int s_ = 0; s_ < 4; s_++) a.yinv[s_] = yinv4[s_];
+            // rows per block: as many as fit the slot files in shared memory
+            const size_t per_row = (size_t)gen.n_mix_slots * sizeof(E4) + (size_t)gen.n_fp_slots * 4;
+            uint32_t R = 128;
+            while (R > 32 && per_row * R + (N_GLOBAL + gen.n_mix) * 4 > 160 * 1024) R >>= 1;
+            if (per_row * R + (N_GLOBAL + gen.n_mix) * 4 > 220 * 1024) throw Err("data-defined circuit: too many live values for the interpreter's shared-memory slot file");
+            a.rows_per_block = R;
+            dev.launch<GenEvalCheckKernel, 128, 1>((unsigned)((D + R - 1) / R), 1, (int)R, per_row * R + (N_GLOBAL + gen.n_mix) * 4 + 16, a);
+            dev.sync();
+        } else {
             const uint32_t nc = cd.n_constraints();
             std::vector<E4> mp(nc);
             E4 cur = e4_one();
@@ -320,9 +385,7 @@ struct Prover {
             EvalCheckArgs a{};
             a.ev_accum = ev[GROUP_ACCUM]; a.ev_code = ev[GROUP_CODE]; a.ev_data = ev[GROUP_DATA];
             a.check = check; a.mixpow = d_mp; a.mix = d_mix; a.global0 = globals[0];
-            const uint32_t three_n = fpow(THREE, N), w4 = rou_fwd(2);
-            uint32_t y = three_n;
-            for (int s = 0; s < 4; s++) { a.yinv[s] = finv(fsub(y, ONE)); y = fmul(y, w4); }
+            for (int s_ = 0; s_ < 4; s_++) a.yinv[s_] = yinv4[s_];
             a.po2 = po2; a.cd = cd;
             a.rows_per_block = 128;
             dev.launch<EvalCheckKernel, 128, 1>((unsigned)((D + 127) / 128), 1, 128, (size_t)nc * sizeof(E4) + (size_t)6 * cd.n_free * 2 + 16, a);
@@ -354,6 +417,35 @@ struct Prover {
             dev.launch<PowBitrevKernel, 256, 1>((unsigned)((N + 255) / 256), 1, 256, 0, W4, (const E4*)d_xs, po2);
             dev.sync();
         }
+        std::vector<E4> coeff_u(T + CHECK_SIZE);
+        std::vector<uint32_t> reg_tap(W);
+        std::vector<uint8_t> reg_two(W);
+        if (gen.active) {
+            // data-defined circuit: arbitrary tap sets.  Evaluations for every (column, back slot), then per register
+            // the Lagrange interpolant through its tap points.
+            Backs4 bk{};
+            bk.nb = (uint32_t)gen.backs.size();
+            for (uint32_t s_ = 0; s_ < bk.nb; s_++) bk.back[s_] = gen.backs[s_];
+            E4* d_ev = arena.take<E4>((size_t)GEN_MAX_BACKS * W);
+            E4* d_evc = arena.take<E4>((size_t)2 * CHECK_SIZE);
+            const uint32_t goff4[3] = {0, GEN_MAX_BACKS * cd.w_accum, GEN_MAX_BACKS * (cd.w_accum + cd.w_code)};
+            for (int g = 0; g < 3; g++) dot_group_g(tr[g], cir.group_width(g), gen.d_colmask[g], bk, Lw, d_ev + goff4[g]);
+            dot_group(check, CHECK_SIZE, 0, W4, d_evc);
+            std::vector<E4> h_ev((size_t)GEN_MAX_BACKS * W), h_evc((size_t)2 * CHECK_SIZE);
+            dev.d2h(h_ev.data(), d_ev, h_ev.size() * sizeof(E4));
+            dev.d2h(h_evc.data(), d_evc, h_evc.size() * sizeof(E4));
+            dev.sync();
+            for (const GenReg& r : gen.regs) {
+                E4 xs[4], ys[4];
+                for (uint32_t k = 0; k < r.size; k++) {
+                    const uint32_t back = gen.taps[r.tap_begin + k].back;
+                    xs[k] = e4_scale(z, fpow(back_one, back));
+                    ys[k] = h_ev[goff4[r.group] + GEN_MAX_BACKS * r.offset + gen.back_slot(back)];
+                }
+                lagrange_e4(&coeff_u[r.tap_begin], xs, ys, r.size);
+            }
+            for (uint32_t c = 0; c < CHECK_SIZE; c++) coeff_u[T + c] = h_evc[2 * c];
+        } else {
         E4* d_evals = arena.take<E4>((size_t)2 * (W + CHECK_SIZE));
         uint32_t goff[4] = {0, 2 * cd.w_accum, 2 * (cd.w_accum + cd.w_code), 2 * W};
         for (int g = 0; g < 3; g++) dot_group(tr[g], cir.group_width(g), cir.group_back1(g), Lw, d_evals + goff[g]);
@@ -362,9 +454,6 @@ struct Prover {
         dev.d2h(h_evals.data(), d_evals, h_evals.size() * sizeof(E4));
         dev.sync();
         // taps order: (group, column, back).  coeff_u: per register, interpolant through its tap points.
-        std::vector<E4> coeff_u(T + CHECK_SIZE);
-        std::vector<uint32_t> reg_tap(W);
-        std::vector<uint8_t> reg_two(W);
         {
             const E4 x0 = z, x1 = e4_scale(z, back_one);
             const E4 dinv = e4_inv(e4_sub(x0, x1));
@@ -383,6 +472,7 @@ struct Prover {
             if (t != T) throw Err("internal: tap count mismatch");
             for (uint32_t c = 0; c < CHECK_SIZE; c++) coeff_u[T + c] = h_evals[goff[3] + 2 * c];
         }
+        }
         proof.insert(proof.end(), reinterpret_cast<uint32_t*>(coeff_u.data()), reinterpret_cast<uint32_t*>(coeff_u.data()) + 4 * coeff_u.size());
         const Digest8 hash_u = host_hash_elems(reinterpret_cast<uint32_t*>(coeff_u.data()), 4 * coeff_u.size());
         rng.mix(hash_u.w);
@@ -391,25 +481,61 @@ struct Prover {
         // ---- DEEP: quotient, point-wise on the trace domain ----
         const E4 dmix = rng.random_ext();
         cp_add("deep_mix", dmix);
-        std::vector<E4> reg_mix(W + CHECK_SIZE);
+        const uint32_t n_regs = gen.active ? (uint32_t)gen.regs.size() : W;
+        std::vector<E4> reg_mix(n_regs + CHECK_SIZE);
         { E4 cur = e4_one(); for (auto& m : reg_mix) { m = cur; cur = e4_mul(cur, dmix); } }
-        DeepMixArgs da{};
-        da.U0 = da.U1a = da.U1b = da.Vc = e4_zero();
-        for (uint32_t reg = 0; reg < W; reg++) {
-            if (reg_two[reg]) { da.U1a = e4_add(da.U1a, e4_mul(reg_mix[reg], coeff_u[reg_tap[reg]])); da.U1b = e4_add(da.U1b, e4_mul(reg_mix[reg], coeff_u[reg_tap[reg] + 1])); }
-            else da.U0 = e4_add(da.U0, e4_mul(reg_mix[reg], coeff_u[reg_tap[reg]]));
-        }
-        for (uint32_t c = 0; c < CHECK_SIZE; c++) da.Vc = e4_add(da.Vc, e4_mul(reg_mix[W + c], coeff_u[T + c]));
-        E4* d_regmix = arena.take<E4>(W + CHECK_SIZE);
+        E4 Vc = e4_zero();
+        for (uint32_t c = 0; c < CHECK_SIZE; c++) Vc = e4_add(Vc, e4_mul(reg_mix[n_regs + c], coeff_u[T + c]));
+        E4* d_regmix = arena.take<E4>(n_regs + CHECK_SIZE);
         dev.h2d(d_regmix, reg_mix.data(), reg_mix.size() * sizeof(E4));
         uint32_t* S0 = arena.take<uint32_t>(4 * N);
         uint32_t* S1 = arena.take<uint32_t>(4 * N);
         uint32_t* fin = arena.take<uint32_t>(4 * N);
-        dev.launch<CheckMixKernel, 256, 1>((unsigned)((N + 255) / 256), 1, 256, 0, (const uint32_t*)check, (const E4*)(d_regmix + W), S0, po2, ntt.rt);
+        dev.launch<CheckMixKernel, 256, 1>((unsigned)((N + 255) / 256), 1, 256, 0, (const uint32_t*)check, (const E4*)(d_regmix + n_regs), S0, po2, ntt.rt);
         ntt.expand_evaluate(S0, N, S1, N, 4, (int)po2, 0);
-        for (int g = 0; g < 3; g++) { da.tr[g] = tr[g]; da.w[g] = cir.group_width(g); da.n_back1[g] = cir.group_back1(g); }
-        da.mixpow = d_regmix; da.S = S1; da.INV = INV; da.INV4 = INV4; da.out = fin; da.omega = omega; da.po2 = po2; da.rt = ntt.rt;
-        dev.launch<DeepMixKernel, 256, 1>((unsigned)((N + 255) / 256), 1, 256, 0, da);
+        if (gen.active) {
+            DeepMixGArgs ga{};
+            const uint32_t C = (uint32_t)gen.combos.size();
+            ga.n_combos = C; ga.Vc = Vc;
+            // registers grouped by combo (the sum is exact, its order is free), mix powers permuted alongside
+            std::vector<uint32_t> rc_sorted; std::vector<E4> rm_sorted;
+            for (uint32_t c = 0; c < C; c++) {
+                ga.combo_start[c] = (uint32_t)rc_sorted.size();
+                ga.combo_nb[c] = (uint32_t)gen.combos[c].size();
+                for (uint32_t k = 0; k < ga.combo_nb[c]; k++) {
+                    ga.combo_back[c][k] = gen.combos[c][k];
+                    ga.combo_fb[c][k] = fmul(fneg(THREE), fpow(omega, gen.combos[c][k]));
+                    ga.U[c][k] = e4_zero();
+                }
+                for (size_t ri = 0; ri < gen.regs.size(); ri++) {
+                    const GenReg& r = gen.regs[ri];
+                    if (r.combo != c) continue;
+                    rc_sorted.push_back((r.group << 28) | r.offset);
+                    rm_sorted.push_back(reg_mix[ri]);
+                    for (uint32_t k = 0; k < r.size; k++) ga.U[c][k] = e4_add(ga.U[c][k], e4_mul(reg_mix[ri], coeff_u[r.tap_begin + k]));
+                }
+            }
+            ga.combo_start[C] = (uint32_t)rc_sorted.size();
+            uint32_t* d_rc = arena.take<uint32_t>(rc_sorted.size());
+            E4* d_rm = arena.take<E4>(rm_sorted.size());
+            dev.h2d(d_rc, rc_sorted.data(), rc_sorted.size() * 4);
+            dev.h2d(d_rm, rm_sorted.data(), rm_sorted.size() * sizeof(E4));
+            for (int g = 0; g < 3; g++) ga.tr[g] = tr[g];
+            ga.regcol = d_rc; ga.regmix = d_rm; ga.S = S1; ga.INV = INV; ga.INV4 = INV4; ga.out = fin; ga.po2 = po2; ga.rt = ntt.rt;
+            dev.launch<DeepMixKernelG, 256, 1>((unsigned)((N + 255) / 256), 1, 256, 0, ga);
+            dev.sync();
+        } else {
+            DeepMixArgs da{};
+            da.U0 = da.U1a = da.U1b = e4_zero();
+            da.Vc = Vc;
+            for (uint32_t reg = 0; reg < W; reg++) {
+                if (reg_two[reg]) { da.U1a = e4_add(da.U1a, e4_mul(reg_mix[reg], coeff_u[reg_tap[reg]])); da.U1b = e4_add(da.U1b, e4_mul(reg_mix[reg], coeff_u[reg_tap[reg] + 1])); }
+                else da.U0 = e4_add(da.U0, e4_mul(reg_mix[reg], coeff_u[reg_tap[reg]]));
+            }
+            for (int g = 0; g < 3; g++) { da.tr[g] = tr[g]; da.w[g] = cir.group_width(g); da.n_back1[g] = cir.group_back1(g); }
+            da.mixpow = d_regmix; da.S = S1; da.INV = INV; da.INV4 = INV4; da.out = fin; da.omega = omega; da.po2 = po2; da.rt = ntt.rt;
+            dev.launch<DeepMixKernel, 256, 1>((unsigned)((N + 255) / 256), 1, 256, 0, da);
+        }
         ntt.interpolate(fin, N, fin, N, 4, (int)po2, true);  // bit-reversed coefficients of the FRI polynomial
         mark(10);
         dev.sync();  // reg_mix upload done; stage boundary
@@ -496,6 +622,7 @@ struct Prover {
     }
 
     void witgen(uint32_t p, uint64_t trace_seed, uint64_t blind, uint32_t* globals_out) {
+        if (gen.active) throw Err("hfb200_witgen_synth: only for the built-in synthetic circuit");
         bind();
         layout(p);
         const size_t N = (size_t)1 << po2;

@@ -38,6 +38,29 @@ typedef struct {
     uint32_t flags;   /* reserved, 0 */
 } hfb200_circuit_desc;
 
+/* Circuit as DATA (SURVEY.md section 8b `hfb200_circuit_register`): what upstream ships as generated code is accepted
+ * here as tables, in upstream's own shapes --
+ *   taps  : risc0_zkp::taps::TapSet  -- (group, offset, back) sorted; group ids 0 = accum, 1 = code, 2 = data
+ *   steps : risc0_zkp::adapter::PolyExtStepDef -- Const / Get / GetGlobal / Add / Sub / Mul / True / AndEqz / AndCond;
+ *           fp vars and mix vars are two SSA index spaces, every step pushes one; `ret` = mix var of the result.
+ *           CONST a = canonical value | GET a = tap index | GET_GLOBAL a = 0 (globals) / 1 (mix), b = offset |
+ *           ADD/SUB/MUL a, b = fp vars | TRUE | AND_EQZ a = mix var, b = fp var | AND_COND a = mix var, b = fp cond, c = inner mix var
+ * Limits: <= 4 taps per register, <= 4 distinct back values, <= 8 distinct tap sets.  For a data-defined circuit the
+ * witness and the accum columns are the caller's (two-phase API); hfb200_witgen_synth / finish(NULL) are refused. */
+typedef struct { uint32_t group, offset, back; } hfb200_tap;
+typedef struct { uint32_t op, a, b, c; } hfb200_poly_step;
+enum { HFB200_OP_CONST = 0, HFB200_OP_GET = 1, HFB200_OP_GET_GLOBAL = 2, HFB200_OP_ADD = 3, HFB200_OP_SUB = 4, HFB200_OP_MUL = 5,
+       HFB200_OP_TRUE = 6, HFB200_OP_AND_EQZ = 7, HFB200_OP_AND_COND = 8 };
+typedef struct {
+    uint32_t w_code, w_data, w_accum; /* group widths */
+    uint32_t n_mix;                   /* accum mix elements drawn after the DATA commit (upstream REGCOUNT_MIX) */
+    const hfb200_tap* taps;
+    size_t n_taps;
+    const hfb200_poly_step* steps;
+    size_t n_steps;
+    uint32_t ret;
+} hfb200_circuit_ir;
+
 #define HFB200_N_GLOBAL 32u
 #define HFB200_DIGEST_WORDS 8u
 
@@ -45,6 +68,8 @@ typedef struct {
 /* Replaces `segment_prover(hashfn)` / HAL construction.  Allocates the device arena for segments up to
  * 2^max_po2 cycles (12 <= max_po2 <= 22) and registers the circuit. */
 const char* hfb200_init(int device, uint32_t max_po2, const hfb200_circuit_desc* circuit, hfb200_ctx** out);
+/* Same, for a circuit given as data. */
+const char* hfb200_init_ir(int device, uint32_t max_po2, const hfb200_circuit_ir* circuit, hfb200_ctx** out);
 void hfb200_destroy(hfb200_ctx* ctx);
 void hfb200_free_error(const char* msg);
 const char* hfb200_version(void);

@@ -1,0 +1,79 @@
+"""Circuits as DATA (SURVEY.md section 8b `hfb200_circuit_register`): tap table + constraint polynomial in the shape of
+upstream's PolyExtStepDef.  The synthetic circuit is expressed as such data (oracle/synth_ir.py); the oracle interprets
+it, the product compiles it to bytecode and runs the interpreter kernel (here: on the host emulator)."""
+import numpy as np
+import pytest
+from conftest import SMALL
+
+
+def _segment(orc, widths, po2, variant):
+    cir = orc.Circuit(*widths, variant=variant)
+    code = cir.gen_code(po2)
+    g = cir.gen_globals(5)
+    data = cir.gen_data(po2, code, g, 5, 1)
+    return cir, g, code, data
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_oracle_ir_equals_builtin_formula(orc, variant):
+    cir, g, code, data = _segment(orc, SMALL, 12, variant)
+    cir_ir = orc.Circuit(*SMALL, variant=variant, use_ir=True)
+    seal, cps, _ = cir.prove(12, g, code, data, 1)
+    seal_ir, _, _ = cir_ir.prove(12, g, code, data, 1)
+    assert (seal == seal_ir).all()
+    assert cir_ir.verify(seal, cps["code_root"]) == 12 and cir.verify(seal_ir, cps["code_root"]) == 12
+    if variant:
+        assert {tuple(t) for t in cir.taps().tolist() if t[2] == 2}  # v2 really taps back 2
+        assert cir.n_taps == orc.Circuit(*SMALL).n_taps + SMALL[1] // 4
+
+
+@pytest.mark.parametrize("variant,nest", [(0, False), (0, True), (1, False), (1, True)])
+def test_data_defined_circuit_matches_oracle(pkg, emu_lib, orc, variant, nest):
+    from oracle import synth_ir
+    widths, po2 = (12, 24, 8), 12
+    cir, g, code, data = _segment(orc, widths, po2, variant)
+    ir = synth_ir.build(widths, variant, nest=nest)
+    cir_ir = orc.Circuit(*widths, variant=variant)
+    cir_ir.set_ir(ir["taps"], ir["steps"], ir["ret"])
+    oseal, ocps, _ = cir_ir.prove(po2, g, code, data, 1)
+    with pkg.Context(0, po2, widths, lib=emu_lib, ir=ir) as c:
+        mix = c.segment_begin(po2, g, code, data, 1)
+        assert (mix == ocps["accum_mix"]).all()
+        seal = c.segment_finish(cir.step_accum(po2, data, mix, 1))   # step_accum is the caller's for data-defined circuits
+        cps = c.checkpoints()
+        for k, v in ocps.items():
+            if k in cps:
+                assert (cps[k] == v).all(), k
+        assert len(seal) == c.seal_words(po2) == len(oseal) and (seal == oseal).all()
+        assert cir_ir.verify(seal, ocps["code_root"]) == po2
+        if variant == 0 and not nest:
+            # the same circuit through the built-in kernels gives the same seal
+            with pkg.Context(0, po2, widths, lib=emu_lib) as b:
+                assert (b.prove_segment(po2, g, code, data, 1) == seal).all()
+        # the library does not own witgen / step_accum of a data-defined circuit
+        with pytest.raises(pkg.Hfb200Error, match="caller"):
+            c.segment_begin(po2, g, code, data, 1)
+            c.segment_finish(None)
+        with pytest.raises(pkg.Hfb200Error):
+            c.witgen_synth(po2, 1, 1)
+
+
+def test_ir_validation(pkg, emu_lib):
+    from oracle import synth_ir
+    ir = synth_ir.build(SMALL, 0)
+
+    def bad(**kw):
+        d = dict(ir); d.update(kw)
+        with pytest.raises(pkg.Hfb200Error):
+            pkg.Context(0, 12, SMALL, lib=emu_lib, ir=d)
+    taps = ir["taps"].copy(); taps[[0, 1]] = taps[[1, 0]]
+    bad(taps=taps)                                               # not sorted
+    taps = ir["taps"].copy(); taps[0, 1] = 999
+    bad(taps=taps)                                               # column out of range
+    steps = ir["steps"].copy(); steps[5, 0] = 42
+    bad(steps=steps)                                             # unknown op
+    steps = ir["steps"].copy(); steps[np.argmax(steps[:, 0] == 5), 1] = 10**6
+    bad(steps=steps)                                             # operand used before definition
+    bad(ret=10**6)                                               # ret is not a mix var
+    many = np.array([(2, 0, b) for b in range(6)] + [(2, c, 0) for c in range(1, SMALL[1])], np.uint32)
+    bad(taps=many)                                               # > 4 taps on one register

@@ -206,3 +206,26 @@ def test_odd_circuit_widths(pkg, gpu_lib, orc, widths, po2):
         seal = c.prove_segment(po2, g, code, data, 3)
         assert len(seal) == len(oseal) and (seal == oseal).all()
         assert cir.verify(seal, ocps["code_root"]) == po2
+
+
+@pytest.mark.parametrize("widths,po2,variant,nest", [(SMALL, 12, 0, False), ((16, 64, 16), 13, 1, True), (DEFAULT, 14, 1, False)])
+def test_data_defined_circuit_on_gpu(pkg, gpu_lib, orc, widths, po2, variant, nest):
+    """hfb200_init_ir: tap table + PolyExtStep-shaped constraint list compiled to bytecode, interpreter kernel, generic
+    DEEP kernels (tap sets {0},{0,1},{0,1,2}); seal equal to the oracle interpreting the same data."""
+    from oracle import synth_ir
+    cir = orc.Circuit(*widths, variant=variant)
+    code = cir.gen_code(po2); g = cir.gen_globals(5); data = cir.gen_data(po2, code, g, 5, 1)
+    ir = synth_ir.build(widths, variant, nest=nest)
+    cir_ir = orc.Circuit(*widths, variant=variant)
+    cir_ir.set_ir(ir["taps"], ir["steps"], ir["ret"])
+    oseal, ocps, _ = cir_ir.prove(po2, g, code, data, 1)
+    with pkg.Context(0, po2, widths, lib=gpu_lib, ir=ir) as c:
+        mix = c.segment_begin(po2, g, code, data, 1)
+        assert (mix == ocps["accum_mix"]).all()
+        seal = c.segment_finish(cir.step_accum(po2, data, mix, 1))
+        cps = c.checkpoints()
+        for k, v in ocps.items():
+            if k in cps:
+                assert (cps[k] == v).all(), k
+        assert len(seal) == len(oseal) and (seal == oseal).all()
+        assert cir_ir.verify(seal, ocps["code_root"]) == po2
