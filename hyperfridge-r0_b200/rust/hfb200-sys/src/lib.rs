@@ -21,6 +21,35 @@ pub struct hfb200_circuit_desc {
     pub flags: u32,
 }
 
+/// Circuit as data: upstream's TapSet and PolyExtStepDef flattened to u32 tables (include/hfb200.h).
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct hfb200_tap {
+    pub group: u32,
+    pub offset: u32,
+    pub back: u32,
+}
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct hfb200_poly_step {
+    pub op: u32,
+    pub a: u32,
+    pub b: u32,
+    pub c: u32,
+}
+#[repr(C)]
+pub struct hfb200_circuit_ir {
+    pub w_code: u32,
+    pub w_data: u32,
+    pub w_accum: u32,
+    pub n_mix: u32,
+    pub taps: *const hfb200_tap,
+    pub n_taps: usize,
+    pub steps: *const hfb200_poly_step,
+    pub n_steps: usize,
+    pub ret: u32,
+}
+
 #[repr(C)]
 pub struct hfb200_segment_job {
     pub po2: u32,
@@ -38,6 +67,7 @@ pub struct hfb200_segment_job {
 
 extern "C" {
     pub fn hfb200_init(device: c_int, max_po2: u32, circuit: *const hfb200_circuit_desc, out: *mut *mut hfb200_ctx) -> *const c_char;
+    pub fn hfb200_init_ir(device: c_int, max_po2: u32, circuit: *const hfb200_circuit_ir, out: *mut *mut hfb200_ctx) -> *const c_char;
     pub fn hfb200_destroy(ctx: *mut hfb200_ctx);
     pub fn hfb200_free_error(msg: *const c_char);
     pub fn hfb200_seal_words(ctx: *const hfb200_ctx, po2: u32) -> usize;
