@@ -76,6 +76,33 @@ HD uint32_t fmul_lazy(uint32_t a, uint32_t b) {
 }
 // x^7 with 4 multiplies; x4 stays lazy (it only meets the canonical x3).
 HD uint32_t sbox7(uint32_t x) { uint32_t x2 = fmul(x, x), x3 = fmul(x2, x), x4 = fmul_lazy(x2, x2); return fmul(x3, x4); }
+// Signed Montgomery product: for |a * b| < 2^31 * p the value hi(a*b) - hi(m*p), m = lo(a*b) * p^-1 (all signed), is the
+// exact quotient (a*b - m*p) / 2^32 and lies in (-p, p): no correction step at all.
+HD int32_t smul(int32_t a, int32_t b) {
+    const int64_t o = (int64_t)a * b;
+    const int32_t m = (int32_t)((uint32_t)o * P_INV);
+#ifdef __CUDA_ARCH__
+    const int32_t mp = __mulhi(m, (int32_t)P);
+#else
+    const int32_t mp = (int32_t)(((int64_t)m * (int64_t)P) >> 32);
+#endif
+    return (int32_t)(o >> 32) - mp;
+}
+// (s + rc)^7 for canonical s, rc: the sum enters the chain as the signed representative s + rc - p in [-p, p) (one IADD3),
+// the four products stay signed in (-p, p) and only the result is made canonical: 4 * 4 + 2 instructions instead of 21.
+#ifndef P2_SIGNED_SBOX
+#define P2_SIGNED_SBOX 1
+#endif
+HD uint32_t sbox7_rc(uint32_t s, uint32_t rc) {
+#if P2_SIGNED_SBOX
+    const int32_t x = (int32_t)(s + rc - P);
+    const int32_t x2 = smul(x, x), x3 = smul(x2, x), x4 = smul(x2, x2);
+    const uint32_t r = (uint32_t)smul(x3, x4);
+    return umin32(r, r + P);
+#else
+    return sbox7(padd(s, rc));
+#endif
+}
 // x * d mod p for a constant d given as (d, d' = floor(d 2^32 / p)) -- Shoup: no 64-bit product, result already in [0, 2p).
 // x may be any residue representation (here Montgomery), d is the canonical constant.
 HD uint32_t fmul_const(uint32_t x, uint32_t d, uint32_t dp) {
@@ -120,18 +147,18 @@ HD void p2_mix(uint32_t* s) {
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
 #pragma unroll
-        for (int i = 0; i < 24; i++) s[i] = sbox7(padd(s[i], k.rc_first[r * 24 + i]));
+        for (int i = 0; i < 24; i++) s[i] = sbox7_rc(s[i], k.rc_first[r * 24 + i]);
         p2_m_ext(s);
     }
 #pragma unroll 1
     for (int r = 0; r < 21; r++) {
-        s[0] = sbox7(padd(s[0], k.rc_partial[r]));
+        s[0] = sbox7_rc(s[0], k.rc_partial[r]);
         p2_m_int(s, k);
     }
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
 #pragma unroll
-        for (int i = 0; i < 24; i++) s[i] = sbox7(padd(s[i], k.rc_last[r * 24 + i]));
+        for (int i = 0; i < 24; i++) s[i] = sbox7_rc(s[i], k.rc_last[r * 24 + i]);
         p2_m_ext(s);
     }
 }
@@ -245,10 +272,10 @@ __device__ __forceinline__ uint32_t wp2_mix(uint32_t x, int lane, const WarpCons
     const P2Consts& k = p2c();
     x = wp2_m_ext(x, lane);
 #pragma unroll
-    for (int r = 0; r < 4; r++) x = wp2_m_ext(sbox7(fadd(x, w.rcf[r])), lane);
+    for (int r = 0; r < 4; r++) x = wp2_m_ext(sbox7_rc(x, w.rcf[r]), lane);
 #pragma unroll 1
     for (int r = 0; r < 21; r++) {
-        const uint32_t y = sbox7(fadd(x, k.rc_partial[r]));
+        const uint32_t y = sbox7_rc(x, k.rc_partial[r]);
         if (lane == 0) x = y;
         uint32_t s = x;
 #pragma unroll
@@ -256,7 +283,7 @@ __device__ __forceinline__ uint32_t wp2_mix(uint32_t x, int lane, const WarpCons
         x = lane < 24 ? fadd(s, fmul_const(x, w.d, w.dp)) : 0u;
     }
 #pragma unroll
-    for (int r = 0; r < 4; r++) x = wp2_m_ext(sbox7(fadd(x, w.rcl[r])), lane);
+    for (int r = 0; r < 4; r++) x = wp2_m_ext(sbox7_rc(x, w.rcl[r]), lane);
     return x;
 }
 __device__ __forceinline__ void wp2_hash_pair(uint32_t* nodes, uint64_t i, int lane, const WarpConsts& w) {
