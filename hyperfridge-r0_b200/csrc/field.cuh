@@ -54,6 +54,15 @@ HD uint32_t fmul_shoup(uint32_t x, uint32_t d, uint32_t dp) {
     return umin32(r, r - P);
 }
 HD uint32_t shoup_quot(uint32_t d) { return (uint32_t)(((uint64_t)d << 32) / P); }
+// The same quotient from the Montgomery form wm = d 2^32 mod p, without a division: d 2^32 = q p + wm exactly, so
+// q = (d 2^32 - wm) / p = -wm p^-1 (mod 2^32).
+HD uint32_t shoup_quot_mont(uint32_t wm) { return (0u - wm) * P_INV; }
+// (w, w') pair at word offset 2 t of an 8-byte aligned table
+HD void ld_pair(const uint32_t* tw, uint32_t t, uint32_t& w, uint32_t& wp) {
+    const uint2 v = *reinterpret_cast<const uint2*>(tw + 2 * t);
+    w = v.x; wp = v.y;
+}
+HD uint32_t fmul_pair(uint32_t x, const uint32_t* tw, uint32_t t) { uint32_t w, wp; ld_pair(tw, t, w, wp); return fmul_shoup(x, w, wp); }
 
 struct __align__(16) E4 { uint32_t c[4]; };
 

@@ -278,7 +278,7 @@ HD void round_t(const KCtx& cx, const uint32_t* tw, int k_, int c_, int l0_, con
                     uint32_t x = v[j + h];
                     if (!(L0 == 0 && (j & (h - 1)) == 0)) {
                         const uint32_t ti = TWL ? (1u << (l0 + q - 1)) + ((uint32_t)(j & (h - 1)) << l0) + low : (low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q);
-                        x = SHP ? fmul_shoup(x, tw[2 * ti], tw[2 * ti + 1]) : fmul(x, tw[ti]);
+                        x = SHP ? fmul_pair(x, tw, ti) : fmul(x, tw[ti]);
                     }
                     v[j + h] = fsub(v[j], x);
                     v[j] = fadd(v[j], x);
@@ -296,7 +296,7 @@ HD void round_t(const KCtx& cx, const uint32_t* tw, int k_, int c_, int l0_, con
                     uint32_t d = fsub(a, b);
                     if (!(L0 == 0 && (j & (h - 1)) == 0)) {
                         const uint32_t ti = TWL ? (1u << (l0 + q - 1)) + ((uint32_t)(j & (h - 1)) << l0) + low : (low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q);
-                        d = SHP ? fmul_shoup(d, tw[2 * ti], tw[2 * ti + 1]) : fmul(d, tw[ti]);
+                        d = SHP ? fmul_pair(d, tw, ti) : fmul(d, tw[ti]);
                     }
                     v[j + h] = d;
                 }
@@ -370,11 +370,11 @@ struct StridedKernel2 {
     }
     HD static void run(const KCtx& cx, uint32_t* sm, Str2Args p) {
         uint32_t* s = sm;
-        uint32_t* tw = sm + padded_words(1u << (p.b + p.c));
+        uint32_t* tw = sm + ((padded_words(1u << (p.b + p.c)) + 1u) & ~1u);  // 8-byte aligned (w, w') pairs
         const uint32_t half = 1u << (p.b - 1);
         for (uint32_t i = cx.tid; i < half; i += cx.nt) {
             const uint32_t w = p.inv ? tab_pow(p.rt.i_lo, p.rt.i_hi, i << (24 - p.b)) : tab_pow(p.rt.f_lo, p.rt.f_hi, i << (24 - p.b));
-            if (SB >= 6) { const uint32_t ws = from_mont(w); tw[2 * i] = ws; tw[2 * i + 1] = shoup_quot(ws); }  // Shoup pairs
+            if (SB >= 6) { tw[2 * i] = from_mont(w); tw[2 * i + 1] = shoup_quot_mont(w); }  // Shoup pairs
             else tw[i] = w;
         }
         cx.sync();
@@ -401,6 +401,7 @@ struct Mid2Args {
     uint32_t flags;
     uint32_t n_inv;
     int units, alias, ut;
+    int shp;         // twI / twF / G2 hold Shoup (w, w') pairs (the compile-time main-group instantiation)
     int nri, Ri[4];  // inverse rounds, top level first; the last one (RF levels) runs in registers
     int nrf, Rf[4];  // forward rounds; the first one (RF levels) runs in registers, fused with the inverse tail
     RootTables rt;
@@ -410,11 +411,12 @@ struct Mid2Layout {
     HD Mid2Layout(const Mid2Args& p) {
         uint32_t o = 0;
         const bool intt = p.flags & MID_INTT, fwd = p.flags & MID_FWD, fly = p.flags & MID_GFLY;
-        twI = o; if (intt) o += 1u << p.a;          // per-level layout: tw[2^(l-1) + x] = w_{2^l}^-x
-        twF = o; if (fwd) o += 1u << (p.a + p.e);
+        const uint32_t pw = p.shp ? 2u : 1u;        // words per twiddle entry
+        twI = o; if (intt) o += pw << p.a;          // per-level layout: tw[2^(l-1) + x] = w_{2^l}^-x
+        twF = o; if (fwd) o += pw << (p.a + p.e);
         G3 = o; if (intt && p.b > 0 && !fly) o += 1u << p.a;
         Gs = o; if (intt && !fly) o += 1u << p.a;
-        G2 = o; if (fwd && p.b > 0 && !fly) o += 1u << (p.a + p.e);
+        G2 = o; if (fwd && p.b > 0 && !fly) o += pw << (p.a + p.e);
         unit0 = o;
         uint32_t u = 0;
         A = u; if (intt && !(fwd && p.alias)) u += padded_words(1u << p.a);
@@ -429,6 +431,7 @@ template <int MA, int ME>
 struct MiddleKernel2 {
     static constexpr bool kBarrier = true;
     static constexpr int PSB = (MA == 10 && ME == 2) ? 6 : 5;  // pad shift of the forward buffer B
+    static constexpr bool SHP = (MA == 10 && ME == 2);         // Shoup (w, w') pairs in twI / twF / G2 (host sets p.shp alike)
     HD static int A_(const Mid2Args& p) { return MA >= 0 ? MA : p.a; }
     HD static int E_(const Mid2Args& p) { return ME >= 0 ? ME : p.e; }
     HD static uint32_t g3(const Mid2Args& p, uint32_t rb, uint32_t i) { return tab_pow(p.rt.i_lo, p.rt.i_hi, (rb * i) << (24 - p.n)); }
@@ -458,7 +461,7 @@ struct MiddleKernel2 {
         HD bool affine(int, int) const { return true; }
         HD uint32_t ld_i(uint32_t) const { return 0; }
         HD void st_i(uint32_t pos, uint32_t v) const {
-            if (mode == 1) v = fmul(v, G2[pos]); else if (mode == 2) v = fmul(v, tab_pow(lo, hi, (rb * pos) << shift));
+            if (mode == 1) v = SHP ? fmul_pair(v, G2, pos) : fmul(v, G2[pos]); else if (mode == 2) v = fmul(v, tab_pow(lo, hi, (rb * pos) << shift));
             dst[pos] = v;
         }
     };
@@ -485,7 +488,7 @@ struct MiddleKernel2 {
                     const uint32_t a = v[j], b = v[j + h];
                     v[j] = fadd(a, b);
                     uint32_t d = fsub(a, b);
-                    if ((j & (h - 1)) != 0) d = fmul(d, twI[(1u << (q - 1)) + (uint32_t)(j & (h - 1))]);
+                    if ((j & (h - 1)) != 0) { const uint32_t ti = (1u << (q - 1)) + (uint32_t)(j & (h - 1)); d = SHP ? fmul_pair(d, twI, ti) : fmul(d, twI[ti]); }
                     v[j + h] = d;
                 }
             }
@@ -514,7 +517,7 @@ struct MiddleKernel2 {
             for (int j = 0; j < (1 << RF); j++) {
                 if (j & h) continue;
                 uint32_t x = w[j + h];
-                if (!(RZ && (j & (h - 1)) == 0)) x = fmul(x, twF[(1u << (e + q - 1)) + ((uint32_t)(j & (h - 1)) << e) + r]);
+                if (!(RZ && (j & (h - 1)) == 0)) { const uint32_t ti = (1u << (e + q - 1)) + ((uint32_t)(j & (h - 1)) << e) + r; x = SHP ? fmul_pair(x, twF, ti) : fmul(x, twF[ti]); }
                 w[j + h] = fsub(w[j], x);
                 w[j] = fadd(w[j], x);
             }
@@ -558,7 +561,7 @@ struct MiddleKernel2 {
             for (uint32_t i = cx.tid; i < na; i += cx.nt) {
                 uint32_t v = ONE;
                 if (i >= 1) { const int l = 32 - clz32(i); v = tab_pow(p.rt.i_lo, p.rt.i_hi, (i - (1u << (l - 1))) << (24 - l)); }
-                twI[i] = v;
+                if (SHP) { twI[2 * i] = from_mont(v); twI[2 * i + 1] = shoup_quot_mont(v); } else twI[i] = v;
             }
             if (!fly) {
                 if (p.b > 0) for (uint32_t i = cx.tid; i < na; i += cx.nt) G3[i] = g3(p, rb, i);
@@ -569,9 +572,12 @@ struct MiddleKernel2 {
             for (uint32_t i = cx.tid; i < nf; i += cx.nt) {
                 uint32_t v = ONE;
                 if (i >= 1) { const int l = 32 - clz32(i); v = tab_pow(p.rt.f_lo, p.rt.f_hi, (i - (1u << (l - 1))) << (24 - l)); }
-                twF[i] = v;
+                if (SHP) { twF[2 * i] = from_mont(v); twF[2 * i + 1] = shoup_quot_mont(v); } else twF[i] = v;
             }
-            if (!fly && p.b > 0) for (uint32_t i = cx.tid; i < nf; i += cx.nt) G2[i] = g2(p, rb, i);
+            if (!fly && p.b > 0) for (uint32_t i = cx.tid; i < nf; i += cx.nt) {
+                const uint32_t g = g2(p, rb, i);
+                if (SHP) { G2[2 * i] = from_mont(g); G2[2 * i + 1] = shoup_quot_mont(g); } else G2[i] = g;
+            }
         }
         cx.sync();
         const int gmode = p.b == 0 ? 0 : (fly ? 2 : 1);
@@ -590,11 +596,11 @@ struct MiddleKernel2 {
                 if constexpr (MA == 10 && ME == 2) {  // host dispatches this instantiation only for the fused iNTT+LDE
                     // main-group schedule, all sizes compile-time: DIF 3+3 (+4 in registers), DIT (4 in registers +) 3+3
                     const SmemIOT<PSB> SB6{B};
-                    round_t<3, true, 10, 0, 7, true>(ux, twI, 10, 0, 7, G, SA); ux.sync();
-                    round_t<3, true, 10, 0, 4, true, true>(ux, twI, 10, 0, 4, SA, SA); ux.sync();
+                    round_t<3, true, 10, 0, 7, true, false, true>(ux, twI, 10, 0, 7, G, SA); ux.sync();
+                    round_t<3, true, 10, 0, 4, true, true, true>(ux, twI, 10, 0, 4, SA, SA); ux.sync();
                     tail<4>(ux, p, rb, false, G, A, twI, twF, Gs, B, dst_coef, D); ux.sync();
-                    round_t<3, false, 12, 0, 6, true>(ux, twF, 12, 0, 6, SB6, SB6); ux.sync();
-                    round_t<3, false, 12, 0, 9, true>(ux, twF, 12, 0, 9, SB6, D);
+                    round_t<3, false, 12, 0, 6, true, false, true>(ux, twF, 12, 0, 6, SB6, SB6); ux.sync();
+                    round_t<3, false, 12, 0, 9, true, false, true>(ux, twF, 12, 0, 9, SB6, D);
                 } else {
                 bool from_global = true;
                 if (intt) {
@@ -704,7 +710,7 @@ struct Ntt {
         p.in = in; p.out = out; p.in_stride = in_stride; p.out_stride = out_stride; p.ncols = ncols;
         p.a = a; p.b = b; p.c = c; p.inv = inv ? 1 : 0; p.rt = rt;
         p.nr = split_rounds(b, p.R);
-        const size_t smem = (size_t)(padded_words(1u << (b + c)) + (1u << b)) * 4;  // tile + twiddle (w, w') pairs
+        const size_t smem = (size_t)(((padded_words(1u << (b + c)) + 1u) & ~1u) + (1u << b)) * 4;  // tile + twiddle (w, w') pairs
         const uint64_t tiles = (uint64_t)ncols << (a - c);
         unsigned per_sm = (unsigned)((220 * 1024) / (smem + 1024));
         if (per_sm < 1) per_sm = 1;
@@ -752,8 +758,12 @@ struct Ntt {
 #ifdef HFB200_EMU
         p.ut = MID_UT;
 #endif
-        const size_t budget = a <= 10 ? 112 * 1024 : 200 * 1024;  // two CTAs per SM for the common chunk size
-        int units = 256 / p.ut;
+        const bool main_cfg = a == 10 && e == 2 && intt && fwd && !(p.flags & MID_GFLY);
+        p.shp = main_cfg ? 1 : 0;
+        // main group: ONE 512-thread CTA per SM (8 units sharing one set of Shoup-pair tables, 215 KB); otherwise two
+        // 256-thread CTAs per SM for chunks up to 2^10
+        const size_t budget = main_cfg ? 226 * 1024 : (a <= 10 ? 112 * 1024 : 200 * 1024);
+        int units = (main_cfg ? 512 : 256) / p.ut;
         for (;; units >>= 1) {
             p.units = units;
             if ((size_t)Mid2Layout(p).total * 4 <= budget || units == 1) break;
@@ -765,7 +775,7 @@ struct Ntt {
         if (groups > max_groups) groups = max_groups;
         p.cols_per_block = (ncols + groups - 1) / groups;
         groups = (ncols + p.cols_per_block - 1) / p.cols_per_block;
-        if (a == 10 && e == 2 && intt && fwd) dev->launch<MiddleKernel2<10, 2>, 256, 2>((unsigned)chunks, groups, p.units * p.ut, (size_t)Mid2Layout(p).total * 4, p);
+        if (main_cfg) dev->launch<MiddleKernel2<10, 2>, 512, 1>((unsigned)chunks, groups, p.units * p.ut, (size_t)Mid2Layout(p).total * 4, p);
         else dev->launch<MiddleKernel2<-1, -1>, 256, 2>((unsigned)chunks, groups, p.units * p.ut, (size_t)Mid2Layout(p).total * 4, p);
     }
 

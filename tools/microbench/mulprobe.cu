@@ -66,6 +66,14 @@ __global__ void __launch_bounds__(256) probe(uint32_t* out, uint32_t seed, int i
             else if (OP == 7) x[i] = sbox_old(x[i], y[i]);
             else if (OP == 8) x[i] = sbox_acc(x[i], y[i]);
             else if (OP == 9) { uint32_t s = x[i] + y[i]; x[i] = umin32(s, s - P); }
+            else if (OP == 10) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y[i]), "r"(it));
+            else if (OP == 11) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y[i]), "r"(it));
+            else if (OP == 12) { uint64_t a = ((uint64_t)y[i] << 32) | x[i]; asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a) : "r"(x[i]), "r"(y[i])); x[i] = (uint32_t)a; y[i] = (uint32_t)(a >> 32); }
+            else if (OP == 13) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i]));
+            else if (OP == 14) asm volatile("min.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i] ));
+            else if (OP == 15) { asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y[i]), "r"(it)); asm volatile("min.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(it)); }
+            else if (OP == 16) { asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y[i]), "r"(it)); asm volatile("min.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(it)); asm volatile("add.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(it)); }
+            else if (OP == 17) { asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y[i]), "r"(it)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(y[i]), "r"(it)); }
         }
     }
     uint32_t acc = 0;
@@ -103,5 +111,7 @@ int main() {
     run<7>("7 sbox unsigned chain (previous)", N / 4, 4);
     run<8>("8 sbox WIDE-accumulate chain", N / 4, 4);
     run<1>("1 again (clock drift check)", N, 1);
+    run<10>("10 IMAD.LO", N, 0); run<11>("11 IMAD.HI", N, 0); run<12>("12 IMAD.WIDE acc64", N, 0); run<13>("13 IADD", N, 0); run<14>("14 MIN", N, 0);
+    run<15>("15 IMAD.LO + MIN (independent)", N, 0); run<16>("16 IMAD.HI + MIN + IADD (independent)", N, 0); run<17>("17 IMAD.HI + IMAD.LO (independent)", N, 0);
     return 0;
 }
