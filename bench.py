@@ -208,13 +208,16 @@ def main():
     ctx, g = ctxs[0], gl[0]
 
     def run_all(fn, steps):
-        """fn(slot, step) on every context, `steps` times each, one thread per context."""
+        """fn(slot, step) on every context, `steps` times each, one thread per context.  Every context records a
+        device-timeline mark on its own stream before its first and after its last step (hfb200_mark)."""
         errs = []
 
         def work(slot):
             try:
+                ctxs[slot].mark(0)
                 for k in range(steps):
                     fn(slot, k)
+                ctxs[slot].mark(1)
             except Exception as e:  # noqa: BLE001
                 errs.append(e)
         th = [threading.Thread(target=work, args=(i,)) for i in range(F)]
@@ -222,6 +225,11 @@ def main():
         [t.join() for t in th]
         if errs:
             raise errs[0]
+
+    def device_seconds():
+        """Device time of the last run_all on this GPU: earliest start mark to latest end mark over the contexts
+        (CUDA events on the library's own streams; torch.cuda.Event would only see torch's stream)."""
+        return max(a.mark_elapsed(0, b, 1) for a in ctxs for b in ctxs) * 1e-3
 
     # ---------------- value: resident trace ----------------
     seals = [None] * F
@@ -249,10 +257,10 @@ def main():
     t0 = time.perf_counter()
     run_all(step_resident, args.steps)
     barrier()
-    wall = time.perf_counter() - t0
+    host_wall = max_over_ranks(time.perf_counter() - t0)
     launches = sum(c.total_launches() for c in ctxs) - l0
     clocks = sampler.stop() if rank == 0 else None
-    wall = max_over_ranks(wall)
+    wall = max_over_ranks(device_seconds())  # device timeline, max over ranks
     dev_ms = max_over_ranks(dev_ms[0])
     launches_all = int(sum_over_ranks(float(launches)))
     ms_per_step = wall * 1e3 / args.steps
@@ -284,10 +292,13 @@ def main():
         t0 = time.perf_counter()
         run_all(step_host, args.steps)
         barrier()
-        wall_e = max_over_ranks(time.perf_counter() - t0)
+        host_wall_e = max_over_ranks(time.perf_counter() - t0)
+        # e2e includes the host side of the call (pinned-buffer H2D enqueue, transcript, seal D2H): the larger of the
+        # device-timeline span and the host wall clock around the same K steps, max over ranks
+        wall_e = max(max_over_ranks(device_seconds()), host_wall_e)
         e2e_value = world * F * args.steps / wall_e
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(F * ((WIDTHS[0] + WIDTHS[1]) * N * 4 + 128 + 4 * WIDTHS[2])),
-               "d2h_bytes_per_step": int(F * len(seal_h[0]) * 4), "ms_per_step": wall_e * 1e3 / args.steps, "ms_h2d_exposed_per_segment": h2d_ms[0] / args.steps,
+               "d2h_bytes_per_step": int(F * len(seal_h[0]) * 4), "ms_per_step": wall_e * 1e3 / args.steps, "host_wall_ms_per_step": host_wall_e * 1e3 / args.steps, "ms_h2d_exposed_per_segment": h2d_ms[0] / args.steps,
                "camt53_proof_seconds": CAMT53_SEGMENTS / e2e_value, "host_memory": "pinned (hfb200_host_alloc)"}
         for c, (code_h, data_h) in zip(ctxs, hb):
             c.host_free(code_h)
@@ -311,8 +322,18 @@ def main():
     # Poseidon2 (integer-ALU bound, no HBM roofline): permutations/s
     perms = 4 * N * sum((w + 15) // 16 for w in WIDTHS) + 3 * 4 * N
     hash_ms = stage["ms_hash_main"] / args.steps
-    poseidon = {"kernel": "HashRowsKernel + HashFoldKernel (Poseidon2 t=24) over the 3 main trees", "bound": "integer ALU", "permutations": perms,
-                "ms": hash_ms, "gperm_per_s": perms / (hash_ms * 1e-3) / 1e9 if hash_ms > 0 else 0.0}
+    # measured integer-multiply peaks of this GPU (hfb200_bench_modmul: every SM busy with the bare product sequences);
+    # one permutation = 852 Montgomery products (213 S-boxes x 4) + 504 Shoup constant products (21 x 24 diagonal)
+    barrier()
+    peak_sbox = ctx.bench_modmul(2)
+    peak_shoup = ctx.bench_modmul(1)
+    ideal_ms = perms * (852.0 / peak_sbox + 504.0 / peak_shoup) * 1e3 if peak_sbox > 0 and peak_shoup > 0 else 0.0
+    poseidon = {"kernel": "HashRowsKernel + HashFoldKernel (Poseidon2 t=24) over the 3 main trees", "bound": "integer multiply pipe (FMA-heavy)", "permutations": perms,
+                "ms": hash_ms, "gperm_per_s": perms / (hash_ms * 1e-3) / 1e9 if hash_ms > 0 else 0.0,
+                "modmul_per_permutation": {"montgomery_sbox": 852, "shoup_const": 504},
+                "modmul_peak_measured_gmul_s": {"sbox_chain": peak_sbox / 1e9, "shoup": peak_shoup / 1e9},
+                "ms_at_modmul_peak": ideal_ms, "frac_of_modmul_peak": ideal_ms / hash_ms if hash_ms > 0 else 0.0,
+                "note": "multiplications only: the 2160 modular additions per permutation share the issue slots (ALU pipe)"}
 
     # ---------------- CPU baseline (rank 0, N=1 only, bounded sample) ----------------
     cpu = None
@@ -326,7 +347,8 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "ms_per_segment_device_events_single_context": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_per_step, "host_wall_ms_per_step": host_wall * 1e3 / args.steps, "timing": "CUDA events on the prover streams (hfb200_mark), earliest start to latest end over the contexts, max over ranks",
+                "ms_per_segment_device_events_single_context": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32 (BabyBear mod p, Montgomery)", "data": "synthetic",
                 "config": {"workload": "configs[1]: single synthetic rv32im-shaped segment per GPU per step, po2=%d, W=256 (16 code + 192 data + 48 accum), circuit synth-rv32im-shape v1" % po2,
                            "po2": po2, "segments_per_step": world * F, "inflight_per_gpu": F,

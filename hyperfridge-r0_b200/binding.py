@@ -20,7 +20,8 @@ EXPORTS = [
     "hfb200_prove_segment", "hfb200_segment_begin", "hfb200_segment_finish", "hfb200_witgen_synth",
     "hfb200_prove_resident", "hfb200_read_group", "hfb200_seal_words", "hfb200_checkpoint", "hfb200_last_stats",
     "hfb200_total_launches", "hfb200_op_interpolate_ntt", "hfb200_op_expand_ntt", "hfb200_op_lde", "hfb200_op_merkle",
-    "hfb200_op_poseidon2", "hfb200_op_fri_fold", "hfb200_bench_lde", "hfb200_bench_merkle",
+    "hfb200_op_poseidon2", "hfb200_op_fri_fold", "hfb200_bench_lde", "hfb200_bench_merkle", "hfb200_bench_modmul",
+    "hfb200_mark", "hfb200_mark_elapsed",
     "hfb200_pool_create", "hfb200_pool_prove", "hfb200_pool_destroy",
 ]
 
@@ -88,6 +89,9 @@ def load_library(path=None):
         "hfb200_op_fri_fold": (err, [vp, vp, vp, sz, vp]),
         "hfb200_bench_lde": (err, [vp, u32, u32, u32, C.POINTER(C.c_float)]),
         "hfb200_bench_merkle": (err, [vp, u32, u32, u32, C.POINTER(C.c_float)]),
+        "hfb200_bench_modmul": (err, [vp, C.c_int, u32, C.POINTER(C.c_double)]),
+        "hfb200_mark": (err, [vp, C.c_int]),
+        "hfb200_mark_elapsed": (err, [vp, C.c_int, vp, C.c_int, C.POINTER(C.c_float)]),
         "hfb200_pool_create": (err, [C.POINTER(C.c_int), C.c_int, C.c_int, u32, C.POINTER(CircuitDesc), C.POINTER(vp)]),
         "hfb200_pool_prove": (err, [vp, C.POINTER(SegmentJob), sz]),
         "hfb200_pool_destroy": (None, [vp]),
@@ -296,6 +300,22 @@ class Context:
     def bench_merkle(self, po2, count, iters):
         ms = C.c_float()
         self._check(self.lib.hfb200_bench_merkle(self._h, po2, count, iters, C.byref(ms)))
+        return ms.value
+
+    def bench_modmul(self, kind, iters=1 << 15):
+        """Modular products per second of instruction sequence `kind` (0 Montgomery, 1 Shoup, 2 S-box chain)."""
+        r = C.c_double()
+        self._check(self.lib.hfb200_bench_modmul(self._h, kind, iters, C.byref(r)))
+        return r.value
+
+    def mark(self, slot):
+        """Records device-timeline mark `slot` (0..3) on this context's stream."""
+        self._check(self.lib.hfb200_mark(self._h, slot))
+
+    def mark_elapsed(self, slot_a, other, slot_b):
+        """Device milliseconds from this context's mark slot_a to `other`'s mark slot_b."""
+        ms = C.c_float()
+        self._check(self.lib.hfb200_mark_elapsed(self._h, slot_a, other._h, slot_b, C.byref(ms)))
         return ms.value
 
 

@@ -1,6 +1,7 @@
 // C ABI of libhfb200.so (see include/hfb200.h for the boundary contract and reference citations).
 #include "../../include/hfb200.h"
 #include "prover.cuh"
+#include "probe.cuh"
 #include <algorithm>
 #include <atomic>
 #include <memory>
@@ -8,7 +9,13 @@
 
 using namespace hf;
 
-struct hfb200_ctx { Prover p; std::vector<uint32_t> seal; };
+struct hfb200_ctx {
+    Prover p;
+    std::vector<uint32_t> seal;
+#ifndef HFB200_EMU
+    cudaEvent_t marks[4] = {nullptr, nullptr, nullptr, nullptr};
+#endif
+};
 
 static const char* dup_err(const std::string& s) {
     char* m = (char*)std::malloc(s.size() + 1);
@@ -63,6 +70,9 @@ const char* hfb200_init_ir(int device, uint32_t max_po2, const hfb200_circuit_ir
 }
 void hfb200_destroy(hfb200_ctx* ctx) {
     if (!ctx) return;
+#ifndef HFB200_EMU
+    for (auto& m : ctx->marks) if (m) { cudaEventDestroy(m); m = nullptr; }
+#endif
     try { ctx->p.destroy(); } catch (...) {}
     delete ctx;
 }
@@ -354,6 +364,50 @@ const char* hfb200_bench_merkle(hfb200_ctx* ctx, uint32_t po2, uint32_t count, u
     t.stop();
     *ms_avg = t.ms() / (iters ? iters : 1);
     t.destroy();
+    API_CATCH
+}
+
+const char* hfb200_bench_modmul(hfb200_ctx* ctx, int kind, uint32_t iters, double* products_per_s) {
+    API_TRY
+    if (!ctx || !products_per_s) throw Err("bench_modmul: NULL argument");
+    if (kind < 0 || kind > 2) throw Err("bench_modmul: kind must be 0 (Montgomery), 1 (Shoup) or 2 (S-box chain)");
+    Prover& p = ctx->p;
+    p.bind();
+    const unsigned blocks = (unsigned)p.dev.sm_count * 4, threads = 256;  // 8 warps per SM sub-partition
+    uint32_t* out = (uint32_t*)p.dev.alloc((size_t)blocks * threads * 4);
+    Timer t; t.init(p.dev.stream);
+    p.dev.launch<ModmulProbeKernel, 256, 1>(blocks, 1, threads, 0, out, 12345u, iters, kind);  // warm-up (clocks)
+    t.start();
+    p.dev.launch<ModmulProbeKernel, 256, 1>(blocks, 1, threads, 0, out, 12345u, iters, kind);
+    t.stop();
+    const float ms = t.ms();
+    t.destroy();
+    p.dev.free(out);
+    const double products = (double)blocks * threads * ModmulProbeKernel::ILP * (double)iters * (kind == 2 ? 4.0 : 1.0);
+    *products_per_s = ms > 0 ? products / (ms * 1e-3) : 0.0;
+    API_CATCH
+}
+const char* hfb200_mark(hfb200_ctx* ctx, int slot) {
+    API_TRY
+    if (!ctx || slot < 0 || slot > 3) throw Err("hfb200_mark: bad argument");
+#ifndef HFB200_EMU
+    ctx->p.bind();
+    if (!ctx->marks[slot]) CUDA_CHECK(cudaEventCreate(&ctx->marks[slot]));
+    CUDA_CHECK(cudaEventRecord(ctx->marks[slot], ctx->p.dev.stream));
+#endif
+    API_CATCH
+}
+const char* hfb200_mark_elapsed(hfb200_ctx* a, int slot_a, hfb200_ctx* b, int slot_b, float* ms) {
+    API_TRY
+    if (!a || !b || !ms || slot_a < 0 || slot_a > 3 || slot_b < 0 || slot_b > 3) throw Err("hfb200_mark_elapsed: bad argument");
+    *ms = 0.f;
+#ifndef HFB200_EMU
+    if (!a->marks[slot_a] || !b->marks[slot_b]) throw Err("hfb200_mark_elapsed: mark not recorded");
+    a->p.bind();
+    CUDA_CHECK(cudaEventSynchronize(a->marks[slot_a]));
+    CUDA_CHECK(cudaEventSynchronize(b->marks[slot_b]));
+    CUDA_CHECK(cudaEventElapsedTime(ms, a->marks[slot_a], b->marks[slot_b]));
+#endif
     API_CATCH
 }
 

@@ -171,6 +171,15 @@ const char* hfb200_op_fri_fold(hfb200_ctx* ctx, uint32_t* out, const uint32_t* i
  * runs the fused trace->LDE pipeline over `count` columns of 2^po2 `iters` times, returns avg ms. */
 const char* hfb200_bench_lde(hfb200_ctx* ctx, uint32_t po2, uint32_t count, uint32_t iters, float* ms_avg);
 const char* hfb200_bench_merkle(hfb200_ctx* ctx, uint32_t po2, uint32_t count, uint32_t iters, float* ms_avg);
+/* Integer-multiply roofline probe (the bound of Poseidon2 and of the NTT butterflies on sm_100a): sustained rate of a
+ * modular-multiply sequence over every SM, 8 independent chains per thread.  kind 0 = Montgomery product, 1 = Shoup
+ * constant product, 2 = the x^7 S-box chain (4 products per step).  Returns products per second. */
+const char* hfb200_bench_modmul(hfb200_ctx* ctx, int kind, uint32_t iters, double* products_per_s);
+/* Device-timeline marks for whole-job timing across several contexts of one device: hfb200_mark records CUDA event
+ * `slot` (0..3) on the context's stream; hfb200_mark_elapsed returns the device time from mark (a, slot_a) to mark
+ * (b, slot_b) after both have completed (a and b may be the same or different contexts of the same device). */
+const char* hfb200_mark(hfb200_ctx* ctx, int slot);
+const char* hfb200_mark_elapsed(hfb200_ctx* a, int slot_a, hfb200_ctx* b, int slot_b, float* ms);
 
 #ifdef __cplusplus
 }
