@@ -202,7 +202,7 @@ struct EvalCheckKernel {
             if (i >= domain) break;
             const uint64_t ib = (i + domain - 4) & dmask;  // back 1 on the x4 domain
             const uint32_t active = p.ev_code[i], first = p.ev_code[domain + i];
-            E4 tot = e4_zero();
+            E4A lt = e4a_zero();  // sum_j mixpow[j] * constraint_j in lazy 64-bit accumulators (field.cuh)
             uint32_t j = 0;
 #pragma unroll 4
             for (uint32_t k = 0; k < cd.n_free; k++, j++) {
@@ -210,7 +210,7 @@ struct EvalCheckKernel {
                 const uint32_t e = derived_expr(k, p.ev_data[(uint64_t)pk[0] * domain + i], p.ev_data[(uint64_t)pk[1] * domain + i], p.ev_data[(uint64_t)pk[2] * domain + i],
                                                 p.ev_data[(uint64_t)pk[3] * domain + i], p.ev_data[(uint64_t)pk[4] * domain + ib], p.ev_code[(uint64_t)pk[5] * domain + i]);
                 const uint32_t cv = fmul(active, fsub(p.ev_data[(uint64_t)(cd.n_free + k) * domain + i], e));
-                tot = e4_add(tot, e4_scale(mp[j], cv));
+                e4a_mac(lt, mp[j], cv);
             }
             const uint32_t nf = fsub(ONE, first);
             for (uint32_t r = 0; r < cd.n_chains; r++) {
@@ -223,9 +223,10 @@ struct EvalCheckKernel {
                 s.c[0] = fadd(s.c[0], first);
                 t.c[0] = fadd(t.c[0], p.ev_data[(uint64_t)cd.chain_src[r] * domain + i]);
                 const E4 pr = e4_mul(s, t);
-                for (int k = 0; k < 4; k++, j++) tot = e4_add(tot, e4_scale(mp[j], fmul(active, fsub(acc.c[k], pr.c[k]))));
+                for (int k = 0; k < 4; k++, j++) e4a_mac(lt, mp[j], fmul(active, fsub(acc.c[k], pr.c[k])));
             }
-            tot = e4_add(tot, e4_scale(mp[j], fmul(first, fsub(p.ev_data[i], p.global0))));
+            e4a_mac(lt, mp[j], fmul(first, fsub(p.ev_data[i], p.global0)));
+            const E4 tot = e4a_redc(lt);
             const uint32_t yi = p.yinv[i & 3];
             for (int k = 0; k < 4; k++) p.check[(uint64_t)k * domain + i] = fmul(tot.c[k], yi);
         }

@@ -47,6 +47,9 @@ struct PowBitrevKernel {
 };
 
 static constexpr uint32_t DOT_CPB = 4, DOT_RPB = 4096, DOT_T = 256;
+#ifndef DOT_MINB
+#define DOT_MINB 2  // resident CTAs per SM the register allocation of DotKernel is bounded for
+#endif
 
 // partial[(col * nblk + blk) * 2 + b] = sum over the block's rows of cols[col][r] * Wt[(r + b) mod n]
 // (b = 1 only for col < n_back1).  grid.x = row blocks, grid.y = column groups of DOT_CPB.
@@ -58,8 +61,8 @@ struct DotKernel {
         const uint64_t row0 = (uint64_t)cx.bx * DOT_RPB;
         E4* red = reinterpret_cast<E4*>(sm);  // [DOT_T][DOT_CPB*2]
         for (uint32_t it = cx.tid; it < DOT_T; it += cx.nt) {
-            E4 acc[DOT_CPB][2];
-            for (uint32_t c = 0; c < DOT_CPB; c++) { acc[c][0] = e4_zero(); acc[c][1] = e4_zero(); }
+            E4A acc[DOT_CPB][2];  // lazy 64-bit accumulators (field.cuh): one wide multiply-add per term
+            for (uint32_t c = 0; c < DOT_CPB; c++) { acc[c][0] = e4a_zero(); acc[c][1] = e4a_zero(); }
             // two rows per trip, all loads issued before the multiply-accumulate chains (memory-level parallelism)
             for (uint64_t r = row0 + it; r < row0 + DOT_RPB && r < n; r += 2 * DOT_T) {
                 const uint64_t r2 = r + DOT_T;
@@ -75,11 +78,11 @@ struct DotKernel {
                 }
 #pragma unroll
                 for (uint32_t c = 0; c < DOT_CPB; c++) {
-                    acc[c][0] = e4_add(acc[c][0], e4_add(e4_scale(w0, ta[c]), e4_scale(v0, tb[c])));
-                    if (c0 + c < n_back1) acc[c][1] = e4_add(acc[c][1], e4_add(e4_scale(w1, ta[c]), e4_scale(v1, tb[c])));
+                    e4a_mac(acc[c][0], w0, ta[c]); e4a_mac(acc[c][0], v0, tb[c]);
+                    if (c0 + c < n_back1) { e4a_mac(acc[c][1], w1, ta[c]); e4a_mac(acc[c][1], v1, tb[c]); }
                 }
             }
-            for (uint32_t c = 0; c < DOT_CPB; c++) { red[(it * DOT_CPB + c) * 2] = acc[c][0]; red[(it * DOT_CPB + c) * 2 + 1] = acc[c][1]; }
+            for (uint32_t c = 0; c < DOT_CPB; c++) { red[(it * DOT_CPB + c) * 2] = e4a_redc(acc[c][0]); red[(it * DOT_CPB + c) * 2 + 1] = e4a_redc(acc[c][1]); }
         }
         cx.sync();
         for (uint32_t stride = DOT_T / 2; stride >= 1; stride >>= 1) {
@@ -115,8 +118,9 @@ struct CheckMixKernel {
         const uint64_t n = 1ull << po2;
         const uint64_t i = (uint64_t)cx.bx * cx.nt + cx.tid;
         if (i >= n) return;
-        E4 acc = e4_zero();
-        for (uint32_t c = 0; c < 16; c++) acc = e4_add(acc, e4_scale(mixpow[c], check_coeffs[(uint64_t)c * n + i]));
+        E4A la = e4a_zero();
+        for (uint32_t c = 0; c < 16; c++) e4a_mac(la, mixpow[c], check_coeffs[(uint64_t)c * n + i]);
+        const E4 acc = e4a_redc(la);
         const uint32_t un = tab_pow(rt.ip3_lo, rt.ip3_hi, brev((uint32_t)i, po2));
         for (int k = 0; k < 4; k++) S[(uint64_t)k * n + i] = fmul(acc.c[k], un);
     }
@@ -142,15 +146,17 @@ struct DeepMixKernel {
         const uint64_t n = 1ull << p.po2;
         const uint64_t i = (uint64_t)cx.bx * cx.nt + cx.tid;
         if (i >= n) return;
-        E4 c0 = e4_zero(), c1 = e4_zero();
+        E4A l0 = e4a_zero(), l1 = e4a_zero();  // lazy 64-bit accumulators: one wide multiply-add per (register, component)
         uint32_t reg = 0;
         for (int g = 0; g < 3; g++) {
             const uint32_t* base = p.tr[g] + i;
-            for (uint32_t c = 0; c < p.w[g]; c++, reg++) {
-                const E4 t = e4_scale(p.mixpow[reg], base[(uint64_t)c * n]);
-                if (c < p.n_back1[g]) c1 = e4_add(c1, t); else c0 = e4_add(c0, t);
-            }
+            const uint32_t nb = p.n_back1[g] < p.w[g] ? p.n_back1[g] : p.w[g];
+#pragma unroll 4
+            for (uint32_t c = 0; c < nb; c++, reg++) e4a_mac(l1, p.mixpow[reg], base[(uint64_t)c * n]);
+#pragma unroll 4
+            for (uint32_t c = nb; c < p.w[g]; c++, reg++) e4a_mac(l0, p.mixpow[reg], base[(uint64_t)c * n]);
         }
+        const E4 c0 = e4a_redc(l0), c1 = e4a_redc(l1);
         const uint32_t w = tab_pow(p.rt.f_lo, p.rt.f_hi, (uint32_t)(i << (24 - p.po2)));
         const uint32_t y = fmul(w, INV3);
         // 1/(y - z) = -3/(3z - w^i) ; 1/(y - z w^-1) = -3 w /(3z - w^(i+1))

@@ -117,6 +117,34 @@ HD E4 e4_inv(const E4& a) {
     return r;
 }
 
+// ---- lazy dot products ---------------------------------------------------------------------------------------------
+// sum_i x_i * y_i of canonical residues accumulated as a 64-bit integer with ONE wide multiply-add per term and no
+// per-term Montgomery reduction.  Invariant: hi < p.  A product is < p^2 < 2^62, so hi grows by at most 2^30 + 1 per
+// term and the conditional subtraction of p * 2^32 (one min on the high word) restores hi < p.  redc() then maps the
+// sum to sum * 2^-32 mod p: exactly what the chain fadd(acc, fmul(x_i, y_i)) computes, at a third of the multiplier work.
+struct A64 { uint32_t lo, hi; };
+HD A64 a64_zero() { A64 a; a.lo = 0; a.hi = 0; return a; }
+HD void mac(A64& a, uint32_t x, uint32_t y) {
+    const uint64_t t = (uint64_t)x * y + (((uint64_t)a.hi << 32) | a.lo);
+    const uint32_t h = (uint32_t)(t >> 32);
+    a.lo = (uint32_t)t;
+    a.hi = umin32(h, h - P);
+}
+HD uint32_t redc(const A64& a) {
+    const uint32_t m = a.lo * P_INV;
+#ifdef __CUDA_ARCH__
+    const uint32_t mp = __umulhi(m, P);
+#else
+    const uint32_t mp = (uint32_t)(((uint64_t)m * P) >> 32);
+#endif
+    const uint32_t r = a.hi - mp;
+    return umin32(r, r + P);
+}
+struct E4A { A64 c[4]; };
+HD E4A e4a_zero() { E4A a; a.c[0] = a.c[1] = a.c[2] = a.c[3] = a64_zero(); return a; }
+HD void e4a_mac(E4A& a, const E4& w, uint32_t t) { mac(a.c[0], w.c[0], t); mac(a.c[1], w.c[1], t); mac(a.c[2], w.c[2], t); mac(a.c[3], w.c[3], t); }
+HD E4 e4a_redc(const E4A& a) { return e4(redc(a.c[0]), redc(a.c[1]), redc(a.c[2]), redc(a.c[3])); }
+
 HD int clz32(uint32_t x) {
 #ifdef __CUDA_ARCH__
     return __clz((int)x);
