@@ -247,19 +247,26 @@ struct GlobStridedIO {  // element (pos, batch) of a strided tile: row pos at st
 // blocks tw[2^(l-1) + x] = w_{2^l}^x, so consecutive lanes read consecutive words (no bank conflicts when c = 0).
 // HF: lanes enumerate `high` first (only for c = 0); keeps rounds with l0 < 5 off the same banks.
 // SHP: the table holds canonical (w, w' = floor(w 2^32 / p)) pairs at tw[2 i], tw[2 i + 1] and multiplies use Shoup's form.
-template <int R, bool INV, int K, int C, int L0, bool TWL = false, bool HF = false, bool SHP = false, typename LD, typename ST>
+// PF: software-pipelined loads (two register sets): the loads of the thread's next item are issued before the
+// butterflies of the current one, so a global-facing round does not sit on the long scoreboard.
+template <int R, bool INV, int K, int C, int L0, bool TWL = false, bool HF = false, bool SHP = false, bool PF = false, typename LD, typename ST>
 HD void round_t(const KCtx& cx, const uint32_t* tw, int k_, int c_, int l0_, const LD& L, const ST& S) {
     const int k = K >= 0 ? K : k_, c = C >= 0 ? C : c_, l0 = L0 >= 0 ? L0 : l0_;
     const uint32_t items = 1u << (k - R + c);
     const uint32_t cmask = (1u << c) - 1u, lmask = (1u << l0) - 1u;
     const bool laff = L.affine(l0, c), saff = S.affine(l0, c);
     const uint32_t lstep = L.step(l0, c), sstep = S.step(l0, c);
-    for (uint32_t it = cx.tid; it < items; it += cx.nt) {
-        const uint32_t batch = it & cmask, t = it >> c;
-        const uint32_t nhigh_mask = (items >> (l0 + c)) - 1u;
-        const uint32_t low = HF ? (t >> (k - R - l0)) : (t & lmask), high = HF ? (t & nhigh_mask) : (t >> l0);
-        const uint32_t base = (high << (l0 + R)) | low;
-        uint32_t v[1 << R];
+    const uint32_t nhigh_mask = (items >> (l0 + c)) - 1u;
+    auto split = [&](uint32_t it, uint32_t& batch, uint32_t& low, uint32_t& base) {
+        batch = it & cmask;
+        const uint32_t t = it >> c;
+        low = HF ? (t >> (k - R - l0)) : (t & lmask);
+        const uint32_t high = HF ? (t & nhigh_mask) : (t >> l0);
+        base = (high << (l0 + R)) | low;
+    };
+    auto load = [&](uint32_t it, uint32_t* v) {
+        uint32_t batch, low, base;
+        split(it, batch, low, base);
         if (laff) {
             const uint32_t i0 = L.base(base, batch, c);
 #pragma unroll
@@ -268,6 +275,10 @@ HD void round_t(const KCtx& cx, const uint32_t* tw, int k_, int c_, int l0_, con
 #pragma unroll
             for (int j = 0; j < (1 << R); j++) v[j] = L.ld_i(L.base(base + ((uint32_t)j << l0), batch, c));
         }
+    };
+    auto compute_store = [&](uint32_t it, uint32_t* v) {
+        uint32_t batch, low, base;
+        split(it, batch, low, base);
         if (!INV) {
 #pragma unroll
             for (int q = 1; q <= R; q++) {
@@ -310,6 +321,24 @@ HD void round_t(const KCtx& cx, const uint32_t* tw, int k_, int c_, int l0_, con
 #pragma unroll
             for (int j = 0; j < (1 << R); j++) S.st_i(S.base(base + ((uint32_t)j << l0), batch, c), v[j]);
         }
+    };
+    if constexpr (PF) {
+        const uint32_t nt = (uint32_t)cx.nt;
+        uint32_t v0[1 << R], v1[1 << R];
+        uint32_t it = (uint32_t)cx.tid;
+        if (it < items) load(it, v0);
+        for (; it < items; it += 2 * nt) {
+            if (it + nt < items) load(it + nt, v1);
+            compute_store(it, v0);
+            if (it + 2 * nt < items) load(it + 2 * nt, v0);
+            if (it + nt < items) compute_store(it + nt, v1);
+        }
+    } else {
+        for (uint32_t it = cx.tid; it < items; it += cx.nt) {
+            uint32_t v[1 << R];
+            load(it, v);
+            compute_store(it, v);
+        }
     }
 }
 template <bool INV, bool TWL = false, typename LD, typename ST>
@@ -322,6 +351,12 @@ HD void round_io_dyn(const KCtx& cx, const uint32_t* tw, int k, int c, int l0, i
     }
 }
 
+#ifndef STR_MINB
+#define STR_MINB 2
+#endif
+#ifndef STR_PF
+#define STR_PF false  // software-pipelined global loads in the first round of the strided kernels: measured no gain on B200 (5.35 vs 5.41 ms per 192-column LDE, 120 vs 64 registers), kept as an option
+#endif
 struct Str2Args {
     const uint32_t* in;
     uint32_t* out;                   // may alias `in`
@@ -343,11 +378,11 @@ struct StridedKernel2 {
             // fixed schedule: SB = R0 + R1 + R2 with R0 = 4 on the global-facing first round
             constexpr int R0 = 4, R1 = (SB - 4 + 1) / 2, R2 = SB - 4 - R1;
             if (INV) {
-                round_t<R0, true, SB, SC, SB - R0, false, false, true>(cx, tw, SB, SC, SB - R0, G, S); cx.sync();
+                round_t<R0, true, SB, SC, SB - R0, false, false, true, STR_PF>(cx, tw, SB, SC, SB - R0, G, S); cx.sync();
                 round_t<R1, true, SB, SC, R2, false, false, true>(cx, tw, SB, SC, R2, S, S); cx.sync();
                 round_t<(R2 > 0 ? R2 : 1), true, SB, SC, 0, false, false, true>(cx, tw, SB, SC, 0, S, G);
             } else {
-                round_t<R0, false, SB, SC, 0, false, false, true>(cx, tw, SB, SC, 0, G, S); cx.sync();
+                round_t<R0, false, SB, SC, 0, false, false, true, STR_PF>(cx, tw, SB, SC, 0, G, S); cx.sync();
                 round_t<R1, false, SB, SC, R0, false, false, true>(cx, tw, SB, SC, R0, S, S); cx.sync();
                 round_t<(R2 > 0 ? R2 : 1), false, SB, SC, R0 + R1, false, false, true>(cx, tw, SB, SC, R0 + R1, S, G);
             }
@@ -654,6 +689,7 @@ static inline NttPlan ntt_plan(int n, int e) {
     pl.a = a;
     pl.b = n - a;
     pl.c = pl.b == 0 ? 0 : (14 - pl.b < 5 ? 14 - pl.b : 5);
+    if (const char* env = std::getenv("HFB200_NTT_C")) { int v = std::atoi(env); if (v >= 0 && v <= pl.c) pl.c = v; }
     if (pl.c > pl.a) pl.c = pl.a;
     if (pl.c < 0) pl.c = 0;
     return pl;
@@ -715,15 +751,18 @@ struct Ntt {
         unsigned per_sm = (unsigned)((220 * 1024) / (smem + 1024));
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 4) per_sm = 4;
+        if (const char* env = std::getenv("HFB200_NTT_PER_SM")) { int v = std::atoi(env); if (v >= 1 && v <= 8) per_sm = (unsigned)v; }
         uint64_t grid = (uint64_t)dev->sm_count * per_sm;
         if (grid > tiles) grid = tiles;
         const int key = b * 10000 + c * 100 + a;
         switch (key) {
-            case 100410: dev->launch<StridedKernel2<10, 4, 10>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
-            case 100412: dev->launch<StridedKernel2<10, 4, 12>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
-            case 100411: dev->launch<StridedKernel2<10, 4, 11>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
-            case 100413: dev->launch<StridedKernel2<10, 4, 13>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
-            case 100414: dev->launch<StridedKernel2<10, 4, 14>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
+            case 100310: dev->launch<StridedKernel2<10, 3, 10>, 256, 4>((unsigned)grid, 1, 256, smem, p); break;
+            case 100312: dev->launch<StridedKernel2<10, 3, 12>, 256, 4>((unsigned)grid, 1, 256, smem, p); break;
+            case 100410: dev->launch<StridedKernel2<10, 4, 10>, 256, STR_MINB>((unsigned)grid, 1, 256, smem, p); break;
+            case 100412: dev->launch<StridedKernel2<10, 4, 12>, 256, STR_MINB>((unsigned)grid, 1, 256, smem, p); break;
+            case 100411: dev->launch<StridedKernel2<10, 4, 11>, 256, STR_MINB>((unsigned)grid, 1, 256, smem, p); break;
+            case 100413: dev->launch<StridedKernel2<10, 4, 13>, 256, STR_MINB>((unsigned)grid, 1, 256, smem, p); break;
+            case 100414: dev->launch<StridedKernel2<10, 4, 14>, 256, STR_MINB>((unsigned)grid, 1, 256, smem, p); break;
             case 90510: dev->launch<StridedKernel2<9, 5, 10>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
             case 90512: dev->launch<StridedKernel2<9, 5, 12>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
             case 70510: dev->launch<StridedKernel2<7, 5, 10>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
