@@ -16,7 +16,7 @@ P = 2013265921
 
 # Every symbol include/hfb200.h declares (tests check that the built library exports all of them).
 EXPORTS = [
-    "hfb200_init", "hfb200_init_ir", "hfb200_destroy", "hfb200_free_error", "hfb200_version", "hfb200_host_alloc", "hfb200_host_free",
+    "hfb200_init", "hfb200_init_ir", "hfb200_ir_source", "hfb200_ir_jit_active", "hfb200_destroy", "hfb200_free_error", "hfb200_version", "hfb200_host_alloc", "hfb200_host_free",
     "hfb200_prove_segment", "hfb200_segment_begin", "hfb200_segment_finish", "hfb200_witgen_synth",
     "hfb200_prove_resident", "hfb200_read_group", "hfb200_seal_words", "hfb200_checkpoint", "hfb200_last_stats",
     "hfb200_total_launches", "hfb200_op_interpolate_ntt", "hfb200_op_expand_ntt", "hfb200_op_lde", "hfb200_op_merkle",
@@ -66,6 +66,8 @@ def load_library(path=None):
     sig = {
         "hfb200_init": (err, [C.c_int, u32, C.POINTER(CircuitDesc), C.POINTER(vp)]),
         "hfb200_init_ir": (err, [C.c_int, u32, C.POINTER(CircuitIR), C.POINTER(vp)]),
+        "hfb200_ir_source": (err, [C.POINTER(CircuitIR), C.c_char_p, sz, C.POINTER(sz)]),
+        "hfb200_ir_jit_active": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "hfb200_destroy": (None, [vp]),
         "hfb200_free_error": (None, [vp]),
         "hfb200_version": (C.c_char_p, []),
@@ -302,6 +304,12 @@ class Context:
         self._check(self.lib.hfb200_bench_merkle(self._h, po2, count, iters, C.byref(ms)))
         return ms.value
 
+    def ir_jit_active(self):
+        """(active, compile_ms): whether eval_check of this data-defined circuit runs the NVRTC-specialised kernel."""
+        ms = C.c_float()
+        a = self.lib.hfb200_ir_jit_active(self._h, C.byref(ms))
+        return bool(a), ms.value
+
     def bench_modmul(self, kind, iters=1 << 15):
         """Modular products per second of instruction sequence `kind` (0 Montgomery, 1 Shoup, 2 S-box chain)."""
         r = C.c_double()
@@ -317,6 +325,22 @@ class Context:
         ms = C.c_float()
         self._check(self.lib.hfb200_mark_elapsed(self._h, slot_a, other._h, slot_b, C.byref(ms)))
         return ms.value
+
+
+def ir_source(ir, circuit, lib=None):
+    """CUDA source that hfb200_init_ir compiles for the eval_check of a data-defined circuit (needs no device)."""
+    lib = lib or load_library()
+    taps, steps = _u32(ir["taps"]), _u32(ir["steps"])
+    desc = CircuitIR(circuit[0], circuit[1], circuit[2], int(ir["n_mix"]), taps.ctypes.data, taps.size // 3, steps.ctypes.data, steps.size // 4, int(ir["ret"]))
+    need = C.c_size_t()
+    e = lib.hfb200_ir_source(C.byref(desc), None, 0, C.byref(need))
+    if e:
+        msg = C.cast(e, C.c_char_p).value.decode(errors="replace"); lib.hfb200_free_error(e); raise Hfb200Error(msg)
+    buf = C.create_string_buffer(need.value)
+    e = lib.hfb200_ir_source(C.byref(desc), buf, need.value, C.byref(need))
+    if e:
+        msg = C.cast(e, C.c_char_p).value.decode(errors="replace"); lib.hfb200_free_error(e); raise Hfb200Error(msg)
+    return buf.value.decode()
 
 
 class Pool:

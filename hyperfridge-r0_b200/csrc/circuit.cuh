@@ -353,6 +353,7 @@ struct GenericCircuitHost {
         for (auto& c : combos) combo_begin.push_back(combo_begin.back() + (uint32_t)c.size());
         for (size_t r = 0; r < regs.size(); r++) regs[r].combo = (uint32_t)(std::lower_bound(combos.begin(), combos.end(), backsets[r]) - combos.begin());
         compile(st, n_steps, ret);
+        if (!dev) return;  // analysis only (hfb200_ir_source)
         // device tables
         d_prog = (BcIns*)dev->alloc(prog.size() * sizeof(BcIns));
         dev->h2d(d_prog, prog.data(), prog.size() * sizeof(BcIns));

@@ -68,6 +68,22 @@ const char* hfb200_init_ir(int device, uint32_t max_po2, const hfb200_circuit_ir
     *out = ctx;
     API_CATCH
 }
+const char* hfb200_ir_source(const hfb200_circuit_ir* c, char* out, size_t cap, size_t* need) {
+    API_TRY
+    if (!c) throw Err("hfb200_ir_source: NULL circuit");
+    GenericCircuitHost g;
+    g.init(nullptr, c->w_code, c->w_data, c->w_accum, c->n_mix, reinterpret_cast<const IrTap*>(c->taps), c->n_taps,
+           reinterpret_cast<const IrStep*>(c->steps), c->n_steps, c->ret);
+    const std::string src = jit_source(g);
+    if (need) *need = src.size() + 1;
+    if (out && cap) { const size_t n = std::min(cap - 1, src.size()); std::memcpy(out, src.data(), n); out[n] = 0; }
+    API_CATCH
+}
+int hfb200_ir_jit_active(const hfb200_ctx* ctx, float* compile_ms) {
+    if (!ctx) return 0;
+    if (compile_ms) *compile_ms = ctx->p.jit.compile_ms;
+    return ctx->p.jit.ready ? 1 : 0;
+}
 void hfb200_destroy(hfb200_ctx* ctx) {
     if (!ctx) return;
 #ifndef HFB200_EMU

@@ -10,6 +10,7 @@
 #include "poseidon2.cuh"
 #include "circuit.cuh"
 #include "deep.cuh"
+#include "jit.cuh"
 
 namespace hf {
 
@@ -51,6 +52,7 @@ struct Prover {
     Merkle merkle;
     CircuitHost cir;
     GenericCircuitHost gen;  // active for data-defined circuits (hfb200_init_ir)
+    JitEvalCheck jit;        // their eval_check, specialised at registration (NVRTC, sm_100a)
     uint32_t max_po2 = 0;
     int device_id = 0;
     Arena arena;
@@ -113,6 +115,7 @@ struct Prover {
         merkle.init(&dev);
         if (taps) {
             gen.init(&dev, wc, wd, wa, n_mix_ir, taps, n_taps, steps, n_steps, ret);
+            jit.init(gen);
             cir.init_widths(wc, wd, wa, (uint32_t)gen.taps.size(), n_mix_ir);
         } else {
             cir.init(&dev, wc, wd, wa);
@@ -123,6 +126,7 @@ struct Prover {
     }
     void destroy() {
         dev.free(arena.base);
+        jit.destroy();
         gen.destroy(&dev);
         cir.destroy(&dev);
         ntt.destroy();
@@ -362,6 +366,14 @@ struct Prover {
             dev.h2d(d_mp, mp.data(), mp.size() * sizeof(E4));
             uint32_t* d_gl = arena.take<uint32_t>(N_GLOBAL);
             dev.h2d(d_gl, globals, N_GLOBAL * 4);
+            if (jit.ready) {
+                JitEvalArgs ja{};
+                ja.ev[0] = ev[GROUP_ACCUM]; ja.ev[1] = ev[GROUP_CODE]; ja.ev[2] = ev[GROUP_DATA];
+                ja.check = check; ja.mixpow = d_mp; ja.mix = d_mix; ja.globals = d_gl; ja.po2 = po2;
+                for (int s_ = 0; s_ < 4; s_++) ja.yinv[s_] = yinv4[s_];
+                jit.launch(dev, ja, D);
+                dev.sync();
+            } else {
             GenEvalArgs a{};
             a.ev[0] = ev[GROUP_ACCUM]; a.ev[1] = ev[GROUP_CODE]; a.ev[2] = ev[GROUP_DATA];
             a.check = check; a.prog = gen.d_prog; a.n_ins = (uint32_t)gen.prog.size(); a.mixpow = d_mp; a.mix = d_mix; a.globals = d_gl;
@@ -375,6 +387,7 @@ struct Prover {
             a.rows_per_block = R;
             dev.launch<GenEvalCheckKernel, 128, 1>((unsigned)((D + R - 1) / R), 1, (int)R, per_row * R + (N_GLOBAL + gen.n_mix) * 4 + 16, a);
             dev.sync();
+            }
         } else {
             const uint32_t nc = cd.n_constraints();
             std::vector<E4> mp(nc);

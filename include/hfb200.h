@@ -70,6 +70,12 @@ typedef struct {
 const char* hfb200_init(int device, uint32_t max_po2, const hfb200_circuit_desc* circuit, hfb200_ctx** out);
 /* Same, for a circuit given as data. */
 const char* hfb200_init_ir(int device, uint32_t max_po2, const hfb200_circuit_ir* circuit, hfb200_ctx** out);
+/* The CUDA source hfb200_init_ir compiles (NVRTC, sm_100a) for the circuit's eval_check: straight-line code, one thread
+ * per LDE row.  Needs no device.  Writes at most `cap` bytes including the terminating NUL; *need = bytes required. */
+const char* hfb200_ir_source(const hfb200_circuit_ir* circuit, char* out, size_t cap, size_t* need);
+/* 1 when the context's eval_check runs the NVRTC-specialised kernel, 0 when it runs the interpreter kernel (built-in
+ * circuit: 0).  *compile_ms (may be NULL) = time hfb200_init_ir spent generating + compiling + loading it. */
+int hfb200_ir_jit_active(const hfb200_ctx* ctx, float* compile_ms);
 void hfb200_destroy(hfb200_ctx* ctx);
 void hfb200_free_error(const char* msg);
 const char* hfb200_version(void);

@@ -77,3 +77,28 @@ def test_ir_validation(pkg, emu_lib):
     bad(ret=10**6)                                               # ret is not a mix var
     many = np.array([(2, 0, b) for b in range(6)] + [(2, c, 0) for c in range(1, SMALL[1])], np.uint32)
     bad(taps=many)                                               # > 4 taps on one register
+
+
+@pytest.mark.parametrize("variant,nest", [(0, False), (1, True)])
+def test_jit_source_compiles_for_sm100a(pkg, tmp_path, variant, nest):
+    """hfb200_ir_source (no device needed): the eval_check kernel hfb200_init_ir specialises with NVRTC is straight-line
+    CUDA that nvcc accepts for sm_100a -- one statement per bytecode instruction, no interpreter loop."""
+    import shutil
+    import subprocess
+    from oracle import synth_ir
+    widths = (12, 24, 8)
+    ir = synth_ir.build(widths, variant, nest=nest)
+    src = pkg.ir_source(ir, widths)
+    assert "hfb200_eval_check_jit" in src and "e4a_mac" in src and "switch" not in src
+    n_steps = len(ir["steps"])
+    body = src[src.index("hfb200_eval_check_jit"):]
+    assert body.count(";\n") >= n_steps  # every IR step became a statement
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cu = tmp_path / "jit.cu"
+    cu.write_text(src)
+    out = tmp_path / "jit.cubin"
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-cubin", "-o", str(out), str(cu)])
+    assert out.stat().st_size > 1000
+    with pytest.raises(pkg.Hfb200Error):
+        bad = dict(ir); bad["ret"] = 10 ** 6
+        pkg.ir_source(bad, widths)

@@ -229,3 +229,26 @@ def test_data_defined_circuit_on_gpu(pkg, gpu_lib, orc, widths, po2, variant, ne
                 assert (cps[k] == v).all(), k
         assert len(seal) == len(oseal) and (seal == oseal).all()
         assert cir_ir.verify(seal, ocps["code_root"]) == po2
+
+
+@pytest.mark.gpu
+def test_jit_and_interpreter_agree_on_gpu(pkg, gpu_lib, orc, monkeypatch):
+    """The NVRTC-specialised eval_check (default) and the interpreter kernel (HFB200_IR_JIT=0) give the same seal, equal
+    to the oracle's; the JIT really is the path in use."""
+    from oracle import synth_ir
+    widths, po2, variant = (16, 64, 16), 13, 1
+    cir = orc.Circuit(*widths, variant=variant)
+    code = cir.gen_code(po2); g = cir.gen_globals(5); data = cir.gen_data(po2, code, g, 5, 1)
+    ir = synth_ir.build(widths, variant, nest=True)
+    cir_ir = orc.Circuit(*widths, variant=variant)
+    cir_ir.set_ir(ir["taps"], ir["steps"], ir["ret"])
+    oseal, ocps, _ = cir_ir.prove(po2, g, code, data, 1)
+    seals = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("HFB200_IR_JIT", mode)
+        with pkg.Context(0, po2, widths, lib=gpu_lib, ir=ir) as c:
+            active, ms = c.ir_jit_active()
+            assert active == (mode == "1"), (mode, active)
+            mix = c.segment_begin(po2, g, code, data, 1)
+            seals[mode] = c.segment_finish(cir.step_accum(po2, data, mix, 1))
+    assert (seals["1"] == oseal).all() and (seals["0"] == oseal).all()

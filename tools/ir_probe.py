@@ -19,6 +19,6 @@ with pkg.Context(0, po2, W) as a, pkg.Context(0, po2, W, ir=ir) as b:
     for _ in range(2):
         b.segment_begin(po2, g, code, data, 1)
         sb = b.segment_finish(accum)
-    print("seal equal:", (sa == sb).all(), "steps", len(ir["steps"]))
+    print("seal equal:", (sa == sb).all(), "steps", len(ir["steps"]), "jit (active, compile ms):", b.ir_jit_active())
     print("built-in :", {k: round(v, 2) for k, v in a.last_stats().items() if k.startswith("ms_")})
     print("data-def.:", {k: round(v, 2) for k, v in b.last_stats().items() if k.startswith("ms_")})
