@@ -230,7 +230,7 @@ struct OpenKernel {  // grid.x = descriptors
 // ---- DEEP kernels for data-defined circuits: arbitrary tap sets (<= 4 distinct backs, <= 8 distinct back-sets) -------
 namespace hf {
 
-static constexpr uint32_t DOTG_T = 128;
+static constexpr uint32_t DOTG_T = 128, DOTG_CPB = 2;  // 2 columns x 4 backs x 8 accumulator words per thread
 struct Backs4 { uint32_t nb; uint32_t back[GEN_MAX_BACKS]; };
 
 // partial[((col * nblk + blk) * 4) + s] = sum over the block's rows of cols[col][r] * Wt[(r + back[s]) mod n]
@@ -240,34 +240,34 @@ struct DotKernelG {
     HD static void run(const KCtx& cx, uint32_t* sm, const uint32_t* cols, uint64_t col_stride, uint32_t ncols, const uint8_t* colmask, Backs4 bk,
                        const E4* Wt, uint32_t po2, E4* partial) {
         const uint64_t n = 1ull << po2;
-        const uint32_t nblk = cx.gx, c0 = cx.by * DOT_CPB;
+        const uint32_t nblk = cx.gx, c0 = cx.by * DOTG_CPB;
         const uint64_t row0 = (uint64_t)cx.bx * DOT_RPB;
-        E4* red = reinterpret_cast<E4*>(sm);  // [DOTG_T][DOT_CPB * 4]
+        E4* red = reinterpret_cast<E4*>(sm);  // [DOTG_T][DOTG_CPB * 4]
         for (uint32_t it = cx.tid; it < DOTG_T; it += cx.nt) {
-            E4 acc[DOT_CPB][GEN_MAX_BACKS];
-            uint32_t mask[DOT_CPB];
-            for (uint32_t c = 0; c < DOT_CPB; c++) {
+            E4A acc[DOTG_CPB][GEN_MAX_BACKS];  // lazy 64-bit accumulators (field.cuh)
+            uint32_t mask[DOTG_CPB];
+            for (uint32_t c = 0; c < DOTG_CPB; c++) {
                 mask[c] = c0 + c < ncols ? colmask[c0 + c] : 0u;
-                for (uint32_t s = 0; s < GEN_MAX_BACKS; s++) acc[c][s] = e4_zero();
+                for (uint32_t s = 0; s < GEN_MAX_BACKS; s++) acc[c][s] = e4a_zero();
             }
             for (uint64_t r = row0 + it; r < row0 + DOT_RPB && r < n; r += DOTG_T) {
                 E4 w[GEN_MAX_BACKS];
 #pragma unroll
                 for (uint32_t s = 0; s < GEN_MAX_BACKS; s++) w[s] = s < bk.nb ? Wt[(r + bk.back[s]) & (n - 1)] : e4_zero();
 #pragma unroll
-                for (uint32_t c = 0; c < DOT_CPB; c++) {
+                for (uint32_t c = 0; c < DOTG_CPB; c++) {
                     if (c0 + c >= ncols) break;
                     const uint32_t t = cols[(uint64_t)(c0 + c) * col_stride + r];
 #pragma unroll
                     for (uint32_t s = 0; s < GEN_MAX_BACKS; s++)
-                        if ((mask[c] >> s) & 1u) acc[c][s] = e4_add(acc[c][s], e4_scale(w[s], t));
+                        if ((mask[c] >> s) & 1u) e4a_mac(acc[c][s], w[s], t);
                 }
             }
-            for (uint32_t c = 0; c < DOT_CPB; c++)
-                for (uint32_t s = 0; s < GEN_MAX_BACKS; s++) red[(it * DOT_CPB + c) * GEN_MAX_BACKS + s] = acc[c][s];
+            for (uint32_t c = 0; c < DOTG_CPB; c++)
+                for (uint32_t s = 0; s < GEN_MAX_BACKS; s++) red[(it * DOTG_CPB + c) * GEN_MAX_BACKS + s] = e4a_redc(acc[c][s]);
         }
         cx.sync();
-        const uint32_t K = DOT_CPB * GEN_MAX_BACKS;
+        const uint32_t K = DOTG_CPB * GEN_MAX_BACKS;
         for (uint32_t stride = DOTG_T / 2; stride >= 1; stride >>= 1) {
             for (uint32_t w = cx.tid; w < stride * K; w += cx.nt) {
                 const uint32_t it = w / K, k = w % K;
@@ -318,11 +318,13 @@ struct DeepMixKernelG {
         const uint32_t y = fmul(w, INV3);
         E4 r = e4_zero();
         for (uint32_t c = 0; c < p.n_combos; c++) {
-            E4 tot = e4_zero();
+            E4A lt = e4a_zero();
+#pragma unroll 4
             for (uint32_t k = p.combo_start[c]; k < p.combo_start[c + 1]; k++) {
                 const uint32_t rc = p.regcol[k];
-                tot = e4_add(tot, e4_scale(p.regmix[k], p.tr[rc >> 28][(uint64_t)(rc & 0x0FFFFFFFu) * n + i]));
+                e4a_mac(lt, p.regmix[k], p.tr[rc >> 28][(uint64_t)(rc & 0x0FFFFFFFu) * n + i]);
             }
+            const E4 tot = e4a_redc(lt);
             E4 u = e4_zero();
             for (uint32_t k = p.combo_nb[c]; k-- > 0;) u = e4_add(e4_scale(u, y), p.U[c][k]);
             E4 q = e4_sub(tot, u);

@@ -305,7 +305,7 @@ struct Prover {
         const uint32_t nblk = (uint32_t)((N + DOT_RPB - 1) / DOT_RPB);
         const size_t save = arena.off;
         E4* partial = arena.take<E4>((size_t)w * nblk * GEN_MAX_BACKS);
-        dev.launch<DotKernelG, 128, 1>(nblk, (w + DOT_CPB - 1) / DOT_CPB, DOTG_T, (size_t)DOTG_T * DOT_CPB * GEN_MAX_BACKS * sizeof(E4), cols, (uint64_t)N, w, colmask, bk, Wt, po2, partial);
+        dev.launch<DotKernelG, 128, 3>(nblk, (w + DOTG_CPB - 1) / DOTG_CPB, DOTG_T, (size_t)DOTG_T * DOTG_CPB * GEN_MAX_BACKS * sizeof(E4), cols, (uint64_t)N, w, colmask, bk, Wt, po2, partial);
         dev.launch<DotReduceKernelG, 128, 1>((GEN_MAX_BACKS * w + 127) / 128, 1, 128, 0, (const E4*)partial, w, nblk, out_dev);
         arena.off = save;
     }
