@@ -186,6 +186,10 @@ struct EvalCheckArgs {
 // One thread per LDE row; every operand is a coalesced 128-byte line across the warp (served by L2 after the first
 // touch).  A shared-memory row-tile variant (stage all 272 columns of 64 rows, two threads per row) was measured at
 // 20.2 ms against 3.8 ms for this kernel: 78 KB of tile per 128 threads leaves 8 warps per SM (profiles/README.md).
+#ifndef EC_UNROLL
+#define EC_UNROLL 4
+#endif
+static constexpr int kEcUnroll = EC_UNROLL;  // constraints whose operand loads are in flight together
 struct EvalCheckKernel {
     static constexpr bool kBarrier = true;
     HD static void run(const KCtx& cx, uint32_t* sm, EvalCheckArgs p) {
@@ -204,7 +208,7 @@ struct EvalCheckKernel {
             const uint32_t active = p.ev_code[i], first = p.ev_code[domain + i];
             E4A lt = e4a_zero();  // sum_j mixpow[j] * constraint_j in lazy 64-bit accumulators (field.cuh)
             uint32_t j = 0;
-#pragma unroll 4
+#pragma unroll kEcUnroll
             for (uint32_t k = 0; k < cd.n_free; k++, j++) {
                 const uint16_t* pk = spk + 6 * k;
                 const uint32_t e = derived_expr(k, p.ev_data[(uint64_t)pk[0] * domain + i], p.ev_data[(uint64_t)pk[1] * domain + i], p.ev_data[(uint64_t)pk[2] * domain + i],
