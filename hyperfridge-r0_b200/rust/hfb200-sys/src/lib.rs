@@ -68,6 +68,10 @@ pub struct hfb200_segment_job {
 extern "C" {
     pub fn hfb200_init(device: c_int, max_po2: u32, circuit: *const hfb200_circuit_desc, out: *mut *mut hfb200_ctx) -> *const c_char;
     pub fn hfb200_init_ir(device: c_int, max_po2: u32, circuit: *const hfb200_circuit_ir, out: *mut *mut hfb200_ctx) -> *const c_char;
+    /// CUDA source of the eval_check kernel `hfb200_init_ir` specialises with NVRTC (no device needed).
+    pub fn hfb200_ir_source(circuit: *const hfb200_circuit_ir, out: *mut c_char, cap: usize, need: *mut usize) -> *const c_char;
+    /// 1 when the context's eval_check runs the NVRTC-specialised kernel (0: interpreter kernel / built-in circuit).
+    pub fn hfb200_ir_jit_active(ctx: *const hfb200_ctx, compile_ms: *mut f32) -> c_int;
     pub fn hfb200_destroy(ctx: *mut hfb200_ctx);
     pub fn hfb200_free_error(msg: *const c_char);
     pub fn hfb200_seal_words(ctx: *const hfb200_ctx, po2: u32) -> usize;
