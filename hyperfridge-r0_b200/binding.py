@@ -16,7 +16,7 @@ P = 2013265921
 
 # Every symbol include/hfb200.h declares (tests check that the built library exports all of them).
 EXPORTS = [
-    "hfb200_init", "hfb200_init_ir", "hfb200_ir_source", "hfb200_ir_jit_active", "hfb200_destroy", "hfb200_free_error", "hfb200_version", "hfb200_host_alloc", "hfb200_host_free",
+    "hfb200_init", "hfb200_init_ir", "hfb200_ir_source", "hfb200_ir_jit_active", "hfb200_verify_segment", "hfb200_control_root", "hfb200_destroy", "hfb200_free_error", "hfb200_version", "hfb200_host_alloc", "hfb200_host_free",
     "hfb200_prove_segment", "hfb200_segment_begin", "hfb200_segment_finish", "hfb200_witgen_synth",
     "hfb200_prove_resident", "hfb200_read_group", "hfb200_seal_words", "hfb200_checkpoint", "hfb200_last_stats",
     "hfb200_total_launches", "hfb200_op_interpolate_ntt", "hfb200_op_expand_ntt", "hfb200_op_lde", "hfb200_op_merkle",
@@ -68,6 +68,8 @@ def load_library(path=None):
         "hfb200_init_ir": (err, [C.c_int, u32, C.POINTER(CircuitIR), C.POINTER(vp)]),
         "hfb200_ir_source": (err, [C.POINTER(CircuitIR), C.c_char_p, sz, C.POINTER(sz)]),
         "hfb200_ir_jit_active": (C.c_int, [vp, C.POINTER(C.c_float)]),
+        "hfb200_verify_segment": (err, [C.POINTER(CircuitDesc), C.POINTER(CircuitIR), vp, sz, vp, C.POINTER(u32)]),
+        "hfb200_control_root": (err, [vp, u32, vp, vp]),
         "hfb200_destroy": (None, [vp]),
         "hfb200_free_error": (None, [vp]),
         "hfb200_version": (C.c_char_p, []),
@@ -304,6 +306,13 @@ class Context:
         self._check(self.lib.hfb200_bench_merkle(self._h, po2, count, iters, C.byref(ms)))
         return ms.value
 
+    def control_root(self, po2, code):
+        """Control id of (circuit, po2): Merkle root of the committed code group (computed on the GPU)."""
+        code = _u32(code)
+        out = np.empty(8, np.uint32)
+        self._check(self.lib.hfb200_control_root(self._h, po2, _ptr(code), _ptr(out)))
+        return out
+
     def ir_jit_active(self):
         """(active, compile_ms): whether eval_check of this data-defined circuit runs the NVRTC-specialised kernel."""
         ms = C.c_float()
@@ -325,6 +334,28 @@ class Context:
         ms = C.c_float()
         self._check(self.lib.hfb200_mark_elapsed(self._h, slot_a, other._h, slot_b, C.byref(ms)))
         return ms.value
+
+
+def verify_segment(seal, code_root, circuit=(16, 192, 48), ir=None, lib=None):
+    """`Receipt::verify` for one segment seal (hfb200_verify_segment; host-side like the reference's verifier, no GPU
+    needed).  Returns the segment's po2; raises Hfb200Error with the reason when the seal is rejected."""
+    lib = lib or load_library()
+    seal, code_root = _u32(seal), _u32(code_root)
+    if code_root.size != 8:
+        raise Hfb200Error("verify_segment: code_root must have 8 words")
+    po2 = C.c_uint32()
+    if ir is not None:
+        taps, steps = _u32(ir["taps"]), _u32(ir["steps"])
+        d = CircuitIR(circuit[0], circuit[1], circuit[2], int(ir["n_mix"]), taps.ctypes.data, taps.size // 3, steps.ctypes.data, steps.size // 4, int(ir["ret"]))
+        e = lib.hfb200_verify_segment(None, C.byref(d), _ptr(seal), seal.size, _ptr(code_root), C.byref(po2))
+    else:
+        d = CircuitDesc(circuit[0], circuit[1], circuit[2], 0)
+        e = lib.hfb200_verify_segment(C.byref(d), None, _ptr(seal), seal.size, _ptr(code_root), C.byref(po2))
+    if e:
+        msg = C.cast(e, C.c_char_p).value.decode(errors="replace")
+        lib.hfb200_free_error(e)
+        raise Hfb200Error(msg)
+    return po2.value
 
 
 def ir_source(ir, circuit, lib=None):

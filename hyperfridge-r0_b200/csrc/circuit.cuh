@@ -243,6 +243,16 @@ struct CircuitHost {
     uint16_t* tab_mem = nullptr;
     std::vector<uint16_t> h_picks, h_chain_src;
     void init(Dev* dev, uint32_t wc, uint32_t wd, uint32_t wa) {
+        init_host(wc, wd, wa);
+        tab_mem = (uint16_t*)dev->alloc((h_picks.size() + h_chain_src.size()) * 2 + 16);
+        dev->h2d(tab_mem, h_picks.data(), h_picks.size() * 2);
+        dev->h2d(tab_mem + h_picks.size(), h_chain_src.data(), h_chain_src.size() * 2);
+        dev->sync();
+        cd.picks = tab_mem;
+        cd.chain_src = tab_mem + h_picks.size();
+    }
+    // host tables only (also what the verifier needs)
+    void init_host(uint32_t wc, uint32_t wd, uint32_t wa) {
         if (wc < CODE_FIXED + 1 || wd < 8 || (wd & 3) || wa < 4 || (wa & 3) || wc > 4096 || wd > 4096 || wa > 4096) throw Err("circuit: unsupported widths");
         cd.w_code = wc; cd.w_data = wd; cd.w_accum = wa;
         cd.n_free = wd / 2; cd.n_prev = cd.n_free / 2; cd.n_chains = wa / 4;
@@ -258,12 +268,6 @@ struct CircuitHost {
         }
         h_chain_src.resize(cd.n_chains);
         for (uint32_t r = 0; r < cd.n_chains; r++) h_chain_src[r] = (uint16_t)((13 * r + 5) % wd);
-        tab_mem = (uint16_t*)dev->alloc((h_picks.size() + h_chain_src.size()) * 2 + 16);
-        dev->h2d(tab_mem, h_picks.data(), h_picks.size() * 2);
-        dev->h2d(tab_mem + h_picks.size(), h_chain_src.data(), h_chain_src.size() * 2);
-        dev->sync();
-        cd.picks = tab_mem;
-        cd.chain_src = tab_mem + h_picks.size();
         // taps: accum all {0,1}; code all {0}; data: columns < n_prev {0,1}, others {0}
         n_taps = 2 * wa + wc + wd + cd.n_prev;
     }
@@ -330,6 +334,14 @@ struct GenericCircuitHost {
         if (!tp || !st || n_taps == 0 || n_steps == 0) throw Err("circuit: empty tap table or step list");
         w[GROUP_ACCUM] = wa; w[GROUP_CODE] = wc; w[GROUP_DATA] = wd; n_mix = n_mix_;
         if (wc == 0 || wd == 0 || wa == 0 || wc > 65535 || wd > 65535 || wa > 65535) throw Err("circuit: bad group widths");
+        analyze_taps(tp, n_taps);
+        compile(st, n_steps, ret);
+        if (!dev) return;  // analysis only (hfb200_ir_source, verifier)
+        upload(dev);
+    }
+    // tap table -> registers, tap sets ("combos"), distinct backs.  w[] must be set.
+    void analyze_taps(const IrTap* tp, size_t n_taps) {
+        regs.clear(); backs.clear();
         taps.assign(tp, tp + n_taps);
         std::vector<std::vector<uint32_t>> backsets;
         for (size_t i = 0; i < taps.size();) {
@@ -356,8 +368,8 @@ struct GenericCircuitHost {
         combo_begin.assign(1, 0);
         for (auto& c : combos) combo_begin.push_back(combo_begin.back() + (uint32_t)c.size());
         for (size_t r = 0; r < regs.size(); r++) regs[r].combo = (uint32_t)(std::lower_bound(combos.begin(), combos.end(), backsets[r]) - combos.begin());
-        compile(st, n_steps, ret);
-        if (!dev) return;  // analysis only (hfb200_ir_source)
+    }
+    void upload(Dev* dev) {
         // device tables
         d_prog = (BcIns*)dev->alloc(prog.size() * sizeof(BcIns));
         dev->h2d(d_prog, prog.data(), prog.size() * sizeof(BcIns));

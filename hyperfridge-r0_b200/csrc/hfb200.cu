@@ -2,6 +2,7 @@
 #include "../../include/hfb200.h"
 #include "prover.cuh"
 #include "probe.cuh"
+#include "verify.cuh"
 #include <algorithm>
 #include <atomic>
 #include <memory>
@@ -383,6 +384,34 @@ const char* hfb200_bench_merkle(hfb200_ctx* ctx, uint32_t po2, uint32_t count, u
     API_CATCH
 }
 
+const char* hfb200_verify_segment(const hfb200_circuit_desc* c, const hfb200_circuit_ir* ir, const uint32_t* seal, size_t seal_words,
+                                  const uint32_t* code_root, uint32_t* po2_out) {
+    API_TRY
+    if ((c == nullptr) == (ir == nullptr)) throw Err("hfb200_verify_segment: pass exactly one of circuit / ir");
+    if (!seal || !code_root) throw Err("hfb200_verify_segment: NULL seal or code_root");
+    VCircuit vc;
+    if (c) vc.init_builtin(c->w_code, c->w_data, c->w_accum);
+    else vc.init_ir(ir->w_code, ir->w_data, ir->w_accum, ir->n_mix, reinterpret_cast<const IrTap*>(ir->taps), ir->n_taps,
+                    reinterpret_cast<const IrStep*>(ir->steps), ir->n_steps, ir->ret);
+    verify_segment(vc, seal, seal_words, code_root, po2_out);
+    API_CATCH
+}
+const char* hfb200_control_root(hfb200_ctx* ctx, uint32_t po2, const uint32_t* code, uint32_t* root_out) {
+    API_TRY
+    if (!ctx || !code || !root_out) throw Err("hfb200_control_root: NULL argument");
+    Prover& p = ctx->p;
+    p.bind();
+    p.layout(po2);
+    const size_t N = (size_t)1 << po2, D = 4 * N;
+    const uint32_t w = p.cir.group_width(GROUP_CODE);
+    p.dev.h2d(p.tr[GROUP_CODE], code, (size_t)w * N * 4);
+    p.ntt.lde(p.tr[GROUP_CODE], N, p.ev[GROUP_CODE], D, p.scratch, w, (int)po2);
+    p.merkle.build(p.ev[GROUP_CODE], D, (uint32_t)D, w, p.nodes[GROUP_CODE]);
+    p.dev.d2h(root_out, p.nodes[GROUP_CODE] + 8, 32);  // heap layout: node 1 is the root
+    p.dev.sync();
+    p.have_trace = false;  // the resident trace (if any) lost its code group
+    API_CATCH
+}
 const char* hfb200_bench_modmul(hfb200_ctx* ctx, int kind, uint32_t iters, double* products_per_s) {
     API_TRY
     if (!ctx || !products_per_s) throw Err("bench_modmul: NULL argument");

@@ -95,3 +95,31 @@ class Receipt:
 
     def seal_bytes(self) -> int:
         return 0 if isinstance(self.inner, str) else sum(4 * len(s.seal) for s in self.inner.segments)
+
+    def verify(self, control_ids, circuit=(16, 192, 48), ir=None, lib=None) -> None:
+        """`receipt.verify(HYPERFRIDGE_ID)` of the reference (/root/reference/host/src/main.rs:622-624,
+        /root/reference/verifier/src/main.rs:124-126) for the part this path owns: every segment seal is checked by
+        `hfb200_verify_segment` against the control id of its po2 (`control_ids`: {po2: 8 words}, the analogue of upstream's
+        per-po2 control-id table), segment indices must run 0..n-1, and a dev-mode `Fake` receipt is refused exactly like
+        upstream refuses it outside RISC0_DEV_MODE.  The claim chain (pre/post state digests, image id) belongs to the
+        executor side and is carried opaquely.  Raises Hfb200Error with the reason."""
+        from .binding import verify_segment, Hfb200Error
+        if isinstance(self.inner, str):
+            raise Hfb200Error("verify: %s receipt carries no seal (dev-mode receipts are refused)" % self.inner)
+        segs = self.inner.segments
+        if not segs:
+            raise Hfb200Error("verify: composite receipt without segments")
+        for want, s in enumerate(segs):
+            if s.index != want:
+                raise Hfb200Error("verify: segment index %d at position %d" % (s.index, want))
+            if s.hashfn != "poseidon2":
+                raise Hfb200Error("verify: hash suite %r is not on this path" % s.hashfn)
+            if len(s.seal) < 33:
+                raise Hfb200Error("verify: segment %d: seal truncated" % want)
+            po2 = int(s.seal[32])  # seal layout: 32 globals, po2, ...
+            if po2 not in control_ids:
+                raise Hfb200Error("verify: segment %d: no control id for po2 %d" % (want, po2))
+            try:
+                verify_segment(s.seal, control_ids[po2], circuit, ir=ir, lib=lib)
+            except Hfb200Error as e:
+                raise Hfb200Error("segment %d: %s" % (want, e)) from None

@@ -90,6 +90,13 @@ extern "C" {
     ) -> *const c_char;
     pub fn hfb200_pool_prove(pool: *mut hfb200_pool, jobs: *mut hfb200_segment_job, n_jobs: usize) -> *const c_char;
     pub fn hfb200_pool_destroy(pool: *mut hfb200_pool);
+    /// `Receipt::verify` for one segment seal (host code, no device needed).  Exactly one of `circuit` / `ir` is non-null.
+    pub fn hfb200_verify_segment(
+        circuit: *const hfb200_circuit_desc, ir: *const hfb200_circuit_ir, seal: *const u32, seal_words: usize,
+        code_root: *const u32, po2_out: *mut u32,
+    ) -> *const c_char;
+    /// Control id of (circuit, po2): Merkle root of the committed control columns, computed on the GPU.
+    pub fn hfb200_control_root(ctx: *mut hfb200_ctx, po2: u32, code: *const u32, root_out: *mut u32) -> *const c_char;
 }
 
 /// Same contract as `risc0_sys::ffi_wrap`.

@@ -117,6 +117,18 @@ size_t hfb200_seal_words(const hfb200_ctx* ctx, uint32_t po2);
  *        final_poly_hash fri_root_<r> fri_mix_<r> fri_final_hash query_positions */
 const char* hfb200_checkpoint(hfb200_ctx* ctx, const char* name, uint32_t* out, size_t cap, size_t* n_words);
 
+/* ---- verification ---------------------------------------------------------------------------- */
+/* `Receipt::verify` for one segment seal (the reference's uses: /root/reference/host/src/main.rs:622-624,
+ * /root/reference/verifier/src/main.rs:124-126).  Mirrors risc0-zkp `verify::Verifier::verify` + the circuit's
+ * constraint polynomial at the DEEP point; runs on the host like upstream's verifier and needs no device or context.
+ * Exactly one of `circuit` (built-in stand-in circuit) / `ir` (data-defined circuit) is non-NULL.  `code_root` = the 8-word
+ * control id of (circuit, po2), e.g. hfb200_control_root or the "code_root" checkpoint of a trusted proof.
+ * Returns NULL when the seal is valid, else the reason. */
+const char* hfb200_verify_segment(const hfb200_circuit_desc* circuit, const hfb200_circuit_ir* ir, const uint32_t* seal, size_t seal_words,
+                                  const uint32_t* code_root /*[8]*/, uint32_t* po2_out);
+/* Control id: Merkle root of the x4 LDE of the code (control) columns, u32[w_code][2^po2] on the host. */
+const char* hfb200_control_root(hfb200_ctx* ctx, uint32_t po2, const uint32_t* code, uint32_t* root_out /*[8]*/);
+
 /* ---- measurement ------------------------------------------------------------------------------ */
 typedef struct {
     float ms_total;        /* whole segment, host wall clock from entry to seal bytes on host                 */

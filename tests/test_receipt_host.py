@@ -39,5 +39,19 @@ def test_host_mirror_proves_a_session(pkg, emu_lib, orc):
     cir = orc.Circuit(*SMALL)
     for s, seg in zip(rec.inner.segments, segs):                    # every segment seal verifies
         assert cir.verify(np.array(s.seal, np.uint32), cir.control_id(seg.po2)) == seg.po2
+    # `receipt.verify(id)` as the reference's host and verifier call it: product-side verifier, per-po2 control ids
+    ids = {12: cir.control_id(12), 13: cir.control_id(13)}
+    rec.verify(ids, circuit=SMALL, lib=emu_lib)
+    with pytest.raises(pkg.Hfb200Error, match="no control id"):
+        rec.verify({12: ids[12]}, circuit=SMALL, lib=emu_lib)
+    rec.inner.segments[1].seal[100] ^= 1
+    with pytest.raises(pkg.Hfb200Error, match="segment 1"):
+        rec.verify(ids, circuit=SMALL, lib=emu_lib)
+    rec.inner.segments[1].seal[100] ^= 1
+    rec.inner.segments[2].index = 5
+    with pytest.raises(pkg.Hfb200Error, match="segment index"):
+        rec.verify(ids, circuit=SMALL, lib=emu_lib)
+    with pytest.raises(pkg.Hfb200Error, match="Fake"):
+        pkg.Receipt("Fake", pkg.Journal(b"")).verify(ids)
     with pytest.raises(pkg.Hfb200Error):
         pkg.ProverOpts(hashfn="sha-256")

@@ -1,0 +1,124 @@
+"""Product-side segment verifier (`hfb200_verify_segment`, SURVEY.md section 8f row N3: `Receipt::verify` as the
+reference calls it at host/src/main.rs:622-624 and verifier/src/main.rs:124-126).  It is host code inside
+libhfb200.so and needs no device, so the whole file runs in the CPU tier.  The oracle's verifier is the independent
+second implementation: both must accept the same seals and reject the same tampered ones."""
+import numpy as np
+import pytest
+from conftest import SMALL, make_segment
+
+
+@pytest.fixture(scope="module")
+def proved(orc):
+    cir, g, code, data = make_segment(orc, SMALL, 12)
+    seal, cps, _ = cir.prove(12, g, code, data, 1)
+    return cir, seal, cps
+
+
+def test_accepts_oracle_seal(pkg, gpu_lib, proved):
+    cir, seal, cps = proved
+    assert pkg.verify_segment(seal, cps["code_root"], SMALL, lib=gpu_lib) == 12
+    assert pkg.verify_segment(seal, cir.control_id(12), SMALL, lib=gpu_lib) == 12
+
+
+@pytest.mark.parametrize("widths,po2", [((16, 64, 16), 12), (SMALL, 13), ((20, 40, 12), 12)])
+def test_accepts_other_shapes(pkg, gpu_lib, orc, widths, po2):
+    cir, g, code, data = make_segment(orc, widths, po2, trace_seed=9, blind_seed=3)
+    seal, cps, _ = cir.prove(po2, g, code, data, 3)
+    assert pkg.verify_segment(seal, cps["code_root"], widths, lib=gpu_lib) == po2
+
+
+def test_tamper_rejected_like_the_oracle(pkg, gpu_lib, proved):
+    cir, seal, cps = proved
+    rng = np.random.default_rng(1)
+    positions = [0, 5, 32, 33, 40, len(seal) // 3, len(seal) // 2, len(seal) - 1] + rng.integers(0, len(seal), 40).tolist()
+    for pos in positions:
+        bad = seal.copy()
+        bad[pos] ^= 1
+        with pytest.raises(pkg.Hfb200Error, match="verify"):
+            pkg.verify_segment(bad, cps["code_root"], SMALL, lib=gpu_lib)
+        with pytest.raises(RuntimeError):
+            cir.verify(bad, cps["code_root"])
+    with pytest.raises(pkg.Hfb200Error, match="truncated"):
+        pkg.verify_segment(seal[:-1], cps["code_root"], SMALL, lib=gpu_lib)
+    with pytest.raises(pkg.Hfb200Error, match="trailing"):
+        pkg.verify_segment(np.concatenate([seal, seal[:1]]), cps["code_root"], SMALL, lib=gpu_lib)
+    wrong = cps["code_root"].copy(); wrong[0] ^= 1
+    with pytest.raises(pkg.Hfb200Error, match="control id"):
+        pkg.verify_segment(seal, wrong, SMALL, lib=gpu_lib)
+    with pytest.raises(pkg.Hfb200Error):
+        pkg.verify_segment(seal, cps["code_root"][:7], SMALL, lib=gpu_lib)
+    # a seal for another circuit shape cannot be parsed as this one
+    with pytest.raises(pkg.Hfb200Error):
+        pkg.verify_segment(seal, cps["code_root"], (8, 24, 8), lib=gpu_lib)
+
+
+def test_non_canonical_element_rejected(pkg, gpu_lib, proved):
+    cir, seal, cps = proved
+    bad = seal.copy()
+    bad[3] = np.uint32(bad[3] + 2013265921) if bad[3] < (1 << 32) - 2013265921 else np.uint32(0xFFFFFFFF)
+    with pytest.raises(pkg.Hfb200Error, match="non-canonical"):
+        pkg.verify_segment(bad, cps["code_root"], SMALL, lib=gpu_lib)
+
+
+def test_invalid_witness_rejected(pkg, gpu_lib, orc):
+    cir, g, code, data = make_segment(orc, SMALL, 12)
+    bad = data.copy()
+    bad[cir.w[1] // 2 + 1, 7] ^= 1
+    seal, cps, _ = cir.prove(12, g, code, bad, 1)
+    with pytest.raises(pkg.Hfb200Error, match="constraint polynomial"):
+        pkg.verify_segment(seal, cps["code_root"], SMALL, lib=gpu_lib)
+
+
+@pytest.mark.parametrize("variant,nest", [(0, False), (1, True)])
+def test_data_defined_circuit(pkg, gpu_lib, orc, variant, nest):
+    from oracle import synth_ir
+    widths, po2 = (12, 24, 8), 12
+    cir = orc.Circuit(*widths, variant=variant)
+    code = cir.gen_code(po2)
+    g = cir.gen_globals(5)
+    data = cir.gen_data(po2, code, g, 5, 1)
+    ir = synth_ir.build(widths, variant, nest=nest)
+    cir.set_ir(ir["taps"], ir["steps"], ir["ret"])
+    seal, cps, _ = cir.prove(po2, g, code, data, 1)
+    assert pkg.verify_segment(seal, cps["code_root"], widths, ir=ir, lib=gpu_lib) == po2
+    if variant == 0:
+        # same circuit, built-in formula
+        assert pkg.verify_segment(seal, cps["code_root"], widths, lib=gpu_lib) == po2
+    bad = seal.copy(); bad[len(seal) // 2] ^= 4
+    with pytest.raises(pkg.Hfb200Error):
+        pkg.verify_segment(bad, cps["code_root"], widths, ir=ir, lib=gpu_lib)
+    # a different constraint list must not accept the seal: flip the first Const of the step list
+    other = dict(ir)
+    steps = np.array(ir["steps"], dtype=np.uint32).reshape(-1, 4).copy()
+    k = int(np.nonzero(steps[:, 0] == 0)[0][0])
+    steps[k, 1] ^= 1
+    other["steps"] = steps.reshape(-1)
+    with pytest.raises(pkg.Hfb200Error):
+        pkg.verify_segment(seal, cps["code_root"], widths, ir=other, lib=gpu_lib)
+
+
+def test_emulated_prover_seal_verifies(pkg, emu_lib, gpu_lib, orc):
+    """Seal produced by the product's own pipeline (kernel sources on the host emulator) -> product verifier."""
+    widths, po2 = SMALL, 12
+    cir, g, code, data = make_segment(orc, widths, po2)
+    with pkg.Context(0, po2, widths, lib=emu_lib) as c:
+        seal = c.prove_segment(po2, g, code, data, 1)
+        root = c.control_root(po2, code)
+        assert (root == cir.control_id(po2)).all()
+    assert pkg.verify_segment(seal, root, widths, lib=gpu_lib) == po2
+
+
+@pytest.mark.gpu
+def test_gpu_seal_verifies_and_control_root(pkg, orc):
+    widths, po2 = (16, 192, 48), 14
+    cir, g, code, data = make_segment(orc, widths, po2)
+    with pkg.Context(0, po2, widths) as c:
+        seal = c.prove_segment(po2, g, code, data, 1)
+        root = c.control_root(po2, code)
+        assert (root == cir.control_id(po2)).all()
+        assert (c.prove_segment(po2, g, code, data, 1) == seal).all()  # control_root leaves the context usable
+    assert pkg.verify_segment(seal, root, widths) == po2
+    assert cir.verify(seal, root) == po2
+    bad = seal.copy(); bad[len(bad) // 2] ^= 1
+    with pytest.raises(pkg.Hfb200Error):
+        pkg.verify_segment(bad, root, widths)
