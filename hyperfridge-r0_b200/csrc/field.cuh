@@ -18,6 +18,10 @@ HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
 HD uint32_t fadd(uint32_t a, uint32_t b) { uint32_t x = a + b; return umin32(x, x - P); }
 HD uint32_t fsub(uint32_t a, uint32_t b) { uint32_t x = a - b; return umin32(x, x + P); }
+// Uncorrected sum / difference of canonical residues, in [0, 2p) < 2^32: valid ONLY as the first operand of fmul /
+// fmul_shoup (both accept any 32-bit value there), never as an operand of fadd / fsub.
+HD uint32_t fadd_lazy(uint32_t a, uint32_t b) { return a + b; }
+HD uint32_t fsub_lazy(uint32_t a, uint32_t b) { return a - b + P; }
 HD uint32_t fneg(uint32_t a) { return a == 0 ? 0u : P - a; }
 // Montgomery product, subtractive form: hi(a*b) - hi(m*P) with m = lo(a*b) * P^-1 lies in (-P, P).
 HD uint32_t fmul(uint32_t a, uint32_t b) {

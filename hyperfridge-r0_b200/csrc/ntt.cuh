@@ -291,8 +291,13 @@ HD void round_t(const KCtx& cx, const uint32_t* tw, int k_, int c_, int l0_, con
                         const uint32_t ti = TWL ? (1u << (l0 + q - 1)) + ((uint32_t)(j & (h - 1)) << l0) + low : (low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q);
                         x = SHP ? fmul_pair(x, tw, ti) : fmul(x, tw[ti]);
                     }
-                    v[j + h] = fsub(v[j], x);
-                    v[j] = fadd(v[j], x);
+                    // an output that the next level multiplies by a twiddle stays in [0, 2p): both product forms take any
+                    // 32-bit first operand, so its range correction is dropped (decided at compile time)
+                    const int hn = h << 1;
+                    const bool lz0 = q < R && (j & hn) && !(L0 == 0 && (j & (hn - 1)) == 0);
+                    const bool lz1 = q < R && ((j + h) & hn) && !(L0 == 0 && ((j + h) & (hn - 1)) == 0);
+                    v[j + h] = lz1 ? fsub_lazy(v[j], x) : fsub(v[j], x);
+                    v[j] = lz0 ? fadd_lazy(v[j], x) : fadd(v[j], x);
                 }
             }
         } else {
@@ -304,11 +309,12 @@ HD void round_t(const KCtx& cx, const uint32_t* tw, int k_, int c_, int l0_, con
                     if (j & h) continue;
                     const uint32_t a = v[j], b = v[j + h];
                     v[j] = fadd(a, b);
-                    uint32_t d = fsub(a, b);
+                    uint32_t d;
                     if (!(L0 == 0 && (j & (h - 1)) == 0)) {
                         const uint32_t ti = TWL ? (1u << (l0 + q - 1)) + ((uint32_t)(j & (h - 1)) << l0) + low : (low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q);
+                        d = fsub_lazy(a, b);  // in (0, 2p): the product takes any 32-bit first operand
                         d = SHP ? fmul_pair(d, tw, ti) : fmul(d, tw[ti]);
-                    }
+                    } else d = fsub(a, b);
                     v[j + h] = d;
                 }
             }
@@ -522,8 +528,9 @@ struct MiddleKernel2 {
                     if (j & h) continue;
                     const uint32_t a = v[j], b = v[j + h];
                     v[j] = fadd(a, b);
-                    uint32_t d = fsub(a, b);
-                    if ((j & (h - 1)) != 0) { const uint32_t ti = (1u << (q - 1)) + (uint32_t)(j & (h - 1)); d = SHP ? fmul_pair(d, twI, ti) : fmul(d, twI[ti]); }
+                    uint32_t d;
+                    if ((j & (h - 1)) != 0) { const uint32_t ti = (1u << (q - 1)) + (uint32_t)(j & (h - 1)); d = fsub_lazy(a, b); d = SHP ? fmul_pair(d, twI, ti) : fmul(d, twI[ti]); }
+                    else d = fsub(a, b);
                     v[j + h] = d;
                 }
             }
@@ -553,8 +560,11 @@ struct MiddleKernel2 {
                 if (j & h) continue;
                 uint32_t x = w[j + h];
                 if (!(RZ && (j & (h - 1)) == 0)) { const uint32_t ti = (1u << (e + q - 1)) + ((uint32_t)(j & (h - 1)) << e) + r; x = SHP ? fmul_pair(x, twF, ti) : fmul(x, twF[ti]); }
-                w[j + h] = fsub(w[j], x);
-                w[j] = fadd(w[j], x);
+                const int hn = h << 1;  // outputs the next level multiplies stay in [0, 2p) (see round_t)
+                const bool lz0 = q < RF && (j & hn) && !(RZ && (j & (hn - 1)) == 0);
+                const bool lz1 = q < RF && ((j + h) & hn) && !(RZ && ((j + h) & (hn - 1)) == 0);
+                w[j + h] = lz1 ? fsub_lazy(w[j], x) : fsub(w[j], x);
+                w[j] = lz0 ? fadd_lazy(w[j], x) : fadd(w[j], x);
             }
         }
         if (p.nrf > 1) {
