@@ -144,6 +144,40 @@ def reference_arm(args):
     return 0
 
 
+def camt53_leg(pkg, ctx, device, po2, inflight, g, code_h, data_h):
+    """One camt53-sized proof end to end: 37 po2-sized segments, host buffers in, verified receipt out."""
+    import numpy as np
+    import importlib
+    sched = importlib.import_module("hyperfridge_r0_b200.scheduler")
+    with open(os.path.join(ROOT, "tests", "golden", "reference_journal.json")) as f:
+        journal_bytes = bytes(json.load(f)["journal_bytes"])
+    journal_text = pkg.decode_journal(journal_bytes)
+    segs = [pkg.Segment(i, po2, g, code_h, data_h, sched.job_seed(1, 0, i)) for i in range(CAMT53_SEGMENTS)]
+    opts = pkg.ProverOpts(max_segment_po2=po2, circuit=WIDTHS, devices=(device,), contexts_per_device=inflight)
+    cap = ctx.seal_words(po2)
+    with pkg.default_prover(opts) as prover:
+        prover.prove(pkg.Session(segs[:inflight], journal_text), seal_cap=cap)  # warm-up: one segment per worker
+        t0 = time.perf_counter()
+        info = prover.prove(pkg.Session(segs, journal_text), seal_cap=cap)
+        prove_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    wire = info.receipt.to_json()
+    receipt = pkg.Receipt.from_json(wire)
+    json_s = time.perf_counter() - t0
+    control_id = ctx.control_root(po2, code_h)
+    t0 = time.perf_counter()
+    receipt.verify({po2: control_id}, circuit=WIDTHS)
+    verify_s = time.perf_counter() - t0
+    ok = receipt.journal.bytes_ == journal_bytes and len(receipt.inner.segments) == CAMT53_SEGMENTS
+    if not ok:
+        raise SystemExit("bench.py: camt53 receipt does not carry the reference journal")
+    return {"segments": CAMT53_SEGMENTS, "po2": po2, "proof_seconds": prove_s, "segments_per_s": CAMT53_SEGMENTS / prove_s,
+            "receipt_json_bytes": len(wire), "receipt_json_roundtrip_seconds": json_s, "verify_seconds": verify_s, "verified": True,
+            "journal": "reference fixture journal (tests/golden/reference_journal.json), %d bytes" % len(journal_bytes),
+            "how": "default_prover().prove(session) through hfb200_pool_prove with host trace buffers, %d contexts in flight; every seal "
+                   "checked by hfb200_verify_segment against hfb200_control_root; wall clock" % inflight}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -153,7 +187,8 @@ def main():
     ap.add_argument("--po2", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--inflight", type=int, default=2, help="prover contexts (segments in flight) per GPU")
+    ap.add_argument("--no-camt53", action="store_true", help="skip the measured 37-segment proof (N=1 only)")
+    ap.add_argument("--inflight", type=int, default=3, help="prover contexts (segments in flight) per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -270,6 +305,7 @@ def main():
 
     # ---------------- e2e: host buffers through the C ABI ----------------
     e2e = None
+    camt53 = None
     if not args.no_e2e:
         hb = []
         for c in ctxs:
@@ -300,6 +336,13 @@ def main():
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(F * ((WIDTHS[0] + WIDTHS[1]) * N * 4 + 128 + 4 * WIDTHS[2])),
                "d2h_bytes_per_step": int(F * len(seal_h[0]) * 4), "ms_per_step": wall_e * 1e3 / args.steps, "host_wall_ms_per_step": host_wall_e * 1e3 / args.steps, "ms_h2d_exposed_per_segment": h2d_ms[0] / args.steps,
                "camt53_proof_seconds": CAMT53_SEGMENTS / e2e_value, "host_memory": "pinned (hfb200_host_alloc)"}
+        # ---------------- camt53-sized proof, measured (BASELINE.json configs[2]) ----------------
+        # 37 segments (the reference's segment count for data/test, docs/runtime.md:50) of po2=20 through the host mirror
+        # of the reference call site: default_prover().prove(session) -> Receipt (host trace buffers, pool of F contexts),
+        # then the receipt goes through its JSON wire form, every seal through the product verifier, and the journal
+        # must be the reference fixture's.  Wall clock around prove(); verification timed separately.
+        if world == 1 and not args.no_camt53:
+            camt53 = camt53_leg(pkg, ctxs[0], local_rank, po2, F, gl[0], hb[0][0], hb[0][1])
         for c, (code_h, data_h) in zip(ctxs, hb):
             c.host_free(code_h)
             c.host_free(data_h)
@@ -357,7 +400,7 @@ def main():
                            "camt53_segments": CAMT53_SEGMENTS, "camt53_proof_seconds": CAMT53_SEGMENTS / value},
                 "stages_ms_per_segment": {k: v / args.steps for k, v in stage.items() if k.startswith("ms_")},
                 "stages_note": "CUDA events on the library stream, one context in flight (kernel durations undisturbed); value/e2e use %d contexts in flight" % F,
-                "roofline": roofline, "poseidon2": poseidon, "cpu_baseline": cpu, "e2e": e2e,
+                "roofline": roofline, "poseidon2": poseidon, "cpu_baseline": cpu, "e2e": e2e, "camt53": camt53,
                 "gpu_launches": launches_all, "clocks": clocks}
         print(json.dumps(line))
     for c in ctxs:

@@ -15,6 +15,8 @@
 #include <string>
 #include <stdexcept>
 #include <vector>
+#include <atomic>
+#include <mutex>
 #include "field.cuh"
 
 namespace hf {
@@ -72,19 +74,28 @@ __global__ void __launch_bounds__(MAXT, MINB) kernel_entry(A... a) {
 }
 
 struct Dev {
+    static constexpr int MAX_DEVICES = 64;
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
     int sm_count = 148;
+    int device = 0;  // CUDA device ordinal of the owning context
     template <typename Body, int MAXT = 256, int MINB = 1, typename... A>
     void launch(unsigned gx, unsigned gy, int block, size_t smem, A... a) {
         if (gx == 0 || gy == 0) return;
         auto k = kernel_entry<Body, MAXT, MINB, A...>;
         if (smem > 48 * 1024) {
-            // per template instantiation and per host thread (= per device in the multi-GPU pool)
-            static thread_local size_t configured_bytes = 0;
-            if (smem > configured_bytes) {
-                CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                configured_bytes = smem;
+            // The opt-in limit is a property of (kernel, device), shared by every context and host thread that uses
+            // the device: it is only ever raised, under a lock, so a context asking for less cannot lower the limit
+            // under another context's launch (seen as cudaErrorInvalidValue with three contexts in flight).
+            static std::atomic<size_t> configured_bytes[MAX_DEVICES];
+            static std::mutex mu;
+            const int d = device >= 0 && device < MAX_DEVICES ? device : 0;
+            if (smem > configured_bytes[d].load(std::memory_order_acquire)) {
+                std::lock_guard<std::mutex> lock(mu);
+                if (smem > configured_bytes[d].load(std::memory_order_relaxed)) {
+                    CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    configured_bytes[d].store(smem, std::memory_order_release);
+                }
             }
         }
         k<<<dim3(gx, gy), block, smem, stream>>>(a...);

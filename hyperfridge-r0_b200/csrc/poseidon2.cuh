@@ -32,9 +32,9 @@ __constant__ P2Consts g_p2c;
 #define P2C_DEV g_p2c
 #endif
 static P2Consts g_p2c_host;
-static bool g_p2c_host_ready = false;
 static inline const P2Consts& p2_host_consts() {
-    if (!g_p2c_host_ready) { g_p2c_host = p2_make_consts(); g_p2c_host_ready = true; }
+    static const bool once = (g_p2c_host = p2_make_consts(), true);  // thread-safe one-time initialisation
+    (void)once;
     return g_p2c_host;
 }
 

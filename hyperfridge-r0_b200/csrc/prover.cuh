@@ -99,6 +99,7 @@ struct Prover {
         if (device < 0 || device >= count) throw Err("device index out of range");
         CUDA_CHECK(cudaSetDevice(device));
         device_id = device;
+        dev.device = device;
         cudaDeviceProp prop;
         CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
         if (prop.major < 10) throw Err(std::string("libhfb200 is built for sm_100a only; found ") + prop.name);

@@ -79,7 +79,7 @@ class B200Prover:
 
     def prove_segment(self, seg: Segment, seal_cap: int = 1 << 18) -> SegmentReceipt:
         seals, _, _ = self._pool.prove([(seg.po2, seg.globals_, seg.code, seg.data, seg.blind_seed)], seal_cap)
-        return SegmentReceipt(seal=seals[0].tolist(), index=seg.index, hashfn=self.opts.hashfn)
+        return SegmentReceipt(seal=seals[0], index=seg.index, hashfn=self.opts.hashfn)
 
     def prove(self, session: Session, seal_cap: int = 1 << 18) -> ProveInfo:
         for s in session.segments:
@@ -87,7 +87,7 @@ class B200Prover:
                 raise Hfb200Error("segment po2 %d exceeds max_segment_po2 %d" % (s.po2, self.opts.max_segment_po2))
         jobs = [(s.po2, s.globals_, s.code, s.data, s.blind_seed) for s in session.segments]
         seals, devices, ms = self._pool.prove(jobs, seal_cap)
-        segs = [SegmentReceipt(seal=seal.tolist(), index=s.index, hashfn=self.opts.hashfn) for s, seal in zip(session.segments, seals)]
+        segs = [SegmentReceipt(seal=seal, index=s.index, hashfn=self.opts.hashfn) for s, seal in zip(session.segments, seals)]
         receipt = Receipt(CompositeReceipt(segs), Journal(encode_journal(session.journal)))
         return ProveInfo(receipt, {"devices": devices, "segment_ms": ms})
 
