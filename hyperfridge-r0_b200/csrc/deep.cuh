@@ -46,55 +46,103 @@ struct PowBitrevKernel {
     }
 };
 
-static constexpr uint32_t DOT_CPB = 4, DOT_RPB = 4096, DOT_T = 256;
-#ifndef DOT_MINB
-#define DOT_MINB 2  // resident CTAs per SM the register allocation of DotKernel is bounded for
-#endif
+static constexpr uint32_t DOT_RPB = 4096;  // rows per block (= per partial sum)
+// TMA-staged tile: DT_CG columns x DT_R rows of the trace + the DT_R (+1) weights of those rows per pipeline stage.
+static constexpr uint32_t DT_CG = 64, DT_R = 128, DT_STAGES = 3, DT_Q = 4, DT_T = DT_CG * DT_Q;
+static constexpr uint32_t DT_CSTRIDE = DT_R + 4;                                // words; 16-byte aligned column starts
+static constexpr uint32_t DT_STAGE_WORDS = DT_CG * DT_CSTRIDE + (DT_R + 4) * 4;  // columns, then the weights (E4)
+static constexpr size_t DT_SMEM = (size_t)DT_STAGES * DT_STAGE_WORDS * 4 + 64;
 
-// partial[(col * nblk + blk) * 2 + b] = sum over the block's rows of cols[col][r] * Wt[(r + b) mod n]
-// (b = 1 only for col < n_back1).  grid.x = row blocks, grid.y = column groups of DOT_CPB.
+// partial[(col * nblk + blk) * 2 + b] = sum over the block's DOT_RPB rows of cols[col][r] * Wt[(r + b) mod n]
+// (b = 1 only for col < n_back1).  grid.x = row blocks, grid.y = column groups of DT_CG.
+//
+// B200 structure: the column segments (512 B each) and the weight slice of a stage arrive by TMA bulk copies
+// (cp.async.bulk, one mbarrier per stage, 3 stages in flight) issued by warp 0, so no thread ever waits on a global
+// load.  Thread (c, q) owns column c and a quarter q of the stage's rows: its two lazy 64-bit Fp4 accumulators
+// (field.cuh) are the only live state (no cross-thread reduction until the very end), the column word is a conflict-free
+// LDS (rows visited in an order rotated by q: bank = 4 c + i + q) and the weight is a 16-byte LDS shared by the 8 lanes
+// of the same q.  Bound: one IMAD.WIDE per Fp4 component and term.
 struct DotKernel {
     static constexpr bool kBarrier = true;
     HD static void run(const KCtx& cx, uint32_t* sm, const uint32_t* cols, uint64_t col_stride, uint32_t ncols, uint32_t n_back1, const E4* Wt, uint32_t po2, E4* partial) {
         const uint64_t n = 1ull << po2;
-        const uint32_t nblk = cx.gx, c0 = cx.by * DOT_CPB;
+        const uint32_t nblk = cx.gx, c0 = cx.by * DT_CG;
+        const uint32_t ncg = ncols - c0 < DT_CG ? ncols - c0 : DT_CG;
         const uint64_t row0 = (uint64_t)cx.bx * DOT_RPB;
-        E4* red = reinterpret_cast<E4*>(sm);  // [DOT_T][DOT_CPB*2]
-        for (uint32_t it = cx.tid; it < DOT_T; it += cx.nt) {
-            E4A acc[DOT_CPB][2];  // lazy 64-bit accumulators (field.cuh): one wide multiply-add per term
-            for (uint32_t c = 0; c < DOT_CPB; c++) { acc[c][0] = e4a_zero(); acc[c][1] = e4a_zero(); }
-            // two rows per trip, all loads issued before the multiply-accumulate chains (memory-level parallelism)
-            for (uint64_t r = row0 + it; r < row0 + DOT_RPB && r < n; r += 2 * DOT_T) {
-                const uint64_t r2 = r + DOT_T;
-                const bool has2 = r2 < row0 + DOT_RPB && r2 < n;
-                const E4 w0 = Wt[r], w1 = Wt[(r + 1) & (n - 1)];
-                const E4 v0 = has2 ? Wt[r2] : e4_zero(), v1 = has2 ? Wt[(r2 + 1) & (n - 1)] : e4_zero();
-                uint32_t ta[DOT_CPB], tb[DOT_CPB];
-#pragma unroll
-                for (uint32_t c = 0; c < DOT_CPB; c++) {
-                    const bool okc = c0 + c < ncols;
-                    ta[c] = okc ? cols[(uint64_t)(c0 + c) * col_stride + r] : 0u;
-                    tb[c] = (okc && has2) ? cols[(uint64_t)(c0 + c) * col_stride + r2] : 0u;
-                }
-#pragma unroll
-                for (uint32_t c = 0; c < DOT_CPB; c++) {
-                    e4a_mac(acc[c][0], w0, ta[c]); e4a_mac(acc[c][0], v0, tb[c]);
-                    if (c0 + c < n_back1) { e4a_mac(acc[c][1], w1, ta[c]); e4a_mac(acc[c][1], v1, tb[c]); }
-                }
-            }
-            for (uint32_t c = 0; c < DOT_CPB; c++) { red[(it * DOT_CPB + c) * 2] = e4a_redc(acc[c][0]); red[(it * DOT_CPB + c) * 2 + 1] = e4a_redc(acc[c][1]); }
+        const uint32_t n_iter = DOT_RPB / DT_R;
+#ifdef __CUDA_ARCH__
+        constexpr uint32_t NV = 1;
+        uint64_t* bars = reinterpret_cast<uint64_t*>(sm + DT_STAGES * DT_STAGE_WORDS);
+        if (cx.tid == 0) {
+            for (uint32_t s = 0; s < DT_STAGES; s++) mbar_init(&bars[s], 1);
+            mbar_init_fence();
         }
         cx.sync();
-        for (uint32_t stride = DOT_T / 2; stride >= 1; stride >>= 1) {
-            for (uint32_t w = cx.tid; w < stride * DOT_CPB * 2; w += cx.nt) {
-                const uint32_t it = w / (DOT_CPB * 2), k = w % (DOT_CPB * 2);
-                red[it * DOT_CPB * 2 + k] = e4_add(red[it * DOT_CPB * 2 + k], red[(it + stride) * DOT_CPB * 2 + k]);
+        auto issue = [&](uint32_t it) {  // warp 0
+            uint32_t* st = sm + (it % DT_STAGES) * DT_STAGE_WORDS;
+            uint64_t* bar = &bars[it % DT_STAGES];
+            const uint64_t r0 = row0 + (uint64_t)it * DT_R;
+            const bool wrap = r0 + DT_R == n;  // the shifted weight of the last row is Wt[0]
+            if (cx.tid == 0) {
+                mbar_expect_tx(bar, ncg * DT_R * 4 + (DT_R + 1) * 16);
+                tma_bulk_g2s(st + DT_CG * DT_CSTRIDE, Wt + r0, (wrap ? DT_R : DT_R + 1) * 16, bar);
+                if (wrap) tma_bulk_g2s(st + DT_CG * DT_CSTRIDE + DT_R * 4, Wt, 16, bar);
             }
-            cx.sync();
+            __syncwarp();
+            for (uint32_t c = (uint32_t)cx.tid; c < ncg; c += 32) tma_bulk_g2s(st + c * DT_CSTRIDE, cols + (uint64_t)(c0 + c) * col_stride + r0, DT_R * 4, bar);
+        };
+        if (cx.tid < 32) for (uint32_t it = 0; it + 1 < DT_STAGES && it < n_iter; it++) issue(it);
+#else
+        constexpr uint32_t NV = DT_T;
+        (void)n;
+#endif
+        E4A acc[NV][2];
+        for (uint32_t v = 0; v < NV; v++) { acc[v][0] = e4a_zero(); acc[v][1] = e4a_zero(); }
+        for (uint32_t it = 0; it < n_iter; it++) {
+#ifdef __CUDA_ARCH__
+            if (cx.tid < 32 && it + DT_STAGES - 1 < n_iter) issue(it + DT_STAGES - 1);  // its stage was drained in iteration it - 1
+            mbar_wait(&bars[it % DT_STAGES], (it / DT_STAGES) & 1u);
+            const uint32_t* st = sm + (it % DT_STAGES) * DT_STAGE_WORDS;
+#else
+            uint32_t* st = sm;
+            {
+                const uint64_t r0 = row0 + (uint64_t)it * DT_R;
+                for (uint32_t c = 0; c < ncg; c++) for (uint32_t r = 0; r < DT_R; r++) st[c * DT_CSTRIDE + r] = cols[(uint64_t)(c0 + c) * col_stride + r0 + r];
+                E4* wdst = reinterpret_cast<E4*>(st + DT_CG * DT_CSTRIDE);
+                for (uint32_t r = 0; r <= DT_R; r++) wdst[r] = Wt[(r0 + r) & ((1ull << po2) - 1)];
+            }
+#endif
+            const E4* ws = reinterpret_cast<const E4*>(st + DT_CG * DT_CSTRIDE);
+            for (uint32_t t = cx.tid; t < DT_T; t += cx.nt) {
+                const uint32_t c = t / DT_Q, q = t % DT_Q;
+                if (c >= ncg) continue;
+                E4A* a = acc[NV == 1 ? 0 : t];
+                const uint32_t* cs = st + c * DT_CSTRIDE + q * (DT_R / DT_Q);
+                const E4* wq = ws + q * (DT_R / DT_Q);
+                const bool b1 = c0 + c < n_back1;
+#pragma unroll 4
+                for (uint32_t i = 0; i < DT_R / DT_Q; i++) {
+                    const uint32_t rr = (i + q) % (DT_R / DT_Q);
+                    const uint32_t x = cs[rr];
+                    e4a_mac(a[0], wq[rr], x);
+                    if (b1) e4a_mac(a[1], wq[rr + 1], x);
+                }
+            }
+            cx.sync();  // the stage is free for the copy issued in the next iteration
         }
-        for (uint32_t k = cx.tid; k < DOT_CPB * 2; k += cx.nt) {
+        // reduce the DT_Q row quarters of every column
+        E4* red = reinterpret_cast<E4*>(sm);  // [DT_T][2]
+        for (uint32_t t = cx.tid; t < DT_T; t += cx.nt) {
+            const E4A* a = acc[NV == 1 ? 0 : t];
+            red[t * 2] = e4a_redc(a[0]); red[t * 2 + 1] = e4a_redc(a[1]);
+        }
+        cx.sync();
+        for (uint32_t k = cx.tid; k < DT_CG * 2; k += cx.nt) {
             const uint32_t c = k >> 1, b = k & 1;
-            if (c0 + c < ncols) partial[((uint64_t)(c0 + c) * nblk + cx.bx) * 2 + b] = red[k];
+            if (c >= ncg) continue;
+            E4 sum = red[(c * DT_Q) * 2 + b];
+            for (uint32_t q = 1; q < DT_Q; q++) sum = e4_add(sum, red[(c * DT_Q + q) * 2 + b]);
+            partial[((uint64_t)(c0 + c) * nblk + cx.bx) * 2 + b] = sum;
         }
     }
 };

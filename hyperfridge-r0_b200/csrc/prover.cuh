@@ -296,7 +296,7 @@ struct Prover {
         const uint32_t nblk = (uint32_t)((N + DOT_RPB - 1) / DOT_RPB);
         const size_t save = arena.off;
         E4* partial = arena.take<E4>((size_t)w * nblk * 2);
-        dev.launch<DotKernel, 256, DOT_MINB>(nblk, (w + DOT_CPB - 1) / DOT_CPB, DOT_T, (size_t)DOT_T * DOT_CPB * 2 * sizeof(E4), cols, (uint64_t)N, w, n_back1, Wt, po2, partial);
+        dev.launch<DotKernel, 256, 2>(nblk, (w + DT_CG - 1) / DT_CG, DT_T, DT_SMEM, cols, (uint64_t)N, w, n_back1, Wt, po2, partial);
         dev.launch<DotReduceKernel, 128, 1>((2 * w + 127) / 128, 1, 128, 0, (const E4*)partial, w, nblk, out_dev);
         arena.off = save;  // stream order makes reuse by later kernels safe
     }
