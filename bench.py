@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--po2", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-control-cache", action="store_true", help="skip the informational e2e leg with the control group kept on the device")
     ap.add_argument("--no-camt53", action="store_true", help="skip the measured 37-segment proof (N=1 only)")
     ap.add_argument("--inflight", type=int, default=3, help="prover contexts (segments in flight) per GPU")
     args = ap.parse_args()
@@ -337,6 +338,27 @@ def main():
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(F * ((WIDTHS[0] + WIDTHS[1]) * N * 4 + 128 + 4 * WIDTHS[2])),
                "d2h_bytes_per_step": int(F * len(seal_h[0]) * 4), "ms_per_step": wall_e * 1e3 / args.steps, "host_wall_ms_per_step": host_wall_e * 1e3 / args.steps, "ms_h2d_exposed_per_segment": h2d_ms[0] / args.steps,
                "camt53_proof_seconds": CAMT53_SEGMENTS / e2e_value, "host_memory": "pinned (hfb200_host_alloc)"}
+        # ---------------- the same e2e call with the control group kept on the device (opt-in, informational) ----------------
+        # The control (code) columns depend on (circuit, po2) only; hfb200_control_root commits them once and segments then
+        # pass code == NULL: identical seals, one LDE + Merkle tree of 16 columns and 64 MiB of H2D less per segment.  NOT the
+        # headline: `value` and `e2e` above rebuild the control commitment for every segment, as upstream's prover does.
+        if not args.no_control_cache:
+            for c, (code_h, data_h) in zip(ctxs, hb):
+                c.control_root(po2, code_h)
+
+            def step_host_cc(slot, k):
+                seal_h[0] = ctxs[slot].prove_segment(po2, gl[slot], None, hb[slot][1], 1 + rank + 17 * k + 101 * slot)
+
+            run_all(step_host_cc, 2)
+            barrier()
+            t0 = time.perf_counter()
+            run_all(step_host_cc, args.steps)
+            barrier()
+            host_wall_c = max_over_ranks(time.perf_counter() - t0)
+            wall_c = max(max_over_ranks(device_seconds()), host_wall_c)
+            e2e["control_cached"] = {"value": world * F * args.steps / wall_c, "unit": UNIT, "h2d_bytes_per_step": int(F * (WIDTHS[1] * N * 4 + 128)),
+                                     "note": "opt-in: control group committed once per (circuit, po2) with hfb200_control_root, segments pass code = NULL; seals identical; not the headline"}
+
         # ---------------- camt53-sized proof, measured (BASELINE.json configs[2]) ----------------
         # 37 segments (the reference's segment count for data/test, docs/runtime.md:50) of po2=20 through the host mirror
         # of the reference call site: default_prover().prove(session) -> Receipt (host trace buffers, pool of F contexts),

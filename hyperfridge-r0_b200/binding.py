@@ -173,9 +173,11 @@ class Context:
         return self.lib.hfb200_seal_words(self._h, po2)
 
     def prove_segment(self, po2, globals_, code, data, blind_seed):
-        globals_, code, data = _u32(globals_), _u32(code), _u32(data)
+        """code=None reuses the control group loaded by control_root(po2, code)."""
+        globals_, data = _u32(globals_), _u32(data)
+        code = _u32(code) if code is not None else None
         n = 1 << po2
-        if globals_.size != N_GLOBAL or code.size != self.circuit[0] * n or data.size != self.circuit[1] * n:
+        if globals_.size != N_GLOBAL or (code is not None and code.size != self.circuit[0] * n) or data.size != self.circuit[1] * n:
             raise Hfb200Error("prove_segment: trace shape does not match (circuit, po2)")
         cap = self.seal_words(po2)
         seal = np.empty(cap, np.uint32)
@@ -184,7 +186,9 @@ class Context:
         return seal[:got.value]
 
     def segment_begin(self, po2, globals_, code, data, blind_seed):
-        globals_, code, data = _u32(globals_), _u32(code), _u32(data)
+        globals_ = _u32(globals_)
+        code = _u32(code) if code is not None else None
+        data = _u32(data) if data is not None else None
         mix = np.empty(self.circuit[2], np.uint32)
         got = C.c_size_t()
         self._check(self.lib.hfb200_segment_begin(self._h, po2, _ptr(globals_), _ptr(code), _ptr(data), blind_seed, _ptr(mix), mix.size, C.byref(got)))

@@ -114,7 +114,8 @@ void hfb200_host_free(void* p) {
 const char* hfb200_prove_segment(hfb200_ctx* ctx, uint32_t po2, const uint32_t* globals, const uint32_t* code, const uint32_t* data,
                                  uint64_t blind_seed, uint32_t* seal_out, size_t seal_cap, size_t* seal_words) {
     API_TRY
-    if (!ctx || !globals || !code || !data) throw Err("hfb200_prove_segment: NULL argument");
+    if (!ctx || !globals || !data) throw Err("hfb200_prove_segment: NULL argument");
+    if (!code && !ctx->p.control_cached) throw Err("hfb200_prove_segment: code is NULL and no control group is loaded (hfb200_control_root)");
     ctx->p.begin(po2, globals, code, data, blind_seed);
     ctx->p.finish(nullptr, ctx->seal);
     if (const char* e = emit_seal(ctx, seal_out, seal_cap, seal_words)) return e;
@@ -400,6 +401,7 @@ const char* hfb200_control_root(hfb200_ctx* ctx, uint32_t po2, const uint32_t* c
     API_TRY
     if (!ctx || !code || !root_out) throw Err("hfb200_control_root: NULL argument");
     Prover& p = ctx->p;
+    if (p.begun) throw Err("hfb200_control_root: a segment is in flight (call hfb200_segment_finish first)");
     p.bind();
     p.layout(po2);
     const size_t N = (size_t)1 << po2, D = 4 * N;
@@ -407,8 +409,11 @@ const char* hfb200_control_root(hfb200_ctx* ctx, uint32_t po2, const uint32_t* c
     p.dev.h2d(p.tr[GROUP_CODE], code, (size_t)w * N * 4);
     p.ntt.lde(p.tr[GROUP_CODE], N, p.ev[GROUP_CODE], D, p.scratch, w, (int)po2);
     p.merkle.build(p.ev[GROUP_CODE], D, (uint32_t)D, w, p.nodes[GROUP_CODE]);
-    p.dev.d2h(root_out, p.nodes[GROUP_CODE] + 8, 32);  // heap layout: node 1 is the root
-    p.dev.sync();
+    // keep the committed control group for the segments that follow with code == NULL
+    p.commit_tree(Tree{p.ev[GROUP_CODE], D, (uint32_t)D, w, p.nodes[GROUP_CODE]}, "code_root", &p.control_top);
+    p.proof.clear(); p.cps.clear(); p.rng = HostRng();  // commit_tree wrote into the transcript of no segment
+    std::memcpy(root_out, &p.control_top[8], 32);       // heap layout: node 1 is the root
+    p.control_cached = true;
     p.have_trace = false;  // the resident trace (if any) lost its code group
     API_CATCH
 }

@@ -61,6 +61,11 @@ struct Prover {
     // ---- per-segment state ----
     uint32_t po2 = 0;
     bool have_trace = false, begun = false;
+    // Control-group commitment kept across segments (opt-in: hfb200_control_root loads it, code == NULL uses it).  The
+    // control columns depend on (circuit, po2) only -- upstream's verifier checks their root against a per-po2 table --
+    // so their LDE and Merkle tree need not be rebuilt per segment.  Valid while the context stays at this po2.
+    bool control_cached = false;
+    std::vector<uint32_t> control_top;  // the tree's top layers as commit_tree reads them
     uint32_t* tr[3] = {nullptr, nullptr, nullptr};  // resident traces: accum, code, data
     uint32_t* ev[3] = {nullptr, nullptr, nullptr};
     uint32_t* nodes[3] = {nullptr, nullptr, nullptr};
@@ -176,7 +181,7 @@ struct Prover {
     void layout(uint32_t p) {
         if (p < 12 || p > max_po2) throw Err("po2 out of range for this context");
         if (p == po2 && tr[0]) return;
-        po2 = p; have_trace = false;
+        po2 = p; have_trace = false; control_cached = false;
         const size_t N = (size_t)1 << p, D = 4 * N;
         arena.off = 0;
         const uint32_t w[3] = {cir.cd.w_accum, cir.cd.w_code, cir.cd.w_data};
@@ -192,11 +197,17 @@ struct Prover {
     }
 
     // ---- commit helpers ----
-    void commit_tree(const Tree& t, const char* cp_name) {
+    void commit_tree(const Tree& t, const char* cp_name, std::vector<uint32_t>* keep = nullptr, const std::vector<uint32_t>* cached = nullptr) {
         const MerkleShape ms(t.rows);
         std::vector<uint32_t> top((size_t)2 * ms.top_size * 8);
-        dev.d2h(top.data(), t.nodes, top.size() * 4);
-        dev.sync();
+        if (cached) {
+            if (cached->size() != top.size()) throw Err("internal: cached control tree has the wrong shape");
+            top = *cached;
+        } else {
+            dev.d2h(top.data(), t.nodes, top.size() * 4);
+            dev.sync();
+        }
+        if (keep) *keep = top;
         proof.insert(proof.end(), top.begin() + (size_t)ms.top_size * 8, top.end());
         rng.mix(&top[8]);
         cp_add(cp_name, &top[8], 8);
@@ -243,15 +254,23 @@ struct Prover {
         } else
 #endif
         if (data_h) { dev.h2d(tr[GROUP_DATA], data_h, (size_t)cir.cd.w_data * N * 4); }
-        if (code_h && data_h) have_trace = true;
-        if (!have_trace) throw Err("no trace: pass code/data or call hfb200_witgen_synth first");
+        const bool use_control = !code_h && data_h && control_cached;
+        if (code_h) control_cached = false;  // the resident control columns change
+        if ((code_h || use_control) && data_h) have_trace = true;
+        if (!have_trace) throw Err("no trace: pass code/data (code may be NULL after hfb200_control_root) or call hfb200_witgen_synth first");
         mark(1);
         const Digest8 gh = host_hash_elems(globals, N_GLOBAL);
         rng.mix(gh.w);
         proof.insert(proof.end(), globals, globals + N_GLOBAL);
         proof.push_back(po2);
         cp_add("globals_hash", gh.w, 8);
-        commit_group(GROUP_CODE, "code_root", 1, 2, 3);
+        if (use_control) {
+            mark(2); mark(3);
+            const size_t D = 4 * N;
+            commit_tree(Tree{ev[GROUP_CODE], D, (uint32_t)D, cir.cd.w_code, nodes[GROUP_CODE]}, "code_root", nullptr, &control_top);
+        } else {
+            commit_group(GROUP_CODE, "code_root", 1, 2, 3);
+        }
         if (chunked) {
 #ifndef HFB200_EMU
             const size_t D = 4 * N;

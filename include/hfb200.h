@@ -126,7 +126,10 @@ const char* hfb200_checkpoint(hfb200_ctx* ctx, const char* name, uint32_t* out, 
  * Returns NULL when the seal is valid, else the reason. */
 const char* hfb200_verify_segment(const hfb200_circuit_desc* circuit, const hfb200_circuit_ir* ir, const uint32_t* seal, size_t seal_words,
                                   const uint32_t* code_root /*[8]*/, uint32_t* po2_out);
-/* Control id: Merkle root of the x4 LDE of the code (control) columns, u32[w_code][2^po2] on the host. */
+/* Control id: Merkle root of the x4 LDE of the code (control) columns, u32[w_code][2^po2] on the host.
+ * The committed control group stays resident: until the context sees another po2 or another `code` pointer, segments may
+ * pass code == NULL to hfb200_prove_segment / hfb200_segment_begin and reuse it (the control columns depend on
+ * (circuit, po2) only; the seal is bit-identical to the one produced with the columns passed again). */
 const char* hfb200_control_root(hfb200_ctx* ctx, uint32_t po2, const uint32_t* code, uint32_t* root_out /*[8]*/);
 
 /* ---- measurement ------------------------------------------------------------------------------ */

@@ -108,6 +108,34 @@ def test_emulated_prover_seal_verifies(pkg, emu_lib, gpu_lib, orc):
     assert pkg.verify_segment(seal, root, widths, lib=gpu_lib) == po2
 
 
+def test_control_group_cache_on_emulator(pkg, emu_lib, orc):
+    """hfb200_control_root keeps the committed control group; code=None reuses it and yields the identical seal."""
+    widths, po2 = SMALL, 12
+    cir, g, code, data = make_segment(orc, widths, po2)
+    _, g2, _, data2 = make_segment(orc, widths, po2, trace_seed=77)
+    with pkg.Context(0, 13, widths, lib=emu_lib) as c:
+        with pytest.raises(pkg.Hfb200Error, match="no control group"):
+            c.prove_segment(po2, g, None, data, 1)
+        full = c.prove_segment(po2, g, code, data, 1)
+        with pytest.raises(pkg.Hfb200Error, match="no control group"):   # proving does not load the cache by itself
+            c.prove_segment(po2, g, None, data, 1)
+        c.control_root(po2, code)
+        assert (c.prove_segment(po2, g, None, data, 1) == full).all()
+        assert (c.prove_segment(po2, g2, None, data2, 5) == cir.prove(po2, g2, code, data2, 5)[0]).all()   # other segment, same control
+        mix = c.segment_begin(po2, g, None, data, 1)                        # two-phase form
+        with pytest.raises(pkg.Hfb200Error, match="in flight"):
+            c.control_root(po2, code)
+        assert (c.segment_finish(cir.step_accum(po2, data, mix, 1)) == full).all()
+        assert (c.prove_segment(po2, g, code, data, 1) == full).all()      # explicit code drops the cache
+        with pytest.raises(pkg.Hfb200Error, match="no control group"):
+            c.prove_segment(po2, g, None, data, 1)
+        c.control_root(po2, code)
+        cir13, g13, code13, data13 = make_segment(orc, widths, 13)
+        c.prove_segment(13, g13, code13, data13, 1)                         # another po2 re-lays the arena
+        with pytest.raises(pkg.Hfb200Error, match="no control group"):
+            c.prove_segment(po2, g, None, data, 1)
+
+
 @pytest.mark.gpu
 def test_gpu_seal_verifies_and_control_root(pkg, orc):
     widths, po2 = (16, 192, 48), 14
@@ -116,6 +144,7 @@ def test_gpu_seal_verifies_and_control_root(pkg, orc):
         seal = c.prove_segment(po2, g, code, data, 1)
         root = c.control_root(po2, code)
         assert (root == cir.control_id(po2)).all()
+        assert (c.prove_segment(po2, g, None, data, 1) == seal).all()  # cached control group: identical seal
         assert (c.prove_segment(po2, g, code, data, 1) == seal).all()  # control_root leaves the context usable
     assert pkg.verify_segment(seal, root, widths) == po2
     assert cir.verify(seal, root) == po2
