@@ -195,6 +195,11 @@ def main():
         return reference_arm(args)
     if args.warmup < 3:
         args.warmup = 3
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner, for one) goes to
+    # stderr instead; the line itself is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import numpy as np
     import torch
@@ -211,7 +216,6 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -425,7 +429,8 @@ def main():
                 "stages_note": "CUDA events on the library stream, one context in flight (kernel durations undisturbed); value/e2e use %d contexts in flight" % F,
                 "roofline": roofline, "poseidon2": poseidon, "cpu_baseline": cpu, "e2e": e2e, "camt53": camt53,
                 "gpu_launches": launches_all, "clocks": clocks}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     for c in ctxs:
         c.close()
     if dist is not None:
