@@ -693,12 +693,17 @@ static inline int ilog2(uint64_t x) { int k = 0; while ((1ull << k) < x) k++; re
 static inline NttPlan ntt_plan(int n, int e) {
     NttPlan pl;
     int a = n <= 10 ? n : (n - 10 > 10 ? n - 10 : 10);
+    // po2 21 / 22 LDE: keep the 2^10 chunk so that the fused middle stage is the compile-time main-group kernel (tables in
+    // shared memory, Shoup pairs); the strided stages then cover 2^11 / 2^12 rows with 32- / 16-byte row segments.  Measured
+    // at po2 = 22, 192 columns: middle 38.8 -> ~10 ms against a few ms more in the strided stages.
+    if (e == 2 && n > 20 && n <= 22) a = 10;
     if (const char* env = std::getenv("HFB200_NTT_A")) { int v = std::atoi(env); if (v >= 1 && v <= n) a = v; }
     if (a + e > 14) a = 14 - e;
     if (n - a > 12) a = n - 12;
     pl.a = a;
     pl.b = n - a;
     pl.c = pl.b == 0 ? 0 : (14 - pl.b < 5 ? 14 - pl.b : 5);
+    if (pl.b == 12) pl.c = 3;  // 2^15-word tile, one 512-thread CTA per SM: 32-byte row segments instead of 16
     if (const char* env = std::getenv("HFB200_NTT_C")) { int v = std::atoi(env); if (v >= 0 && v <= pl.c) pl.c = v; }
     if (pl.c > pl.a) pl.c = pl.a;
     if (pl.c < 0) pl.c = 0;
@@ -773,6 +778,12 @@ struct Ntt {
             case 100411: dev->launch<StridedKernel2<10, 4, 11>, 256, STR_MINB>((unsigned)grid, 1, 256, smem, p); break;
             case 100413: dev->launch<StridedKernel2<10, 4, 13>, 256, STR_MINB>((unsigned)grid, 1, 256, smem, p); break;
             case 100414: dev->launch<StridedKernel2<10, 4, 14>, 256, STR_MINB>((unsigned)grid, 1, 256, smem, p); break;
+            case 110310: dev->launch<StridedKernel2<11, 3, 10>, 256, STR_MINB>((unsigned)grid, 1, 256, smem, p); break;
+            case 110312: dev->launch<StridedKernel2<11, 3, 12>, 256, STR_MINB>((unsigned)grid, 1, 256, smem, p); break;
+            case 120310: dev->launch<StridedKernel2<12, 3, 10>, 512, 1>((unsigned)grid, 1, 512, smem, p); break;
+            case 120312: dev->launch<StridedKernel2<12, 3, 12>, 512, 1>((unsigned)grid, 1, 512, smem, p); break;
+            case 120210: dev->launch<StridedKernel2<12, 2, 10>, 256, STR_MINB>((unsigned)grid, 1, 256, smem, p); break;
+            case 120212: dev->launch<StridedKernel2<12, 2, 12>, 256, STR_MINB>((unsigned)grid, 1, 256, smem, p); break;
             case 90510: dev->launch<StridedKernel2<9, 5, 10>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
             case 90512: dev->launch<StridedKernel2<9, 5, 12>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
             case 70510: dev->launch<StridedKernel2<7, 5, 10>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
