@@ -703,7 +703,9 @@ static inline NttPlan ntt_plan(int n, int e) {
     pl.a = a;
     pl.b = n - a;
     pl.c = pl.b == 0 ? 0 : (14 - pl.b < 5 ? 14 - pl.b : 5);
-    if (pl.b == 12) pl.c = 3;  // 2^15-word tile, one 512-thread CTA per SM: 32-byte row segments instead of 16
+    // 2^10 .. 2^12 rows: 2^15-word tile on ONE 512-thread CTA per SM (128- / 64- / 32-byte row segments) instead of two
+    // 2^14-word tiles: po2 = 20 NTT stage 7.19 -> 6.85 ms, po2 = 21 17.1 -> 14.1 ms, po2 = 22 38.4 -> 29.9 ms
+    if (pl.b >= 10 && pl.b <= 12) pl.c = 15 - pl.b;
     if (const char* env = std::getenv("HFB200_NTT_C")) { int v = std::atoi(env); if (v >= 0 && v <= pl.c) pl.c = v; }
     if (pl.c > pl.a) pl.c = pl.a;
     if (pl.c < 0) pl.c = 0;
@@ -770,6 +772,7 @@ struct Ntt {
         uint64_t grid = (uint64_t)dev->sm_count * per_sm;
         if (grid > tiles) grid = tiles;
         const int key = b * 10000 + c * 100 + a;
+        static const int big_threads = std::getenv("HFB200_STR_T") ? std::atoi(std::getenv("HFB200_STR_T")) : 1024;
         switch (key) {
             case 100310: dev->launch<StridedKernel2<10, 3, 10>, 256, 4>((unsigned)grid, 1, 256, smem, p); break;
             case 100312: dev->launch<StridedKernel2<10, 3, 12>, 256, 4>((unsigned)grid, 1, 256, smem, p); break;
@@ -780,8 +783,13 @@ struct Ntt {
             case 100414: dev->launch<StridedKernel2<10, 4, 14>, 256, STR_MINB>((unsigned)grid, 1, 256, smem, p); break;
             case 110310: dev->launch<StridedKernel2<11, 3, 10>, 256, STR_MINB>((unsigned)grid, 1, 256, smem, p); break;
             case 110312: dev->launch<StridedKernel2<11, 3, 12>, 256, STR_MINB>((unsigned)grid, 1, 256, smem, p); break;
-            case 120310: dev->launch<StridedKernel2<12, 3, 10>, 512, 1>((unsigned)grid, 1, 512, smem, p); break;
-            case 120312: dev->launch<StridedKernel2<12, 3, 12>, 512, 1>((unsigned)grid, 1, 512, smem, p); break;
+            // 2^15-word tiles: one 1024-thread CTA per SM (512 threads: 6.85 ms, 1024: 6.58 ms for the po2 = 20 NTT stage)
+            case 100510: dev->launch<StridedKernel2<10, 5, 10>, 1024, 1>((unsigned)grid, 1, big_threads, smem, p); break;
+            case 100512: dev->launch<StridedKernel2<10, 5, 12>, 1024, 1>((unsigned)grid, 1, big_threads, smem, p); break;
+            case 110410: dev->launch<StridedKernel2<11, 4, 10>, 1024, 1>((unsigned)grid, 1, big_threads, smem, p); break;
+            case 110412: dev->launch<StridedKernel2<11, 4, 12>, 1024, 1>((unsigned)grid, 1, big_threads, smem, p); break;
+            case 120310: dev->launch<StridedKernel2<12, 3, 10>, 1024, 1>((unsigned)grid, 1, big_threads, smem, p); break;
+            case 120312: dev->launch<StridedKernel2<12, 3, 12>, 1024, 1>((unsigned)grid, 1, big_threads, smem, p); break;
             case 120210: dev->launch<StridedKernel2<12, 2, 10>, 256, STR_MINB>((unsigned)grid, 1, 256, smem, p); break;
             case 120212: dev->launch<StridedKernel2<12, 2, 12>, 256, STR_MINB>((unsigned)grid, 1, 256, smem, p); break;
             case 90510: dev->launch<StridedKernel2<9, 5, 10>, 256, 2>((unsigned)grid, 1, 256, smem, p); break;
