@@ -456,7 +456,7 @@ struct Mid2Layout {
         twI = o; if (intt) o += pw << p.a;          // per-level layout: tw[2^(l-1) + x] = w_{2^l}^-x
         twF = o; if (fwd) o += pw << (p.a + p.e);
         G3 = o; if (intt && p.b > 0 && !fly) o += 1u << p.a;
-        Gs = o; if (intt && !fly) o += 1u << p.a;
+        Gs = o; if (intt && !fly) o += (padded_words(1u << p.a) + 1u) & ~1u;  // padded like the data: the register tail reads 2^RF consecutive entries per thread
         G2 = o; if (fwd && p.b > 0 && !fly) o += pw << (p.a + p.e);
         unit0 = o;
         uint32_t u = 0;
@@ -535,7 +535,7 @@ struct MiddleKernel2 {
                 }
             }
 #pragma unroll
-            for (int j = 0; j < (1 << RF); j++) v[j] = fmul(v[j], fly ? gs(p, rb, base + j) : Gs[base + j]);
+            for (int j = 0; j < (1 << RF); j++) v[j] = fmul(v[j], fly ? gs(p, rb, base + j) : Gs[padi(base + j)]);
         }
         if (!fwd) {
 #pragma unroll
@@ -610,7 +610,7 @@ struct MiddleKernel2 {
             }
             if (!fly) {
                 if (p.b > 0) for (uint32_t i = cx.tid; i < na; i += cx.nt) G3[i] = g3(p, rb, i);
-                for (uint32_t i = cx.tid; i < na; i += cx.nt) Gs[i] = gs(p, rb, i);
+                for (uint32_t i = cx.tid; i < na; i += cx.nt) Gs[padi(i)] = gs(p, rb, i);
             }
         }
         if (fwd) {
