@@ -115,6 +115,9 @@ HD uint32_t fmul_const(uint32_t x, uint32_t d, uint32_t dp) {
     return umin32(r, r - P);
 }
 
+#ifndef P2_DEFERRED_SUM
+#define P2_DEFERRED_SUM 1  // 0: plain internal layer; 1: carried row sum, 23 S by a Shoup product; 2: 23 S by doublings
+#endif
 // External layer: M4 on each 4-chunk (Poseidon2 add/double chain) then add the cross-chunk column sums.
 HD void p2_m_ext(uint32_t* s) {
 #pragma unroll
@@ -150,11 +153,46 @@ HD void p2_mix(uint32_t* s) {
         for (int i = 0; i < 24; i++) s[i] = sbox7_rc(s[i], k.rc_first[r * 24 + i]);
         p2_m_ext(s);
     }
+#if P2_DEFERRED_SUM
+    // Partial rounds with the row sum carried instead of recomputed.  The round maps y_i -> mu_i y_i + S with S = sum_i y_i
+    // (after the S-box on y_0).  With U = sum_{i>=1} y_i kept canonical:  S = y_0 + U,  t_i = mu_i y_i (Shoup: accepts ANY
+    // 32-bit y_i),  U' = sum_{i>=1} t_i + 23 S,  y_0' = t_0 + S (canonical: it meets the S-box),  y_i' = t_i + S left in
+    // [0, 2p) for i >= 1 (one add, no range correction: its only reader is the next Shoup product).
+    {
+        uint32_t U = s[1];
+#pragma unroll
+        for (int i = 2; i < 24; i++) U = padd(U, s[i]);
+#pragma unroll 1
+        for (int r = 0; r < 21; r++) {
+            s[0] = sbox7_rc(s[0], k.rc_partial[r]);
+            const uint32_t S = padd(s[0], U);
+            uint32_t t[24];
+#pragma unroll
+            for (int i = 0; i < 24; i++) t[i] = fmul_const(s[i], k.diag_std[i], k.diag_shoup[i]);
+            uint32_t T = t[1];
+#pragma unroll
+            for (int i = 2; i < 24; i++) T = padd(T, t[i]);
+#if P2_DEFERRED_SUM == 2
+            uint32_t S2 = padd(S, S), S4 = padd(S2, S2), S8 = padd(S4, S4), S16 = padd(S8, S8);
+            const uint32_t S23 = fsub(padd(S16, S8), S);
+#else
+            const uint32_t S23 = fmul_const(S, 23u, (uint32_t)((23ull << 32) / P));
+#endif
+            U = padd(T, S23);
+            s[0] = padd(t[0], S);
+#pragma unroll
+            for (int i = 1; i < 24; i++) s[i] = fadd_lazy(t[i], S);
+        }
+#pragma unroll
+        for (int i = 1; i < 24; i++) s[i] = umin32(s[i], s[i] - P);
+    }
+#else
 #pragma unroll 1
     for (int r = 0; r < 21; r++) {
         s[0] = sbox7_rc(s[0], k.rc_partial[r]);
         p2_m_int(s, k);
     }
+#endif
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
 #pragma unroll
