@@ -52,6 +52,30 @@ def test_tamper_rejected_like_the_oracle(pkg, gpu_lib, proved):
         pkg.verify_segment(seal, cps["code_root"], (8, 24, 8), lib=gpu_lib)
 
 
+def test_random_mutations_never_crash_and_never_verify(pkg, gpu_lib, proved):
+    """Robustness: arbitrary word replacements, truncations and extensions end in a clean rejection (the verifier parses
+    attacker-controlled data: no out-of-range access, no huge allocation)."""
+    cir, seal, cps = proved
+    rng = np.random.default_rng(7)
+    for trial in range(150):
+        bad = seal.copy()
+        kind = trial % 4
+        if kind == 0:      # one word replaced by a random 32-bit value
+            bad[rng.integers(0, len(bad))] = rng.integers(0, 1 << 32, dtype=np.uint64).astype(np.uint32)
+        elif kind == 1:    # a run of words replaced
+            a = int(rng.integers(0, len(bad) - 64)); bad[a:a + 64] = rng.integers(0, 1 << 31, 64, dtype=np.uint64).astype(np.uint32)
+        elif kind == 2:    # truncated anywhere
+            bad = bad[:int(rng.integers(0, len(bad)))]
+        else:              # the po2 word (seal[32]) set to anything
+            bad[32] = np.uint32(rng.integers(0, 64))
+            if bad[32] == seal[32]:
+                bad[32] = np.uint32(31)
+        with pytest.raises(pkg.Hfb200Error):
+            pkg.verify_segment(bad, cps["code_root"], SMALL, lib=gpu_lib)
+    with pytest.raises(pkg.Hfb200Error):
+        pkg.verify_segment(np.zeros(0, np.uint32), cps["code_root"], SMALL, lib=gpu_lib)
+
+
 def test_non_canonical_element_rejected(pkg, gpu_lib, proved):
     cir, seal, cps = proved
     bad = seal.copy()
