@@ -22,7 +22,7 @@ EXPORTS = [
     "hfb200_total_launches", "hfb200_op_interpolate_ntt", "hfb200_op_expand_ntt", "hfb200_op_lde", "hfb200_op_merkle",
     "hfb200_op_poseidon2", "hfb200_op_fri_fold", "hfb200_bench_lde", "hfb200_bench_merkle", "hfb200_bench_modmul",
     "hfb200_mark", "hfb200_mark_elapsed",
-    "hfb200_pool_create", "hfb200_pool_prove", "hfb200_pool_destroy",
+    "hfb200_pool_create", "hfb200_pool_load_control", "hfb200_pool_prove", "hfb200_pool_destroy",
 ]
 
 
@@ -98,6 +98,7 @@ def load_library(path=None):
         "hfb200_mark_elapsed": (err, [vp, C.c_int, vp, C.c_int, C.POINTER(C.c_float)]),
         "hfb200_pool_create": (err, [C.POINTER(C.c_int), C.c_int, C.c_int, u32, C.POINTER(CircuitDesc), C.POINTER(vp)]),
         "hfb200_pool_prove": (err, [vp, C.POINTER(SegmentJob), sz]),
+        "hfb200_pool_load_control": (err, [vp, u32, vp]),
         "hfb200_pool_destroy": (None, [vp]),
     }
     for name, (res, args) in sig.items():
@@ -411,17 +412,33 @@ class Pool:
     def __exit__(self, *a):
         self.close()
 
+    def load_control(self, po2, code):
+        """Shared control group of the po2-sized segments: jobs of that po2 may then pass code=None (identical seals)."""
+        if not hasattr(self, "_control"):
+            self._control = {}
+        if code is None:
+            self._control.pop(po2, None)
+            self._raise(self.lib.hfb200_pool_load_control(self._h, po2, None))
+            return
+        code = _u32(code)
+        if code.size != self.circuit[0] << po2:
+            raise Hfb200Error("load_control: control columns do not match (circuit, po2)")
+        self._control[po2] = code  # keeps the buffer alive: the library holds the pointer
+        self._raise(self.lib.hfb200_pool_load_control(self._h, po2, _ptr(code)))
+
     def prove(self, jobs, seal_cap):
-        """jobs: list of (po2, globals, code, data, blind_seed) with numpy u32 arrays.  Returns (seals, devices, ms)."""
+        """jobs: list of (po2, globals, code, data, blind_seed) with numpy u32 arrays (code may be None after load_control).
+        Returns (seals, devices, ms)."""
         n = len(jobs)
         arr = (SegmentJob * n)()
         keep = []
         seals = [np.empty(seal_cap, np.uint32) for _ in range(n)]
         for i, (po2, g, code, data, seed) in enumerate(jobs):
-            g, code, data = _u32(g), _u32(code), _u32(data)
+            g, data = _u32(g), _u32(data)
+            code = _u32(code) if code is not None else None
             keep.append((g, code, data))
             arr[i].po2, arr[i].blind_seed = po2, seed
-            arr[i].globals, arr[i].code, arr[i].data = g.ctypes.data, code.ctypes.data, data.ctypes.data
+            arr[i].globals, arr[i].code, arr[i].data = g.ctypes.data, (code.ctypes.data if code is not None else None), data.ctypes.data
             arr[i].seal_out, arr[i].seal_cap = seals[i].ctypes.data, seal_cap
         e = self.lib.hfb200_pool_prove(self._h, arr, n)
         errs = []

@@ -5,6 +5,7 @@
 #include "verify.cuh"
 #include <algorithm>
 #include <atomic>
+#include <map>
 #include <memory>
 #include <thread>
 
@@ -201,6 +202,7 @@ uint64_t hfb200_total_launches(const hfb200_ctx* ctx) { return ctx ? ctx->p.dev.
 struct hfb200_pool {
     std::vector<std::unique_ptr<hfb200_ctx>> ctxs;
     std::vector<int> device_of;
+    std::map<uint32_t, const uint32_t*> control;  // po2 -> caller-owned control columns (hfb200_pool_load_control)
 };
 extern "C" {
 
@@ -240,6 +242,15 @@ const char* hfb200_pool_prove(hfb200_pool* pool, hfb200_segment_job* jobs, size_
             if (k >= n_jobs) break;
             hfb200_segment_job& j = jobs[order[k]];
             const auto t0 = std::chrono::steady_clock::now();
+            if (!j.code) {
+                // shared control group: (re)commit it on this context when it is not the one resident for this po2
+                const auto it = pool->control.find(j.po2);
+                if (it == pool->control.end()) { j.error = dup_err("code is NULL and no control group was loaded for this po2 (hfb200_pool_load_control)"); continue; }
+                if (!(ctx->p.control_cached && ctx->p.po2 == j.po2)) {
+                    uint32_t root[8];
+                    if ((j.error = hfb200_control_root(ctx, j.po2, it->second, root))) continue;
+                }
+            }
             j.error = hfb200_prove_segment(ctx, j.po2, j.globals, j.code, j.data, j.blind_seed, j.seal_out, j.seal_cap, &j.seal_words);
             j.device = pool->device_of[w];
             j.ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -250,6 +261,13 @@ const char* hfb200_pool_prove(hfb200_pool* pool, hfb200_segment_job* jobs, size_
     for (auto& t : th) t.join();
     for (size_t i = 0; i < n_jobs; i++)
         if (jobs[i].error) return dup_err(std::string("job ") + std::to_string(i) + ": " + jobs[i].error);
+    API_CATCH
+}
+
+const char* hfb200_pool_load_control(hfb200_pool* pool, uint32_t po2, const uint32_t* code) {
+    API_TRY
+    if (!pool) throw Err("hfb200_pool_load_control: NULL pool");
+    if (code) pool->control[po2] = code; else pool->control.erase(po2);
     API_CATCH
 }
 

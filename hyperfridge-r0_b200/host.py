@@ -27,6 +27,7 @@ class ProverOpts:
     circuit: tuple = (16, 192, 48)
     devices: tuple = (0,)
     contexts_per_device: int = 2
+    reuse_control: bool = False  # opt-in: segments of equal po2 share the control group of the first one (true for rv32im)
 
     def __post_init__(self):
         if self.hashfn != "poseidon2":
@@ -85,7 +86,15 @@ class B200Prover:
         for s in session.segments:
             if s.po2 > self.opts.max_segment_po2:
                 raise Hfb200Error("segment po2 %d exceeds max_segment_po2 %d" % (s.po2, self.opts.max_segment_po2))
-        jobs = [(s.po2, s.globals_, s.code, s.data, s.blind_seed) for s in session.segments]
+        if self.opts.reuse_control:
+            first = {}
+            for s in session.segments:
+                first.setdefault(s.po2, s.code)
+            for po2, code in first.items():
+                self._pool.load_control(po2, code)
+            jobs = [(s.po2, s.globals_, None, s.data, s.blind_seed) for s in session.segments]
+        else:
+            jobs = [(s.po2, s.globals_, s.code, s.data, s.blind_seed) for s in session.segments]
         seals, devices, ms = self._pool.prove(jobs, seal_cap)
         segs = [SegmentReceipt(seal=seal, index=s.index, hashfn=self.opts.hashfn) for s, seal in zip(session.segments, seals)]
         receipt = Receipt(CompositeReceipt(segs), Journal(encode_journal(session.journal)))

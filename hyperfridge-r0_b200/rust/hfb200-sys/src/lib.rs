@@ -89,6 +89,7 @@ extern "C" {
         out: *mut *mut hfb200_pool,
     ) -> *const c_char;
     pub fn hfb200_pool_prove(pool: *mut hfb200_pool, jobs: *mut hfb200_segment_job, n_jobs: usize) -> *const c_char;
+    pub fn hfb200_pool_load_control(pool: *mut hfb200_pool, po2: u32, code: *const u32) -> *const c_char;
     pub fn hfb200_pool_destroy(pool: *mut hfb200_pool);
     /// `Receipt::verify` for one segment seal (host code, no device needed).  Exactly one of `circuit` / `ir` is non-null.
     pub fn hfb200_verify_segment(

@@ -171,6 +171,10 @@ const char* hfb200_pool_create(const int* devices, int n_devices, int contexts_p
                                const hfb200_circuit_desc* circuit, hfb200_pool** out);
 /* Proves all jobs; returns NULL when every job succeeded, else the first job's error (also left in jobs[i].error). */
 const char* hfb200_pool_prove(hfb200_pool* pool, hfb200_segment_job* jobs, size_t n_jobs);
+/* Shared control group for the jobs of one po2 (opt-in): `code` = u32[w_code][2^po2], caller-owned, must stay valid while the pool
+ * may use it (NULL forgets it).  Jobs of that po2 may then carry code == NULL: every worker context commits the control group once
+ * (hfb200_control_root) and reuses it; seals are identical to the ones produced with the columns passed per job. */
+const char* hfb200_pool_load_control(hfb200_pool* pool, uint32_t po2, const uint32_t* code);
 void hfb200_pool_destroy(hfb200_pool* pool);
 
 /* ---- HAL-level operators (second seam: risc0-zkp `Hal` methods), host buffers in/out ----------- */

@@ -31,6 +31,14 @@ def test_host_mirror_proves_a_session(pkg, emu_lib, orc):
     opts = pkg.ProverOpts(max_segment_po2=13, circuit=SMALL, devices=(0, 0), contexts_per_device=1)
     with pkg.default_prover(opts, lib=emu_lib) as prover:
         info = prover.prove(pkg.Session(segs, journal='{"iban":"CH00"}'))
+    # opt-in control-group reuse through the pool: same seals (segments of equal po2 share their control columns here)
+    opts_rc = pkg.ProverOpts(max_segment_po2=13, circuit=SMALL, devices=(0, 0), contexts_per_device=1, reuse_control=True)
+    with pkg.default_prover(opts_rc, lib=emu_lib) as prover:
+        info_rc = prover.prove(pkg.Session(segs, journal='{"iban":"CH00"}'))
+        with pytest.raises(pkg.Hfb200Error, match="no control group"):
+            prover._pool.prove([(14, segs[0].globals_, None, segs[0].data, 1)], 1 << 18)
+    for a, b in zip(info.receipt.inner.segments, info_rc.receipt.inner.segments):
+        assert np.array_equal(np.asarray(a.seal), np.asarray(b.seal))
     rec = pkg.Receipt.from_json(info.receipt.to_json())      # serde-shaped JSON round trip
     assert [s.index for s in rec.inner.segments] == [0, 1, 2]
     for s, e in zip(rec.inner.segments, expect):
