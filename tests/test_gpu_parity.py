@@ -168,6 +168,10 @@ def test_po2_22_large_segment(pkg, gpu_lib, orc):
         assert cir.verify(seal, c.checkpoint("code_root")) == po2
         st = c.last_stats()
         print("po2=22 segment: %.1f ms (ntt %.1f, hash %.1f)" % (st["ms_total"], st["ms_ntt_main"], st["ms_hash_main"]))
+        # the po2 = 22 LDE plan itself (2^10 chunk, 2^12-row strided stages on 2^15-word tiles), bit for bit
+        x = rand_elems(np.random.default_rng(2222), (2, 1 << po2))
+        x[1, ::7] = np.uint32(P - 1)
+        assert (c.op_lde(x) == orc.expand_ntt(orc.zk_shift(orc.interpolate_ntt(x)), 2)).all()
 
 
 def test_pool_and_concurrent_contexts_on_gpu(pkg, gpu_lib, orc):
