@@ -189,7 +189,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-control-cache", action="store_true", help="skip the informational e2e leg with the control group kept on the device")
     ap.add_argument("--no-camt53", action="store_true", help="skip the measured 37-segment proof (N=1 only)")
-    ap.add_argument("--inflight", type=int, default=3, help="prover contexts (segments in flight) per GPU")
+    ap.add_argument("--inflight", type=int, default=4, help="prover contexts (segments in flight) per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
