@@ -213,8 +213,9 @@ struct EvalCheckKernel {
                 const uint16_t* pk = spk + 6 * k;
                 const uint32_t e = derived_expr(k, p.ev_data[(uint64_t)pk[0] * domain + i], p.ev_data[(uint64_t)pk[1] * domain + i], p.ev_data[(uint64_t)pk[2] * domain + i],
                                                 p.ev_data[(uint64_t)pk[3] * domain + i], p.ev_data[(uint64_t)pk[4] * domain + ib], p.ev_code[(uint64_t)pk[5] * domain + i]);
-                const uint32_t cv = fmul(active, fsub(p.ev_data[(uint64_t)(cd.n_free + k) * domain + i], e));
-                e4a_mac(lt, mp[j], cv);
+                // every constraint but the last carries the selector `active`: it is factored out of the sum (one Fp4 scale
+                // at the end instead of one product per constraint; exact arithmetic, same value)
+                e4a_mac(lt, mp[j], fsub(p.ev_data[(uint64_t)(cd.n_free + k) * domain + i], e));
             }
             const uint32_t nf = fsub(ONE, first);
             for (uint32_t r = 0; r < cd.n_chains; r++) {
@@ -227,10 +228,11 @@ struct EvalCheckKernel {
                 s.c[0] = fadd(s.c[0], first);
                 t.c[0] = fadd(t.c[0], p.ev_data[(uint64_t)cd.chain_src[r] * domain + i]);
                 const E4 pr = e4_mul(s, t);
-                for (int k = 0; k < 4; k++, j++) e4a_mac(lt, mp[j], fmul(active, fsub(acc.c[k], pr.c[k])));
+                for (int k = 0; k < 4; k++, j++) e4a_mac(lt, mp[j], fsub(acc.c[k], pr.c[k]));
             }
-            e4a_mac(lt, mp[j], fmul(first, fsub(p.ev_data[i], p.global0)));
-            const E4 tot = e4a_redc(lt);
+            E4A lf = e4a_zero();
+            e4a_mac(lf, mp[j], fmul(first, fsub(p.ev_data[i], p.global0)));
+            const E4 tot = e4_add(e4_scale(e4a_redc(lt), active), e4a_redc(lf));
             const uint32_t yi = p.yinv[i & 3];
             for (int k = 0; k < 4; k++) p.check[(uint64_t)k * domain + i] = fmul(tot.c[k], yi);
         }
