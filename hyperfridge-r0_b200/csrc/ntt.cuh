@@ -638,12 +638,14 @@ struct MiddleKernel2 {
                 const DstIO D{p.out + (uint64_t)col * p.out_stride + ((uint64_t)hi << (p.a + p.e)), G2, p.rt.f_lo, p.rt.f_hi, rb, 24 - p.n - p.e, gmode};
                 uint32_t* dst_coef = p.out + (uint64_t)col * p.out_stride + ((uint64_t)hi << p.a);
                 const SmemIO SA{A}, SB{B};
-                if constexpr (MA == 10 && ME == 2) {  // host dispatches this instantiation only for the fused iNTT+LDE
+                if constexpr (MA == 10 && ME == 2) {  // host dispatches this instantiation for the fused iNTT+LDE and the expand-only LDE
                     // main-group schedule, all sizes compile-time: DIF 3+3 (+4 in registers), DIT (4 in registers +) 3+3
                     const SmemIOT<PSB> SB6{B};
-                    round_t<3, true, 10, 0, 7, true, false, true>(ux, twI, 10, 0, 7, G, SA); ux.sync();
-                    round_t<3, true, 10, 0, 4, true, true, true>(ux, twI, 10, 0, 4, SA, SA); ux.sync();
-                    tail<4>(ux, p, rb, false, G, A, twI, twF, Gs, B, dst_coef, D); ux.sync();
+                    if (intt) {
+                        round_t<3, true, 10, 0, 7, true, false, true>(ux, twI, 10, 0, 7, G, SA); ux.sync();
+                        round_t<3, true, 10, 0, 4, true, true, true>(ux, twI, 10, 0, 4, SA, SA); ux.sync();
+                    }
+                    tail<4>(ux, p, rb, !intt, G, A, twI, twF, Gs, B, dst_coef, D); ux.sync();  // expand-only: coefficients straight from global
                     round_t<3, false, 12, 0, 6, true, false, true>(ux, twF, 12, 0, 6, SB6, SB6); ux.sync();
                     round_t<3, false, 12, 0, 9, true, false, true>(ux, twF, 12, 0, 9, SB6, D);
                 } else {
@@ -826,7 +828,8 @@ struct Ntt {
 #ifdef HFB200_EMU
         p.ut = MID_UT;
 #endif
-        const bool main_cfg = a == 10 && e == 2 && intt && fwd && !(p.flags & MID_GFLY);
+        // the compile-time kernel serves the fused iNTT+LDE and the expand-only LDE (check group, FRI rounds) of 2^10 chunks
+        const bool main_cfg = a == 10 && e == 2 && fwd && !(p.flags & MID_GFLY);
         p.shp = main_cfg ? 1 : 0;
         // main group: ONE 512-thread CTA per SM (8 units sharing one set of Shoup-pair tables, 215 KB); otherwise two
         // 256-thread CTAs per SM for chunks up to 2^10
