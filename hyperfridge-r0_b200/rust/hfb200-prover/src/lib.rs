@@ -33,6 +33,35 @@ impl B200SegmentProver {
     }
 }
 
+impl B200SegmentProver {
+    /// Control id of (circuit, po2): commits the control columns once and keeps them on the device, so that the segments
+    /// that follow can be proved with `prove_trace_shared_control` (identical seals, no per-segment control commitment).
+    pub fn load_control(&self, po2: u32, code: &[u32]) -> Result<[u32; 8]> {
+        let mut root = [0u32; 8];
+        sys::ffi_wrap(|| unsafe { sys::hfb200_control_root(self.ctx, po2, code.as_ptr(), root.as_mut_ptr()) })?;
+        Ok(root)
+    }
+
+    pub fn prove_trace_shared_control(&self, po2: u32, globals: &[u32], data: &[u32], blind_seed: u64) -> Result<Vec<u32>> {
+        let cap = unsafe { sys::hfb200_seal_words(self.ctx, po2) };
+        let mut seal = vec![0u32; cap];
+        let mut words = 0usize;
+        sys::ffi_wrap(|| unsafe {
+            sys::hfb200_prove_segment(self.ctx, po2, globals.as_ptr(), std::ptr::null(), data.as_ptr(), blind_seed, seal.as_mut_ptr(), cap, &mut words)
+        })?;
+        seal.truncate(words);
+        Ok(seal)
+    }
+}
+
+/// `SegmentReceipt::verify_integrity` for the seals this library emits (host code, no GPU needed): `check_code` of upstream's
+/// verifier becomes the comparison against `control_id` (one entry of the per-po2 control-id table).
+pub fn verify_seal(circuit: &sys::hfb200_circuit_desc, seal: &[u32], control_id: &[u32; 8]) -> Result<u32> {
+    let mut po2 = 0u32;
+    sys::ffi_wrap(|| unsafe { sys::hfb200_verify_segment(circuit, std::ptr::null(), seal.as_ptr(), seal.len(), control_id.as_ptr(), &mut po2) })?;
+    Ok(po2)
+}
+
 impl Drop for B200SegmentProver {
     fn drop(&mut self) {
         unsafe { sys::hfb200_destroy(self.ctx) }
