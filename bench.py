@@ -144,38 +144,60 @@ def reference_arm(args):
     return 0
 
 
-def camt53_leg(pkg, ctx, device, po2, inflight, g, code_h, data_h):
-    """One camt53-sized proof end to end: 37 po2-sized segments, host buffers in, verified receipt out."""
+def camt53_leg(pkg, ctx, device, po2, inflight, g, code_h, data_h, rank=0, world=1, dist=None, barrier=None, max_over_ranks=None):
+    """One camt53-sized proof end to end: 37 po2-sized segments, host buffers in, verified receipt out.  With N ranks the
+    segments of the ONE proof are sharded round-robin (scheduler.shard), every rank proves its share on its own GPU through
+    the host mirror of the reference call site, and only the seals return to rank 0 over the host (gather_object), where
+    the receipt is assembled, sent through its JSON wire form and verified seal by seal.  No data-path collective."""
     import numpy as np
     import importlib
     sched = importlib.import_module("hyperfridge_r0_b200.scheduler")
     with open(os.path.join(ROOT, "tests", "golden", "reference_journal.json")) as f:
         journal_bytes = bytes(json.load(f)["journal_bytes"])
     journal_text = pkg.decode_journal(journal_bytes)
-    segs = [pkg.Segment(i, po2, g, code_h, data_h, sched.job_seed(1, 0, i)) for i in range(CAMT53_SEGMENTS)]
+    mine = sched.shard([{"segment": i, "po2": po2} for i in range(CAMT53_SEGMENTS)], rank, world)
+    segs = [pkg.Segment(j["segment"], po2, g, code_h, data_h, sched.job_seed(1, 0, j["segment"])) for j in mine]
     opts = pkg.ProverOpts(max_segment_po2=po2, circuit=WIDTHS, devices=(device,), contexts_per_device=inflight)
     cap = ctx.seal_words(po2)
+    gathered = None
     with pkg.default_prover(opts) as prover:
-        prover.prove(pkg.Session(segs[:inflight], journal_text), seal_cap=cap)  # warm-up: one segment per worker
+        warm = prover.prove(pkg.Session(segs[:inflight], journal_text), seal_cap=cap)  # warm-up: one segment per worker
+        if dist is not None:
+            tmp = [None] * world if rank == 0 else None
+            dist.gather_object([np.asarray(s.seal)[:8] for s in warm.receipt.inner.segments], tmp, dst=0)  # warm the gather path
+            barrier()
         t0 = time.perf_counter()
         info = prover.prove(pkg.Session(segs, journal_text), seal_cap=cap)
+        if dist is not None:
+            gathered = [None] * world if rank == 0 else None
+            dist.gather_object([(s.index, np.asarray(s.seal, dtype=np.uint32)) for s in info.receipt.inner.segments], gathered, dst=0)
         prove_s = time.perf_counter() - t0
+    if max_over_ranks is not None:
+        prove_s = max_over_ranks(prove_s)
+    if rank != 0:
+        return None
+    if gathered is not None:
+        allsegs = sorted((x for part in gathered for x in part), key=lambda t: t[0])
+        full = pkg.Receipt(pkg.CompositeReceipt([pkg.SegmentReceipt(seal=seal, index=i) for i, seal in allsegs]), pkg.Journal(journal_bytes))
+    else:
+        full = info.receipt
     t0 = time.perf_counter()
-    wire = info.receipt.to_json()
+    wire = full.to_json()
     receipt = pkg.Receipt.from_json(wire)
     json_s = time.perf_counter() - t0
     control_id = ctx.control_root(po2, code_h)
     t0 = time.perf_counter()
     receipt.verify({po2: control_id}, circuit=WIDTHS)
     verify_s = time.perf_counter() - t0
-    ok = receipt.journal.bytes_ == journal_bytes and len(receipt.inner.segments) == CAMT53_SEGMENTS
+    ok = receipt.journal.bytes_ == journal_bytes and [s.index for s in receipt.inner.segments] == list(range(CAMT53_SEGMENTS))
     if not ok:
-        raise SystemExit("bench.py: camt53 receipt does not carry the reference journal")
-    return {"segments": CAMT53_SEGMENTS, "po2": po2, "proof_seconds": prove_s, "segments_per_s": CAMT53_SEGMENTS / prove_s,
+        raise SystemExit("bench.py: camt53 receipt does not carry the reference journal / all segments")
+    return {"segments": CAMT53_SEGMENTS, "po2": po2, "n_gpus": world, "proof_seconds": prove_s, "segments_per_s": CAMT53_SEGMENTS / prove_s,
             "receipt_json_bytes": len(wire), "receipt_json_roundtrip_seconds": json_s, "verify_seconds": verify_s, "verified": True,
             "journal": "reference fixture journal (tests/golden/reference_journal.json), %d bytes" % len(journal_bytes),
-            "how": "default_prover().prove(session) through hfb200_pool_prove with host trace buffers, %d contexts in flight; every seal "
-                   "checked by hfb200_verify_segment against hfb200_control_root; wall clock" % inflight}
+            "how": "default_prover().prove(session) through hfb200_pool_prove with host trace buffers, %d contexts in flight per GPU, segments of the "
+                   "one proof sharded round-robin over %d GPU(s), seals gathered on rank 0 over the host; every seal checked by "
+                   "hfb200_verify_segment against hfb200_control_root; wall clock, max over ranks" % (inflight, world)}
 
 
 def main():
@@ -188,7 +210,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-control-cache", action="store_true", help="skip the informational e2e leg with the control group kept on the device")
-    ap.add_argument("--no-camt53", action="store_true", help="skip the measured 37-segment proof (N=1 only)")
+    ap.add_argument("--no-camt53", action="store_true", help="skip the measured 37-segment proof")
     ap.add_argument("--inflight", type=int, default=4, help="prover contexts (segments in flight) per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -368,8 +390,8 @@ def main():
         # of the reference call site: default_prover().prove(session) -> Receipt (host trace buffers, pool of F contexts),
         # then the receipt goes through its JSON wire form, every seal through the product verifier, and the journal
         # must be the reference fixture's.  Wall clock around prove(); verification timed separately.
-        if world == 1 and not args.no_camt53:
-            camt53 = camt53_leg(pkg, ctxs[0], local_rank, po2, F, gl[0], hb[0][0], hb[0][1])
+        if not args.no_camt53:
+            camt53 = camt53_leg(pkg, ctxs[0], local_rank, po2, F, gl[0], hb[0][0], hb[0][1], rank, world, dist, barrier, max_over_ranks)
         for c, (code_h, data_h) in zip(ctxs, hb):
             c.host_free(code_h)
             c.host_free(data_h)
