@@ -124,7 +124,7 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    po2 = oracle_sample_po2(args.steps, args.warmup)
+    po2 = args.sample_po2 if args.sample_po2 else oracle_sample_po2(args.steps, args.warmup)
     run_oracle_sample(po2, max(0, args.warmup)) if args.warmup else None
     t0 = time.perf_counter()
     times, cores = run_oracle_sample(po2, args.steps)
@@ -207,6 +207,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--po2", type=int, default=20)
+    ap.add_argument("--sample-po2", type=int, default=0, help="reference arm: size of the CPU sample segment (default: chosen from steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-control-cache", action="store_true", help="skip the informational e2e leg with the control group kept on the device")

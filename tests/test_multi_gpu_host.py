@@ -102,3 +102,25 @@ def test_two_rank_gloo_run_matches_single_process(pkg, emu_lib, orc):
             ctx.witgen_synth(12, 1000 + 10 * st + sg, seed)
             expect.append((st, sg, int(orc.hash_elems(ctx.prove_resident(seed) % orc.P)[0])))
     assert got == sorted(expect)
+
+
+def test_reference_arm_contract(orc):
+    """`bench.py --impl reference`: one JSON line with the contract's keys on rank 0, nothing on the other ranks."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--sample-po2", "13"]
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2")
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "segments/s" and d["higher_is_better"] is True and d["n_gpus"] == 2
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and "po2=20" in d["metric"]
+    env["RANK"] = "1"
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == ""
