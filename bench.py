@@ -426,7 +426,10 @@ def main():
                 "modmul_per_permutation": {"montgomery_sbox": 852, "shoup_const": 504},
                 "modmul_peak_measured_gmul_s": {"sbox_chain": peak_sbox / 1e9, "shoup": peak_shoup / 1e9},
                 "ms_at_modmul_peak": ideal_ms, "frac_of_modmul_peak": ideal_ms / hash_ms if hash_ms > 0 else 0.0,
-                "note": "multiplications only: the 2160 modular additions per permutation share the issue slots (ALU pipe)"}
+                "ncu": {"source": "profiles/r1_v6_hash_ncu_summary.txt (one --set full capture of HashRowsKernel, 192 columns; static, not re-measured by this run)",
+                        "sm__pipe_alu_cycles_active_pct": 52.3, "sm__pipe_fma_cycles_active_pct": 48.1, "fma_heavy_half_pct": 96.0,
+                        "smsp__issue_active_pct": 61.9, "dram_throughput_pct": 1.7},
+                "note": "multiplications only: the 2160 modular additions per permutation share the issue slots (ALU pipe); integer multiplies issue on the heavy half of the FMA pipe only (fmalite = 0), which is ~96 % busy"}
 
     # ---------------- CPU baseline (rank 0, N=1 only, bounded sample) ----------------
     cpu = None
