@@ -16,3 +16,23 @@ with pkg.Context(0, 14, (16, 64, 16), lib=lib) as ctx:
         code, data = ctx.read_group(1), ctx.read_group(2)
         assert (seal == ctx.prove_segment(po2, g, code, data, 1)).all()
 print("asan probe ok")
+# wider circuits (several DotKernel column groups, ragged widths), control-group reuse, the product verifier on good and bad seals
+for widths, po2 in (((16, 192, 48), 12), ((21, 72, 20), 12)):
+    with pkg.Context(0, po2, widths, lib=lib) as ctx:
+        g = ctx.witgen_synth(po2, 9, 1)
+        code, data = ctx.read_group(1), ctx.read_group(2)
+        seal = ctx.prove_segment(po2, g, code, data, 3)
+        root = ctx.control_root(po2, code)
+        assert (ctx.prove_segment(po2, g, None, data, 3) == seal).all()
+        assert pkg.verify_segment(seal, root, widths, lib=lib) == po2
+        for k in range(40):
+            bad = seal.copy()
+            if k % 2:
+                bad = bad[:int(rng.integers(0, len(bad)))]
+            else:
+                bad[int(rng.integers(0, len(bad)))] = np.uint32(rng.integers(0, 1 << 32, dtype=np.uint64))
+            try:
+                pkg.verify_segment(bad, root, widths, lib=lib)
+            except pkg.Hfb200Error:
+                pass
+print("asan probe 2 ok")
