@@ -1,0 +1,286 @@
+// hfb200_prover.hpp -- C++17 host side above the C ABI (include/hfb200.h): the reference's prover surface for the ONE hot path.
+//
+// The reference is compiled Rust and keeps this surface (/root/reference/host/src/main.rs):
+//     let prover = default_prover();                                   // :420
+//     let receipt = prover.prove(env, HYPERFRIDGE_ELF)?.receipt;       // :423   (ProveInfo { receipt, .. })
+//     serde_json::to_string(&receipt)                                  // :250-252
+//     receipt.journal.bytes / journal decode                           // :258-267
+//     receipt.verify(HYPERFRIDGE_ID)                                   // :622-624, /root/reference/verifier/src/main.rs:118-126
+// No Rust toolchain exists in this image, so the host mirror is written in C++ (header only, nothing but the C ABI underneath)
+// with the same names, argument meaning and error behaviour: errors are exceptions carrying the library's message (anyhow::Error
+// there), a dev-mode `Fake` receipt is refused by verify(), ProverOpts other than poseidon2 / composite are refused at construction.
+// The executor (ELF -> Session -> Segments) is out of scope: a Session here is the list of segment traces
+// the executor + witness generator would have produced, plus the journal the guest committed.  The Rust binding a maintainer adds is
+// in hyperfridge-r0_b200/rust/ and INTEGRATION.md.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "hfb200.h"
+
+namespace hfb200 {
+
+struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
+
+// risc0_sys::ffi_wrap: NULL = ok, else a malloc'd message the caller frees
+inline void ffi_wrap(const char* e) {
+    if (!e) return;
+    const std::string msg(e);
+    hfb200_free_error(e);
+    throw Error(msg);
+}
+
+using Digest = std::array<uint32_t, 8>;
+
+// Subset of risc0_zkvm::ProverOpts that matters on this path (the host passes none: defaults only).
+struct ProverOpts {
+    std::string hashfn = "poseidon2";
+    std::string receipt_kind = "composite";
+    uint32_t max_segment_po2 = 20;
+    hfb200_circuit_desc circuit{16, 192, 48, 0};
+    std::vector<int> devices{0};
+    int contexts_per_device = 2;
+    bool reuse_control = false;  // opt-in: segments of equal po2 share the control group of the first one (true for rv32im)
+};
+
+// What upstream's `Segment` boils down to at the prover seam: po2 and the witness columns (+ blinding seed).  Host pointers,
+// column-major u32[w][2^po2] Montgomery residues, owned by the caller for the duration of prove().
+struct Segment {
+    uint32_t index = 0, po2 = 0;
+    const uint32_t* globals = nullptr;  // [32]
+    const uint32_t* code = nullptr;
+    const uint32_t* data = nullptr;
+    uint64_t blind_seed = 0;
+};
+struct Session {
+    std::vector<Segment> segments;
+    std::string journal;  // the String the guest committed (risc0 serde: u32-LE length, bytes, zero pad to 4)
+};
+
+struct Journal {
+    std::vector<uint8_t> bytes;
+    static Journal encode(const std::string& text) {
+        Journal j;
+        const uint32_t n = (uint32_t)text.size();
+        for (int k = 0; k < 4; k++) j.bytes.push_back((uint8_t)(n >> (8 * k)));
+        j.bytes.insert(j.bytes.end(), text.begin(), text.end());
+        while (j.bytes.size() % 4) j.bytes.push_back(0);
+        return j;
+    }
+    std::string decode() const {
+        if (bytes.size() < 4) throw Error("journal too short");
+        const uint32_t n = bytes[0] | (bytes[1] << 8) | (bytes[2] << 16) | ((uint32_t)bytes[3] << 24);
+        if (4 + (size_t)n > bytes.size()) throw Error("journal length prefix exceeds the payload");
+        return std::string(bytes.begin() + 4, bytes.begin() + 4 + n);
+    }
+};
+
+struct SegmentReceipt {
+    std::vector<uint32_t> seal;
+    uint32_t index = 0;
+    std::string hashfn = "poseidon2";
+};
+
+namespace detail {
+// Minimal reader for the serde-JSON shape of a receipt (numbers, strings, arrays, objects; no escapes beyond \" and \\).
+struct Json {
+    const char* p; const char* end;
+    void ws() { while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++; }
+    bool eat(char c) { ws(); if (p < end && *p == c) { p++; return true; } return false; }
+    void need(char c) { if (!eat(c)) throw Error(std::string("receipt json: expected '") + c + "'"); }
+    std::string str() {
+        need('"');
+        std::string s;
+        while (p < end && *p != '"') { if (*p == '\\' && p + 1 < end) p++; s.push_back(*p++); }
+        need('"');
+        return s;
+    }
+    uint64_t num() {
+        ws();
+        if (p >= end || *p < '0' || *p > '9') throw Error("receipt json: expected a number");
+        uint64_t v = 0;
+        while (p < end && *p >= '0' && *p <= '9') { v = v * 10 + (uint64_t)(*p - '0'); if (v > 0xFFFFFFFFull) throw Error("receipt json: number out of range"); p++; }
+        return v;
+    }
+    void skip() {  // any value
+        ws();
+        if (p >= end) throw Error("receipt json: truncated");
+        if (*p == '"') { str(); return; }
+        if (*p == '{' || *p == '[') {
+            const char open = *p, close = open == '{' ? '}' : ']';
+            p++;
+            if (eat(close)) return;
+            do { if (open == '{') { str(); need(':'); } skip(); } while (eat(','));
+            need(close);
+            return;
+        }
+        while (p < end && *p != ',' && *p != '}' && *p != ']') p++;  // number / true / false / null
+    }
+    template <typename F> void object(F&& field) {
+        need('{');
+        if (eat('}')) return;
+        do { const std::string k = str(); need(':'); field(k); } while (eat(','));
+        need('}');
+    }
+    template <typename F> void array(F&& item) {
+        need('[');
+        if (eat(']')) return;
+        do { item(); } while (eat(','));
+        need(']');
+    }
+};
+}  // namespace detail
+
+// risc0_zkvm::Receipt { inner: InnerReceipt::{Composite, Fake}, journal }
+struct Receipt {
+    bool fake = false;
+    std::vector<SegmentReceipt> segments;  // inner = Composite
+    Journal journal;
+
+    std::string to_json() const {
+        std::string s = "{\"inner\":";
+        if (fake) s += "\"Fake\"";
+        else {
+            s += "{\"Composite\":{\"segments\":[";
+            for (size_t i = 0; i < segments.size(); i++) {
+                if (i) s += ',';
+                s += "{\"seal\":[";
+                for (size_t k = 0; k < segments[i].seal.size(); k++) { if (k) s += ','; s += std::to_string(segments[i].seal[k]); }
+                s += "],\"index\":" + std::to_string(segments[i].index) + ",\"hashfn\":\"" + segments[i].hashfn + "\",\"verifier_parameters\":[0,0,0,0,0,0,0,0],\"claim\":null}";
+            }
+            s += "],\"assumption_receipts\":[],\"verifier_parameters\":[0,0,0,0,0,0,0,0]}}";
+        }
+        s += ",\"journal\":{\"bytes\":[";
+        for (size_t k = 0; k < journal.bytes.size(); k++) { if (k) s += ','; s += std::to_string(journal.bytes[k]); }
+        s += "]}}";
+        return s;
+    }
+    // serde_json::from_slice::<Receipt> (/root/reference/verifier/src/main.rs:118-119)
+    static Receipt from_json(const std::string& text) {
+        Receipt r;
+        detail::Json j{text.data(), text.data() + text.size()};
+        bool have_inner = false, have_journal = false;
+        j.object([&](const std::string& k) {
+            if (k == "inner") {
+                have_inner = true;
+                j.ws();
+                if (j.p < j.end && *j.p == '"') { if (j.str() != "Fake") throw Error("receipt json: unknown inner receipt"); r.fake = true; return; }
+                j.object([&](const std::string& kind) {
+                    if (kind != "Composite") throw Error("receipt json: only Composite / Fake receipts are on this path");
+                    j.object([&](const std::string& f) {
+                        if (f != "segments") { j.skip(); return; }
+                        j.array([&] {
+                            SegmentReceipt sr;
+                            j.object([&](const std::string& g) {
+                                if (g == "seal") j.array([&] { sr.seal.push_back((uint32_t)j.num()); });
+                                else if (g == "index") sr.index = (uint32_t)j.num();
+                                else if (g == "hashfn") sr.hashfn = j.str();
+                                else j.skip();
+                            });
+                            r.segments.push_back(std::move(sr));
+                        });
+                    });
+                });
+            } else if (k == "journal") {
+                have_journal = true;
+                j.object([&](const std::string& f) {
+                    if (f != "bytes") { j.skip(); return; }
+                    j.array([&] { const uint64_t b = j.num(); if (b > 255) throw Error("receipt json: journal byte out of range"); r.journal.bytes.push_back((uint8_t)b); });
+                });
+            } else j.skip();
+        });
+        if (!have_inner || !have_journal) throw Error("receipt json: missing inner / journal");
+        return r;
+    }
+    size_t seal_bytes() const { size_t n = 0; for (const auto& s : segments) n += 4 * s.seal.size(); return n; }
+
+    // `receipt.verify(id)`: every segment seal against the control id of its po2 (upstream's per-po2 control-id table), segment
+    // indices 0..n-1, dev-mode receipts refused.  The claim chain / image id belong to the executor side (out of scope).
+    void verify(const std::map<uint32_t, Digest>& control_ids, const hfb200_circuit_desc& circuit = hfb200_circuit_desc{16, 192, 48, 0}) const {
+        if (fake) throw Error("verify: Fake receipt carries no seal (dev-mode receipts are refused)");
+        if (segments.empty()) throw Error("verify: composite receipt without segments");
+        for (size_t want = 0; want < segments.size(); want++) {
+            const SegmentReceipt& s = segments[want];
+            if (s.index != want) throw Error("verify: segment index " + std::to_string(s.index) + " at position " + std::to_string(want));
+            if (s.hashfn != "poseidon2") throw Error("verify: hash suite " + s.hashfn + " is not on this path");
+            if (s.seal.size() < 33) throw Error("verify: segment " + std::to_string(want) + ": seal truncated");
+            const uint32_t po2 = s.seal[32];  // seal layout: 32 globals, po2, ...
+            const auto it = control_ids.find(po2);
+            if (it == control_ids.end()) throw Error("verify: segment " + std::to_string(want) + ": no control id for po2 " + std::to_string(po2));
+            uint32_t got = 0;
+            try { ffi_wrap(hfb200_verify_segment(&circuit, nullptr, s.seal.data(), s.seal.size(), it->second.data(), &got)); }
+            catch (const Error& e) { throw Error("segment " + std::to_string(want) + ": " + e.what()); }
+        }
+    }
+};
+
+struct ProveInfo {
+    Receipt receipt;
+    std::vector<int> devices;      // which GPU proved each segment
+    std::vector<float> segment_ms;
+};
+
+// `default_prover()` stand-in over hfb200_pool: segments are independent, whole segments go to whichever context is free.
+class Prover {
+  public:
+    explicit Prover(const ProverOpts& o = ProverOpts()) : opts_(o) {
+        if (o.hashfn != "poseidon2") throw Error("only the default poseidon2 hash suite is on the hot path (sha-256 suite: out of scope)");
+        if (o.receipt_kind != "composite") throw Error("succinct / groth16 receipts need the recursion circuit: out of scope");
+        if (o.devices.empty()) throw Error("ProverOpts: no devices");
+        ffi_wrap(hfb200_pool_create(o.devices.data(), (int)o.devices.size(), o.contexts_per_device, o.max_segment_po2, &o.circuit, &pool_));
+    }
+    ~Prover() { hfb200_pool_destroy(pool_); }
+    Prover(const Prover&) = delete;
+    Prover& operator=(const Prover&) = delete;
+    const ProverOpts& opts() const { return opts_; }
+
+    // prover.prove(env, elf) -> ProveInfo
+    ProveInfo prove(const Session& session, size_t seal_cap_words = (size_t)1 << 18) {
+        for (const Segment& s : session.segments)
+            if (s.po2 > opts_.max_segment_po2) throw Error("segment po2 " + std::to_string(s.po2) + " exceeds max_segment_po2 " + std::to_string(opts_.max_segment_po2));
+        const size_t n = session.segments.size();
+        std::vector<std::vector<uint32_t>> seals(n, std::vector<uint32_t>(seal_cap_words));
+        std::vector<hfb200_segment_job> jobs(n);
+        if (opts_.reuse_control) {
+            std::map<uint32_t, const uint32_t*> first;
+            for (const Segment& s : session.segments) first.emplace(s.po2, s.code);
+            for (const auto& kv : first) ffi_wrap(hfb200_pool_load_control(pool_, kv.first, kv.second));
+        }
+        for (size_t i = 0; i < n; i++) {
+            const Segment& s = session.segments[i];
+            std::memset(&jobs[i], 0, sizeof jobs[i]);
+            jobs[i].po2 = s.po2; jobs[i].globals = s.globals; jobs[i].code = opts_.reuse_control ? nullptr : s.code; jobs[i].data = s.data;
+            jobs[i].blind_seed = s.blind_seed; jobs[i].seal_out = seals[i].data(); jobs[i].seal_cap = seal_cap_words;
+        }
+        const char* e = hfb200_pool_prove(pool_, jobs.data(), n);
+        std::string first_err;
+        for (size_t i = 0; i < n; i++)
+            if (jobs[i].error) { if (first_err.empty()) first_err = jobs[i].error; hfb200_free_error(jobs[i].error); }
+        if (e) { if (first_err.empty()) first_err = e; hfb200_free_error(e); }
+        if (!first_err.empty()) throw Error(first_err);
+        ProveInfo info;
+        for (size_t i = 0; i < n; i++) {
+            seals[i].resize(jobs[i].seal_words);
+            SegmentReceipt sr;
+            sr.seal = std::move(seals[i]); sr.index = session.segments[i].index; sr.hashfn = opts_.hashfn;
+            info.receipt.segments.push_back(std::move(sr));
+            info.devices.push_back(jobs[i].device);
+            info.segment_ms.push_back(jobs[i].ms);
+        }
+        info.receipt.journal = Journal::encode(session.journal);
+        return info;
+    }
+
+  private:
+    ProverOpts opts_;
+    hfb200_pool* pool_ = nullptr;
+};
+
+inline std::shared_ptr<Prover> default_prover(const ProverOpts& opts = ProverOpts()) { return std::make_shared<Prover>(opts); }
+
+}  // namespace hfb200
