@@ -50,3 +50,19 @@ def test_no_cpu_fallback_without_gpu(pkg):
         pytest.skip("GPU present")
     with pytest.raises(pkg.Hfb200Error, match="no CUDA device|CUDA"):
         pkg.Context(0, 12, (8, 16, 8))
+
+
+def test_public_headers_compile_standalone(tmp_path):
+    """include/hfb200.h is plain C (C99, no C++ or CUDA types); include/hfb200_prover.hpp is C++17 on top of it, warning-free."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    c = tmp_path / "h.c"
+    c.write_text('#include "hfb200.h"\nint main(void) { return 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), "-c", str(c), "-o", str(tmp_path / "h.o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    cpp = tmp_path / "h.cpp"
+    cpp.write_text('#include "hfb200_prover.hpp"\nint main() { return 0; }\n')
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), "-c", str(cpp), "-o", str(tmp_path / "h2.o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
