@@ -189,6 +189,11 @@ def test_pool_and_concurrent_contexts_on_gpu(pkg, gpu_lib, orc):
         seals, devs, ms = pool.prove(jobs, 40000)
         assert all(len(a) == len(b) and (a == b).all() for a, b in zip(seals, expect))
         assert set(devs) <= set(range(ndev))
+        # opt-in control-group reuse through the pool (mixed po2: a worker re-commits the group when its context changes size)
+        pool.load_control(12, jobs[0][2])
+        pool.load_control(13, jobs[1][2])
+        seals2, _, _ = pool.prove([(p_, g_, None, d_, s_) for (p_, g_, c_, d_, s_) in jobs], 40000)
+        assert all((a == b).all() for a, b in zip(seals2, expect))
     ctxs = [pkg.Context(0, 13, SMALL, lib=gpu_lib) for _ in range(2)]
     out = [None, None]
 
