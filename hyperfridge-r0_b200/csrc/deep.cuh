@@ -46,14 +46,20 @@ struct PowBitrevKernel {
     }
 };
 
-static constexpr uint32_t DOT_RPB = 4096;  // rows per block (= per partial sum)
+static constexpr uint32_t DOT_RPB = 4096;  // rows per block (= per partial sum) of the generic kernel and the upper bound of DotKernel's
+// DotKernel: rows per block chosen by the host so that small segments still spread over the SMs (2^16 cycles: 512 rows per block,
+// 128 row blocks x 3 column groups instead of 16 x 3)
+static inline uint32_t dot_rows_per_block(uint32_t po2) {
+    const uint64_t r = (1ull << po2) / 128;
+    return r < 512 ? 512u : (r > DOT_RPB ? DOT_RPB : (uint32_t)r);
+}
 // TMA-staged tile: DT_CG columns x DT_R rows of the trace + the DT_R (+1) weights of those rows per pipeline stage.
 static constexpr uint32_t DT_CG = 64, DT_R = 128, DT_STAGES = 3, DT_Q = 4, DT_T = DT_CG * DT_Q;
 static constexpr uint32_t DT_CSTRIDE = DT_R + 4;                                // words; 16-byte aligned column starts
 static constexpr uint32_t DT_STAGE_WORDS = DT_CG * DT_CSTRIDE + (DT_R + 4) * 4;  // columns, then the weights (E4)
 static constexpr size_t DT_SMEM = (size_t)DT_STAGES * DT_STAGE_WORDS * 4 + 64;
 
-// partial[(col * nblk + blk) * 2 + b] = sum over the block's DOT_RPB rows of cols[col][r] * Wt[(r + b) mod n]
+// partial[(col * nblk + blk) * 2 + b] = sum over the block's `rpb` rows of cols[col][r] * Wt[(r + b) mod n]
 // (b = 1 only for col < n_back1).  grid.x = row blocks, grid.y = column groups of DT_CG.
 //
 // B200 structure: the column segments (512 B each) and the weight slice of a stage arrive by TMA bulk copies
@@ -64,12 +70,12 @@ static constexpr size_t DT_SMEM = (size_t)DT_STAGES * DT_STAGE_WORDS * 4 + 64;
 // of the same q.  Bound: one IMAD.WIDE per Fp4 component and term.
 struct DotKernel {
     static constexpr bool kBarrier = true;
-    HD static void run(const KCtx& cx, uint32_t* sm, const uint32_t* cols, uint64_t col_stride, uint32_t ncols, uint32_t n_back1, const E4* Wt, uint32_t po2, E4* partial) {
+    HD static void run(const KCtx& cx, uint32_t* sm, const uint32_t* cols, uint64_t col_stride, uint32_t ncols, uint32_t n_back1, const E4* Wt, uint32_t po2, E4* partial, uint32_t rpb) {
         const uint64_t n = 1ull << po2;
         const uint32_t nblk = cx.gx, c0 = cx.by * DT_CG;
         const uint32_t ncg = ncols - c0 < DT_CG ? ncols - c0 : DT_CG;
-        const uint64_t row0 = (uint64_t)cx.bx * DOT_RPB;
-        const uint32_t n_iter = DOT_RPB / DT_R;
+        const uint64_t row0 = (uint64_t)cx.bx * rpb;
+        const uint32_t n_iter = rpb / DT_R;
 #ifdef __CUDA_ARCH__
         constexpr uint32_t NV = 1;
         uint64_t* bars = reinterpret_cast<uint64_t*>(sm + DT_STAGES * DT_STAGE_WORDS);

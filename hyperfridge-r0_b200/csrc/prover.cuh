@@ -149,7 +149,7 @@ struct Prover {
         const size_t N = (size_t)1 << p, W = cir.n_regs();
         // traces W*N, LDE (W+16)*4N, trees 4 * 2*4N*8, scratch wd*N, check 16N, E4 side arrays, FRI (< 40N), slack
         size_t words = W * N + (W + 16) * 4 * N + 4 * 64 * N + (size_t)cir.cd.w_data * N + 16 * N + 8 * 4 * N + 48 * N;
-        words += (W + 16) * ((N + DOT_RPB - 1) / DOT_RPB) * 16 + (1u << 20);
+        words += (W + 16) * ((N + 511) / 512) * 16 + (1u << 20);  // dot-product partials (>= 512 rows per block)
         return words * 4 + (64u << 20);
     }
 
@@ -312,10 +312,11 @@ struct Prover {
     // evaluates `w` columns against weight vector Wt (and its shift by one for the first n_back1 columns)
     void dot_group(const uint32_t* cols, uint32_t w, uint32_t n_back1, const E4* Wt, E4* out_dev) {
         const size_t N = (size_t)1 << po2;
-        const uint32_t nblk = (uint32_t)((N + DOT_RPB - 1) / DOT_RPB);
+        const uint32_t rpb = dot_rows_per_block(po2);
+        const uint32_t nblk = (uint32_t)(N / rpb);
         const size_t save = arena.off;
         E4* partial = arena.take<E4>((size_t)w * nblk * 2);
-        dev.launch<DotKernel, 256, 2>(nblk, (w + DT_CG - 1) / DT_CG, DT_T, DT_SMEM, cols, (uint64_t)N, w, n_back1, Wt, po2, partial);
+        dev.launch<DotKernel, 256, 2>(nblk, (w + DT_CG - 1) / DT_CG, DT_T, DT_SMEM, cols, (uint64_t)N, w, n_back1, Wt, po2, partial, rpb);
         dev.launch<DotReduceKernel, 128, 1>((2 * w + 127) / 128, 1, 128, 0, (const E4*)partial, w, nblk, out_dev);
         arena.off = save;  // stream order makes reuse by later kernels safe
     }
