@@ -431,6 +431,14 @@ def main():
                         "smsp__issue_active_pct": 61.9, "dram_throughput_pct": 1.7},
                 "note": "multiplications only: the 2160 modular additions per permutation share the issue slots (ALU pipe); integer multiplies issue on the heavy half of the FMA pipe only (fmalite = 0), which is ~96 % busy"}
 
+    # the NTT/LDE pipeline against the bound that binds it on sm_100a: 50 butterflies + 6 plain products per trace element,
+    # every one a Shoup-form modular product on the heavy half of the FMA pipe
+    ntt_products = 56.0 * W * N
+    ntt_ideal_ms = ntt_products / peak_shoup * 1e3 if peak_shoup > 0 else 0.0
+    roofline["multiply_bound"] = {"bound": "integer multiply pipe (FMA-heavy)", "modular_products": ntt_products, "peak_measured_gmul_s": peak_shoup / 1e9,
+                                  "ms_at_peak": ntt_ideal_ms, "frac": ntt_ideal_ms / ntt_ms if ntt_ms > 0 else 0.0,
+                                  "note": "multiplications only; at this bound the pipeline would reach %.2f of the HBM peak, which is why the north_star's 0.5 is out of reach for radix-2 BabyBear butterflies on the SIMT pipes" % (ntt_bytes / (ntt_ideal_ms * 1e-3) / 1e9 / peak if ntt_ideal_ms > 0 else 0.0)}
+
     # ---------------- CPU baseline (rank 0, N=1 only, bounded sample) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
