@@ -357,6 +357,9 @@ HD void round_io_dyn(const KCtx& cx, const uint32_t* tw, int k, int c, int l0, i
     }
 }
 
+#ifndef STR_R5
+#define STR_R5 1
+#endif
 #ifndef STR_MINB
 #define STR_MINB 2
 #endif
@@ -380,6 +383,20 @@ struct StridedKernel2 {
     HD static void tile(const KCtx& cx, const Str2Args& p, uint32_t* s, const uint32_t* tw, const uint32_t* src, uint32_t* dst) {
         const GlobStridedIO<SA> G{src, dst, p.a};
         const SmemIO S{s};
+#if STR_R5
+        if constexpr (SB == 10) {
+            // 2^10 rows: two radix-32 rounds (ONE shared-memory round trip instead of two), 32 values per thread, 512 threads
+            // on the 2^15-word tile: 4.82 -> 4.71 ms per 192-column LDE against the 4+3+3 schedule with 1024 threads
+            if (INV) {
+                round_t<5, true, SB, SC, 5, false, false, true>(cx, tw, SB, SC, 5, G, S); cx.sync();
+                round_t<5, true, SB, SC, 0, false, false, true>(cx, tw, SB, SC, 0, S, G);
+            } else {
+                round_t<5, false, SB, SC, 0, false, false, true>(cx, tw, SB, SC, 0, G, S); cx.sync();
+                round_t<5, false, SB, SC, 5, false, false, true>(cx, tw, SB, SC, 5, S, G);
+            }
+            cx.sync();
+        } else
+#endif
         if constexpr (SB >= 6) {
             // fixed schedule: SB = R0 + R1 + R2 with R0 = 4 on the global-facing first round
             constexpr int R0 = 4, R1 = (SB - 4 + 1) / 2, R2 = SB - 4 - R1;
@@ -786,8 +803,13 @@ struct Ntt {
             case 110310: dev->launch<StridedKernel2<11, 3, 10>, 256, STR_MINB>((unsigned)grid, 1, 256, smem, p); break;
             case 110312: dev->launch<StridedKernel2<11, 3, 12>, 256, STR_MINB>((unsigned)grid, 1, 256, smem, p); break;
             // 2^15-word tiles: one 1024-thread CTA per SM (512 threads: 6.85 ms, 1024: 6.58 ms for the po2 = 20 NTT stage)
+#if STR_R5
+            case 100510: dev->launch<StridedKernel2<10, 5, 10>, 512, 1>((unsigned)grid, 1, 512, smem, p); break;
+            case 100512: dev->launch<StridedKernel2<10, 5, 12>, 512, 1>((unsigned)grid, 1, 512, smem, p); break;
+#else
             case 100510: dev->launch<StridedKernel2<10, 5, 10>, 1024, 1>((unsigned)grid, 1, big_threads, smem, p); break;
             case 100512: dev->launch<StridedKernel2<10, 5, 12>, 1024, 1>((unsigned)grid, 1, big_threads, smem, p); break;
+#endif
             case 110410: dev->launch<StridedKernel2<11, 4, 10>, 1024, 1>((unsigned)grid, 1, big_threads, smem, p); break;
             case 110412: dev->launch<StridedKernel2<11, 4, 12>, 1024, 1>((unsigned)grid, 1, big_threads, smem, p); break;
             case 120310: dev->launch<StridedKernel2<12, 3, 10>, 1024, 1>((unsigned)grid, 1, big_threads, smem, p); break;
