@@ -384,15 +384,16 @@ struct StridedKernel2 {
         const GlobStridedIO<SA> G{src, dst, p.a};
         const SmemIO S{s};
 #if STR_R5
-        if constexpr (SB == 10) {
-            // 2^10 rows: two radix-32 rounds (ONE shared-memory round trip instead of two), 32 values per thread, 512 threads
-            // on the 2^15-word tile: 4.82 -> 4.71 ms per 192-column LDE against the 4+3+3 schedule with 1024 threads
+        if constexpr (SB >= 6 && SB <= 10 && SB != 8) {  // 2^8 rows: 4+2+2 levels measured faster (po2 = 18 NTT stage 1.71 against 1.76 ms)
+            // up to 2^10 rows: TWO rounds (one shared-memory round trip), radix up to 32 (32 values per thread, 124 registers).
+            // 2^10 rows, 512 threads on the 2^15-word tile: 4.82 -> 4.71 ms per 192-column LDE against 4+3+3 levels with 1024 threads
+            constexpr int R0 = (SB + 1) / 2, R1 = SB - R0;
             if (INV) {
-                round_t<5, true, SB, SC, 5, false, false, true>(cx, tw, SB, SC, 5, G, S); cx.sync();
-                round_t<5, true, SB, SC, 0, false, false, true>(cx, tw, SB, SC, 0, S, G);
+                round_t<R0, true, SB, SC, SB - R0, false, false, true>(cx, tw, SB, SC, SB - R0, G, S); cx.sync();
+                round_t<R1, true, SB, SC, 0, false, false, true>(cx, tw, SB, SC, 0, S, G);
             } else {
-                round_t<5, false, SB, SC, 0, false, false, true>(cx, tw, SB, SC, 0, G, S); cx.sync();
-                round_t<5, false, SB, SC, 5, false, false, true>(cx, tw, SB, SC, 5, S, G);
+                round_t<R0, false, SB, SC, 0, false, false, true>(cx, tw, SB, SC, 0, G, S); cx.sync();
+                round_t<R1, false, SB, SC, R0, false, false, true>(cx, tw, SB, SC, R0, S, G);
             }
             cx.sync();
         } else
