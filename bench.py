@@ -363,7 +363,7 @@ def main():
         wall_e = max(max_over_ranks(device_seconds()), host_wall_e)
         e2e_value = world * F * args.steps / wall_e
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(F * ((WIDTHS[0] + WIDTHS[1]) * N * 4 + 128 + 4 * WIDTHS[2])),
-               "d2h_bytes_per_step": int(F * len(seal_h[0]) * 4), "ms_per_step": wall_e * 1e3 / args.steps, "host_wall_ms_per_step": host_wall_e * 1e3 / args.steps, "ms_h2d_exposed_per_segment": h2d_ms[0] / args.steps,
+               "d2h_bytes_per_step": int(F * len(seal_h[0]) * 4), "ms_per_step": wall_e * 1e3 / args.steps, "host_wall_ms_per_step": host_wall_e * 1e3 / args.steps, "ms_code_h2d_span_per_segment": h2d_ms[0] / args.steps, "h2d_note": "span of the code-column copy on context 0's stream (it queues behind the other contexts' data copies on the copy engine; those contexts keep the SMs busy meanwhile)",
                "camt53_proof_seconds": CAMT53_SEGMENTS / e2e_value, "host_memory": "pinned (hfb200_host_alloc)"}
         # ---------------- the same e2e call with the control group kept on the device (opt-in, informational) ----------------
         # The control (code) columns depend on (circuit, po2) only; hfb200_control_root commits them once and segments then
