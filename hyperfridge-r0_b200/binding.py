@@ -56,7 +56,7 @@ class SegmentJob(C.Structure):
 
 def load_library(path=None):
     """dlopen the product library.  Raises Hfb200Error when it has not been built (no fallback)."""
-    path = path or LIB_PATH
+    path = path or os.environ.get("HFB200_LIB") or LIB_PATH  # HFB200_LIB: another build of the same library (kernel experiments)
     if not os.path.exists(path):
         raise Hfb200Error("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(the prover has no CPU fallback)" % path)

@@ -86,7 +86,10 @@ struct Prover {
     cudaEvent_t evs[N_EV] = {};
     // host->device staging of the data columns runs on its own stream in H2D_CHUNKS column slices; the LDE of a slice
     // starts as soon as its copy has landed, so the PCIe transfer hides behind the code commit and the data NTTs
-    static constexpr int H2D_CHUNKS = 4;
+#ifndef HFB200_H2D_CHUNKS
+#define HFB200_H2D_CHUNKS 4
+#endif
+    static constexpr int H2D_CHUNKS = HFB200_H2D_CHUNKS;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_ev[H2D_CHUNKS] = {};
     cudaEvent_t copy_gate = nullptr;
