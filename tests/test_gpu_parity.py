@@ -120,6 +120,64 @@ def test_golden_fixture(pkg, gpu_lib, monkeypatch):
             assert cps[k].tolist() == v, k
 
 
+def _check_against_pins(orc, gold, seal, cps):
+    for k, v in gold["checkpoints"].items():
+        assert cps[k].tolist() == v, "checkpoint %s differs from the pinned oracle value" % k
+    assert len(seal) == gold["seal_words"]
+    assert seal[:64].tolist() == gold["seal_head"] and seal[-64:].tolist() == gold["seal_tail"]
+    assert int(seal.astype(np.uint64).sum()) == gold["seal_sum_u64"]
+    assert orc.hash_elems(seal % orc.P).tolist() == gold["seal_hash"]
+
+
+def _load_pins(po2):
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "golden_po2_%d_w256.json" % po2)))
+
+
+def test_headline_po2_20_w256_bit_exact_pinned(pkg, gpu_lib, orc, monkeypatch):
+    """BASELINE.json configs[1] at its largest size, the exact shape bench.py times (W = 256, po2 = 20: 192-column
+    chunked H2D, 12-permutation leaves, the 2^10 x 2^10 NTT plan): every transcript checkpoint, the seal's hash, length,
+    head and tail against the pins generated from the CPU oracle (tests/golden/make_golden_large.py, 131 s on 8
+    threads) -- resident path, host-buffer path through hfb200_prove_segment, and FOUR contexts in flight on one GPU
+    (bench.py's configuration), all against the same pins."""
+    import threading
+    monkeypatch.setenv("HFB200_DEBUG_CHECKPOINTS", "1")
+    gold = _load_pins(20)
+    po2, W = gold["po2"], tuple(gold["widths"])
+    with pkg.Context(0, po2, W, lib=gpu_lib) as c:
+        g = c.witgen_synth(po2, gold["trace_seed"], gold["blind_seed"])
+        seal = c.prove_resident(gold["blind_seed"])
+        _check_against_pins(orc, gold, seal, c.checkpoints())
+        code, data = c.read_group(1), c.read_group(2)
+        seal_host = c.prove_segment(po2, g, code, data, gold["blind_seed"])     # host buffers, chunked H2D
+        _check_against_pins(orc, gold, seal_host, c.checkpoints())
+    ctxs = [pkg.Context(0, po2, W, lib=gpu_lib) for _ in range(4)]
+    out = [None] * 4
+
+    def work(k):
+        for _ in range(2):
+            out[k] = ctxs[k].prove_segment(po2, g, code, data, gold["blind_seed"])
+    th = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for k in range(4):
+        _check_against_pins(orc, gold, out[k], ctxs[k].checkpoints())
+    [c.close() for c in ctxs]
+
+
+def test_headline_po2_20_w256_bit_exact_live_oracle(pkg, gpu_lib, orc):
+    """The same comparison against a LIVE oracle run (about two minutes of host time on 8-16 threads), so the pin file
+    itself cannot go stale unnoticed: whole seal, word for word."""
+    cir, g, code, data = make_segment(orc, DEFAULT, 20)
+    oseal, ocps, _ = cir.prove(20, g, code, data, 1)
+    with pkg.Context(0, 20, DEFAULT, lib=gpu_lib) as c:
+        seal = c.prove_segment(20, g, code, data, 1)
+        assert len(seal) == len(oseal) and (seal == oseal).all()
+        cps = c.checkpoints()
+        for k, v in ocps.items():
+            if k in cps:
+                assert (cps[k] == v).all(), k
+
+
 def test_tampered_gpu_seal_rejected(pkg, gpu_lib, orc):
     with pkg.Context(0, 12, SMALL, lib=gpu_lib) as c:
         c.witgen_synth(12, TRACE_SEED, 1)
@@ -172,6 +230,17 @@ def test_po2_22_large_segment(pkg, gpu_lib, orc):
         x = rand_elems(np.random.default_rng(2222), (2, 1 << po2))
         x[1, ::7] = np.uint32(P - 1)
         assert (c.op_lde(x) == orc.expand_ntt(orc.zk_shift(orc.interpolate_ntt(x)), 2)).all()
+
+
+def test_po2_22_w256_bit_exact_pinned(pkg, gpu_lib, orc, monkeypatch):
+    """configs[4]: the po2 = 22, W = 256 seal against pins generated from the CPU oracle (make_golden_large.py)."""
+    monkeypatch.setenv("HFB200_DEBUG_CHECKPOINTS", "1")
+    gold = _load_pins(22)
+    po2, W = gold["po2"], tuple(gold["widths"])
+    with pkg.Context(0, po2, W, lib=gpu_lib) as c:
+        c.witgen_synth(po2, gold["trace_seed"], gold["blind_seed"])
+        seal = c.prove_resident(gold["blind_seed"])
+        _check_against_pins(orc, gold, seal, c.checkpoints())
 
 
 def test_pool_and_concurrent_contexts_on_gpu(pkg, gpu_lib, orc):
