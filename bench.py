@@ -161,13 +161,13 @@ def camt53_leg(pkg, ctx, device, po2, inflight, g, code_h, data_h, rank=0, world
     cap = ctx.seal_words(po2)
     gathered = None
     with pkg.default_prover(opts) as prover:
-        warm = prover.prove(pkg.Session(segs[:inflight], journal_text), seal_cap=cap)  # warm-up: one segment per worker
+        warm = prover.prove(pkg.Session(segs[:inflight], journal_text), seal_cap=cap, n_total=CAMT53_SEGMENTS)  # warm-up: one segment per worker
         if dist is not None:
             tmp = [None] * world if rank == 0 else None
             dist.gather_object([np.asarray(s.seal)[:8] for s in warm.receipt.inner.segments], tmp, dst=0)  # warm the gather path
             barrier()
         t0 = time.perf_counter()
-        info = prover.prove(pkg.Session(segs, journal_text), seal_cap=cap)
+        info = prover.prove(pkg.Session(segs, journal_text), seal_cap=cap, n_total=CAMT53_SEGMENTS)
         if dist is not None:
             gathered = [None] * world if rank == 0 else None
             dist.gather_object([(s.index, np.asarray(s.seal, dtype=np.uint32)) for s in info.receipt.inner.segments], gathered, dst=0)
@@ -187,7 +187,7 @@ def camt53_leg(pkg, ctx, device, po2, inflight, g, code_h, data_h, rank=0, world
     json_s = time.perf_counter() - t0
     control_id = ctx.control_root(po2, code_h)
     t0 = time.perf_counter()
-    receipt.verify({po2: control_id}, circuit=WIDTHS)
+    receipt.verify(pkg.default_image_id(), {po2: control_id}, circuit=WIDTHS)  # seals + claim chain (image id, state chain, journal digest)
     verify_s = time.perf_counter() - t0
     ok = receipt.journal.bytes_ == journal_bytes and [s.index for s in receipt.inner.segments] == list(range(CAMT53_SEGMENTS))
     if not ok:

@@ -22,8 +22,20 @@ EXPORTS = [
     "hfb200_total_launches", "hfb200_op_interpolate_ntt", "hfb200_op_expand_ntt", "hfb200_op_lde", "hfb200_op_merkle",
     "hfb200_op_poseidon2", "hfb200_op_fri_fold", "hfb200_bench_lde", "hfb200_bench_merkle", "hfb200_bench_modmul",
     "hfb200_mark", "hfb200_mark_elapsed",
-    "hfb200_pool_create", "hfb200_pool_load_control", "hfb200_pool_prove", "hfb200_pool_destroy",
+    "hfb200_pool_create", "hfb200_pool_create_ir", "hfb200_pool_load_control", "hfb200_pool_prove", "hfb200_pool_destroy",
+    "hfb200_set_blinding", "hfb200_pool_set_blinding", "hfb200_pool_stats", "hfb200_pool_inject_fault",
+    "hfb200_digest_bytes", "hfb200_digest_pair", "hfb200_claim_encode", "hfb200_claim_decode", "hfb200_claim_next_state", "hfb200_verify_claims",
 ]
+
+BLIND_OS_ENTROPY, BLIND_DETERMINISTIC = 0, 1
+
+
+def _default_blinding(deterministic):
+    """The C ABI's default is OS entropy (zero-knowledge).  The parity tests and the bench need reproducible seals: they ask for
+    the deterministic mode explicitly, or through HFB200_DETERMINISTIC_BLINDING=1 (set by tests/conftest.py and bench.py)."""
+    if deterministic is None:
+        deterministic = os.environ.get("HFB200_DETERMINISTIC_BLINDING", "0") == "1"
+    return BLIND_DETERMINISTIC if deterministic else BLIND_OS_ENTROPY
 
 
 class Hfb200Error(RuntimeError):
@@ -51,7 +63,26 @@ class CircuitIR(C.Structure):
 class SegmentJob(C.Structure):
     _fields_ = [("po2", C.c_uint32), ("globals", C.c_void_p), ("code", C.c_void_p), ("data", C.c_void_p), ("blind_seed", C.c_uint64),
                 ("seal_out", C.c_void_p), ("seal_cap", C.c_size_t), ("seal_words", C.c_size_t), ("error", C.c_void_p),
-                ("device", C.c_int), ("ms", C.c_float)]
+                ("device", C.c_int), ("ms", C.c_float), ("attempts", C.c_int)]
+
+
+class Claim(C.Structure):
+    """hfb200_claim: what upstream's ReceiptClaim boils down to on this path (pre / post state, exit code, output digest)."""
+    _fields_ = [("pre", C.c_uint32 * 8), ("post", C.c_uint32 * 8), ("output", C.c_uint32 * 8), ("exit_code", C.c_uint32)]
+
+    def to_obj(self):
+        return {"pre": list(self.pre), "post": list(self.post), "exit_code": "SystemSplit" if self.exit_code else "Halted", "output": list(self.output)}
+
+
+EXIT_HALTED, EXIT_SYSTEM_SPLIT = 0, 1
+
+
+class PoolStats(C.Structure):
+    _fields_ = [("contexts", C.c_size_t), ("contexts_retired", C.c_size_t), ("faults", C.c_uint64), ("retries", C.c_uint64),
+                ("contexts_recreated", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 def load_library(path=None):
@@ -100,6 +131,17 @@ def load_library(path=None):
         "hfb200_pool_prove": (err, [vp, C.POINTER(SegmentJob), sz]),
         "hfb200_pool_load_control": (err, [vp, u32, vp]),
         "hfb200_pool_destroy": (None, [vp]),
+        "hfb200_pool_create_ir": (err, [C.POINTER(C.c_int), C.c_int, C.c_int, u32, C.POINTER(CircuitIR), C.POINTER(vp)]),
+        "hfb200_set_blinding": (err, [vp, C.c_int]),
+        "hfb200_pool_set_blinding": (err, [vp, C.c_int]),
+        "hfb200_pool_stats": (err, [vp, C.POINTER(PoolStats)]),
+        "hfb200_pool_inject_fault": (err, [vp, sz, u64, C.c_int]),
+        "hfb200_digest_bytes": (err, [C.c_char_p, sz, vp]),
+        "hfb200_digest_pair": (err, [vp, vp, vp]),
+        "hfb200_claim_encode": (err, [C.POINTER(Claim), vp]),
+        "hfb200_claim_decode": (err, [vp, sz, C.POINTER(Claim)]),
+        "hfb200_claim_next_state": (err, [vp, u32, u32, vp]),
+        "hfb200_verify_claims": (err, [C.POINTER(vp), C.POINTER(sz), sz, vp, C.c_char_p, sz]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -124,8 +166,10 @@ CHECKPOINT_NAMES = ["globals_hash", "code_root", "data_root", "accum_mix", "accu
 class Context:
     """One hfb200_ctx: one host thread <-> one GPU.  Mirrors upstream's `segment_prover(hashfn)` object."""
 
-    def __init__(self, device=0, max_po2=20, circuit=(16, 192, 48), lib=None, ir=None):
-        """`ir`: optional data-defined circuit {"taps": u32[n,3], "steps": u32[m,4], "ret": int, "n_mix": int} (hfb200_init_ir)."""
+    def __init__(self, device=0, max_po2=20, circuit=(16, 192, 48), lib=None, ir=None, deterministic=None):
+        """`ir`: optional data-defined circuit {"taps": u32[n,3], "steps": u32[m,4], "ret": int, "n_mix": int} (hfb200_init_ir).
+        `deterministic`: blinding derived from the blind_seed arguments alone (tests / bench); default = OS entropy unless
+        HFB200_DETERMINISTIC_BLINDING=1."""
         self.lib = lib or load_library()
         self.circuit = tuple(int(x) for x in circuit)
         self.max_po2 = max_po2
@@ -141,6 +185,10 @@ class Context:
             desc = CircuitDesc(self.circuit[0], self.circuit[1], self.circuit[2], 0)
             self._check(self.lib.hfb200_init(device, max_po2, C.byref(desc), C.byref(h)))
         self._h = h
+        self.set_blinding(_default_blinding(deterministic))
+
+    def set_blinding(self, mode):
+        self._check(self.lib.hfb200_set_blinding(self._h, int(mode)))
 
     def _check(self, e):
         if e:
@@ -363,6 +411,69 @@ def verify_segment(seal, code_root, circuit=(16, 192, 48), ir=None, lib=None):
     return po2.value
 
 
+def _raise_err(lib, e):
+    if e:
+        msg = C.cast(e, C.c_char_p).value.decode(errors="replace")
+        lib.hfb200_free_error(e)
+        raise Hfb200Error(msg)
+
+
+def digest_bytes(data, lib=None):
+    """Poseidon2 digest of a byte string (hfb200_digest_bytes): the journal digest of this path's claims."""
+    lib = lib or load_library()
+    out = np.zeros(8, np.uint32)
+    data = bytes(data)
+    _raise_err(lib, lib.hfb200_digest_bytes(data, len(data), _ptr(out)))
+    return out
+
+
+def digest_pair(a, b, lib=None):
+    lib = lib or load_library()
+    a, b, out = _u32(a), _u32(b), np.zeros(8, np.uint32)
+    _raise_err(lib, lib.hfb200_digest_pair(_ptr(a), _ptr(b), _ptr(out)))
+    return out
+
+
+def claim_next_state(pre, index, po2, lib=None):
+    lib = lib or load_library()
+    pre, out = _u32(pre), np.zeros(8, np.uint32)
+    _raise_err(lib, lib.hfb200_claim_next_state(_ptr(pre), index, po2, _ptr(out)))
+    return out
+
+
+def claim_encode(globals_, pre, post, exit_code, output, lib=None):
+    """Returns a copy of the 32 globals with the claim words written (hfb200_claim_encode)."""
+    lib = lib or load_library()
+    g = _u32(globals_).copy()
+    c = Claim()
+    c.pre[:] = [int(x) for x in pre]; c.post[:] = [int(x) for x in post]; c.output[:] = [int(x) for x in output]
+    c.exit_code = int(exit_code)
+    _raise_err(lib, lib.hfb200_claim_encode(C.byref(c), _ptr(g)))
+    return g
+
+
+def claim_decode(seal, lib=None):
+    lib = lib or load_library()
+    seal = _u32(seal)
+    c = Claim()
+    _raise_err(lib, lib.hfb200_claim_decode(_ptr(seal), seal.size, C.byref(c)))
+    return c
+
+
+def verify_claims(seals, image_id, journal_bytes, lib=None):
+    """The claim chain of `receipt.verify(image_id)` over seals in segment order (hfb200_verify_claims)."""
+    lib = lib or load_library()
+    seals = [_u32(s) for s in seals]
+    n = len(seals)
+    ptrs = (C.c_void_p * n)(*[s.ctypes.data for s in seals])
+    lens = (C.c_size_t * n)(*[s.size for s in seals])
+    image_id = _u32(image_id)
+    if image_id.size != 8:
+        raise Hfb200Error("verify_claims: image id must have 8 words")
+    journal_bytes = bytes(journal_bytes)
+    _raise_err(lib, lib.hfb200_verify_claims(ptrs, lens, n, _ptr(image_id), journal_bytes, len(journal_bytes)))
+
+
 def ir_source(ir, circuit, lib=None):
     """CUDA source that hfb200_init_ir compiles for the eval_check of a data-defined circuit (needs no device)."""
     lib = lib or load_library()
@@ -383,17 +494,34 @@ class Pool:
     """hfb200_pool: worker contexts on several GPUs fed from one queue of independent segments (no collectives).
     Mirrors the segment loop of upstream's `ProverImpl::prove_session`."""
 
-    def __init__(self, devices=(0,), contexts_per_device=1, max_po2=20, circuit=(16, 192, 48), lib=None):
+    def __init__(self, devices=(0,), contexts_per_device=1, max_po2=20, circuit=(16, 192, 48), lib=None, ir=None, deterministic=None):
         self.lib = lib or load_library()
         self.circuit = tuple(int(x) for x in circuit)
-        desc = CircuitDesc(self.circuit[0], self.circuit[1], self.circuit[2], 0)
         devs = (C.c_int * len(devices))(*devices)
         h = C.c_void_p()
         self._h = None
-        e = self.lib.hfb200_pool_create(devs, len(devices), contexts_per_device, max_po2, C.byref(desc), C.byref(h))
+        if ir is not None:
+            taps, steps = _u32(ir["taps"]), _u32(ir["steps"])
+            desc = CircuitIR(self.circuit[0], self.circuit[1], self.circuit[2], int(ir["n_mix"]), taps.ctypes.data, taps.size // 3,
+                             steps.ctypes.data, steps.size // 4, int(ir["ret"]))
+            e = self.lib.hfb200_pool_create_ir(devs, len(devices), contexts_per_device, max_po2, C.byref(desc), C.byref(h))
+        else:
+            desc = CircuitDesc(self.circuit[0], self.circuit[1], self.circuit[2], 0)
+            e = self.lib.hfb200_pool_create(devs, len(devices), contexts_per_device, max_po2, C.byref(desc), C.byref(h))
         self._raise(e)
         self._h = h
         self.workers = len(devices) * contexts_per_device
+        self._raise(self.lib.hfb200_pool_set_blinding(self._h, _default_blinding(deterministic)))
+        self.last_attempts = []
+
+    def stats(self):
+        st = PoolStats()
+        self._raise(self.lib.hfb200_pool_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def inject_fault(self, worker, after_jobs=0, kind=0):
+        """Test hook (hfb200_pool_inject_fault): kind 0 = device fault (context re-created, job re-queued), 1 = plain failure."""
+        self._raise(self.lib.hfb200_pool_inject_fault(self._h, worker, after_jobs, kind))
 
     def _raise(self, e):
         if e:
@@ -426,9 +554,11 @@ class Pool:
         self._control[po2] = code  # keeps the buffer alive: the library holds the pointer
         self._raise(self.lib.hfb200_pool_load_control(self._h, po2, _ptr(code)))
 
-    def prove(self, jobs, seal_cap):
+    def prove(self, jobs, seal_cap, return_errors=False):
         """jobs: list of (po2, globals, code, data, blind_seed) with numpy u32 arrays (code may be None after load_control).
-        Returns (seals, devices, ms)."""
+        Returns (seals, devices, ms); raises on the first failed job unless return_errors=True, in which case the result is
+        (seals, devices, ms, errors) with errors[i] = None or the job's message (failed jobs have an empty seal; the others are
+        proved regardless, like the reference's batch tooling sets failed inputs aside)."""
         n = len(jobs)
         arr = (SegmentJob * n)()
         keep = []
@@ -436,17 +566,28 @@ class Pool:
         for i, (po2, g, code, data, seed) in enumerate(jobs):
             g, data = _u32(g), _u32(data)
             code = _u32(code) if code is not None else None
+            rows = 1 << po2
+            if g.size != N_GLOBAL or data.size != self.circuit[1] * rows or (code is not None and code.size != self.circuit[0] * rows):
+                raise Hfb200Error("pool.prove: job %d: trace shape does not match (circuit, po2)" % i)
             keep.append((g, code, data))
             arr[i].po2, arr[i].blind_seed = po2, seed
             arr[i].globals, arr[i].code, arr[i].data = g.ctypes.data, (code.ctypes.data if code is not None else None), data.ctypes.data
             arr[i].seal_out, arr[i].seal_cap = seals[i].ctypes.data, seal_cap
         e = self.lib.hfb200_pool_prove(self._h, arr, n)
-        errs = []
+        errs = [None] * n
         for i in range(n):
             if arr[i].error:
-                errs.append(C.cast(arr[i].error, C.c_char_p).value.decode(errors="replace"))
+                errs[i] = C.cast(arr[i].error, C.c_char_p).value.decode(errors="replace")
                 self.lib.hfb200_free_error(arr[i].error)
+        self.last_attempts = [arr[i].attempts for i in range(n)]
+        out = ([seals[i][:arr[i].seal_words] if errs[i] is None else seals[i][:0] for i in range(n)], [arr[i].device for i in range(n)],
+               [arr[i].ms for i in range(n)])
+        if return_errors:
+            if e:
+                self.lib.hfb200_free_error(e)
+            return out + (errs,)
         self._raise(e)
-        if errs:
-            raise Hfb200Error(errs[0])
-        return [seals[i][:arr[i].seal_words] for i in range(n)], [arr[i].device for i in range(n)], [arr[i].ms for i in range(n)]
+        first = [m for m in errs if m is not None]
+        if first:
+            raise Hfb200Error(first[0])
+        return out

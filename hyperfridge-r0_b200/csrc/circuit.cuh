@@ -13,6 +13,7 @@
 #pragma once
 #include <algorithm>
 #include "dev.cuh"
+#include "blind.cuh"
 
 namespace hf {
 
@@ -29,17 +30,6 @@ HD uint64_t splitmix64(uint64_t z) {
 HD uint32_t synth_value(uint64_t seed, uint32_t col, uint32_t row) {
     return to_mont((uint32_t)(splitmix64(seed ^ (((uint64_t)col << 32) | row)) % P));
 }
-HD uint32_t blind_value(uint64_t seed, uint32_t group, uint32_t col, uint32_t row) {
-    const uint64_t key = splitmix64(seed ^ 0x6E6F697365ull) ^ ((uint64_t)group << 60) ^ ((uint64_t)col << 32) ^ row;
-    uint64_t v = 0;
-    for (int i = 0; i < 3; i++) {
-        const uint64_t d = splitmix64(key + (uint64_t)i * 0xD1342543DE82EF95ull);
-        v = ((v << 32) + (uint32_t)d) % P;
-        v = ((v << 32) + (uint32_t)(d >> 32)) % P;
-    }
-    return to_mont((uint32_t)v);
-}
-
 struct CircuitDev {
     uint32_t w_code, w_data, w_accum, n_free, n_prev, n_chains;
     const uint16_t* picks;      // [n_free][6] : a, b, c, d, p, x   (device memory)
@@ -77,12 +67,12 @@ struct GenCodeKernel {
 };
 struct GenFreeKernel {  // free columns (active rows) + blinding rows of every data column
     static constexpr bool kBarrier = false;
-    HD static void run(const KCtx& cx, uint32_t*, uint32_t* data, CircuitDev cd, uint32_t po2, uint64_t trace_seed, uint64_t blind_seed, uint32_t global0) {
+    HD static void run(const KCtx& cx, uint32_t*, uint32_t* data, CircuitDev cd, uint32_t po2, uint64_t trace_seed, BlindKey blind, uint32_t global0) {
         const uint64_t n = 1ull << po2, act = n - ZK_CYCLES;
         const uint64_t t = (uint64_t)cx.bx * cx.nt + cx.tid;
         if (t >= (uint64_t)cd.w_data * n) return;
         const uint32_t c = (uint32_t)(t >> po2), r = (uint32_t)(t & (n - 1));
-        if (r >= act) data[t] = blind_value(blind_seed, GROUP_DATA, c, r);
+        if (r >= act) data[t] = blind_value(blind, GROUP_DATA, c, r);
         else if (c < cd.n_free) data[t] = (c == 0 && r == 0) ? global0 : synth_value(trace_seed, c, r);
     }
 };
@@ -119,7 +109,7 @@ static constexpr uint32_t ACC_ITEMS = 256, ACC_PER = 8, ACC_RPB = ACC_ITEMS * AC
 // mode 1: read the exclusive block offset from partial[...] and write the running products (+ blinding rows)
 struct AccumKernel {
     static constexpr bool kBarrier = true;
-    HD static void run(const KCtx& cx, uint32_t* sm, uint32_t* accum, const uint32_t* data, const uint32_t* mix, E4* partial, CircuitDev cd, uint32_t po2, uint64_t blind_seed, int mode) {
+    HD static void run(const KCtx& cx, uint32_t* sm, uint32_t* accum, const uint32_t* data, const uint32_t* mix, E4* partial, CircuitDev cd, uint32_t po2, BlindKey blind, int mode) {
         const uint64_t n = 1ull << po2, act = n - ZK_CYCLES;
         const uint32_t chain = cx.by, blk = cx.bx, nblk = cx.gx;
         const uint32_t* src = data + (uint64_t)cd.chain_src[chain] * n;
@@ -151,7 +141,7 @@ struct AccumKernel {
                     E4 t = m; t.c[0] = fadd(t.c[0], src[r]); pr = e4_mul(pr, t);
                     for (int k = 0; k < 4; k++) accum[(uint64_t)(4 * chain + k) * n + r] = pr.c[k];
                 } else {
-                    for (int k = 0; k < 4; k++) accum[(uint64_t)(4 * chain + k) * n + r] = blind_value(blind_seed, GROUP_ACCUM, 4 * chain + k, (uint32_t)r);
+                    for (int k = 0; k < 4; k++) accum[(uint64_t)(4 * chain + k) * n + r] = blind_value(blind, GROUP_ACCUM, 4 * chain + k, (uint32_t)r);
                 }
             }
         }

@@ -5,6 +5,8 @@
 #include "verify.cuh"
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <map>
 #include <memory>
 #include <thread>
@@ -19,9 +21,11 @@ struct hfb200_ctx {
 #endif
 };
 
+// the one message that is NOT malloc'd (returned when malloc itself fails); hfb200_free_error recognises it by address
+static const char kOomMessage[] = "hfb200: out of memory while reporting an error";
 static const char* dup_err(const std::string& s) {
     char* m = (char*)std::malloc(s.size() + 1);
-    if (!m) return "hfb200: out of memory while reporting an error";
+    if (!m) return kOomMessage;
     std::memcpy(m, s.c_str(), s.size() + 1);
     return m;
 }
@@ -45,7 +49,7 @@ const char* hfb200_version(void) {
 #endif
 }
 
-void hfb200_free_error(const char* msg) { std::free((void*)msg); }
+void hfb200_free_error(const char* msg) { if (msg && msg != kOomMessage) std::free((void*)msg); }
 
 const char* hfb200_init(int device, uint32_t max_po2, const hfb200_circuit_desc* c, hfb200_ctx** out) {
     API_TRY
@@ -95,8 +99,19 @@ void hfb200_destroy(hfb200_ctx* ctx) {
     delete ctx;
 }
 
+const char* hfb200_set_blinding(hfb200_ctx* ctx, int mode) {
+    API_TRY
+    if (!ctx) throw Err("hfb200_set_blinding: NULL ctx");
+    if (mode != BLIND_OS_ENTROPY && mode != BLIND_DETERMINISTIC) throw Err("hfb200_set_blinding: mode must be HFB200_BLIND_OS_ENTROPY or HFB200_BLIND_DETERMINISTIC");
+    if (ctx->p.begun) throw Err("hfb200_set_blinding: a segment is in flight");
+    ctx->p.blind_mode = mode;
+    API_CATCH
+}
+
 const char* hfb200_host_alloc(size_t bytes, void** out) {
     API_TRY
+    if (!out) throw Err("hfb200_host_alloc: out is NULL");
+    *out = nullptr;
 #ifndef HFB200_EMU
     CUDA_CHECK(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
 #else
@@ -116,7 +131,6 @@ const char* hfb200_prove_segment(hfb200_ctx* ctx, uint32_t po2, const uint32_t* 
                                  uint64_t blind_seed, uint32_t* seal_out, size_t seal_cap, size_t* seal_words) {
     API_TRY
     if (!ctx || !globals || !data) throw Err("hfb200_prove_segment: NULL argument");
-    if (!code && !ctx->p.control_cached) throw Err("hfb200_prove_segment: code is NULL and no control group is loaded (hfb200_control_root)");
     ctx->p.begin(po2, globals, code, data, blind_seed);
     ctx->p.finish(nullptr, ctx->seal);
     if (const char* e = emit_seal(ctx, seal_out, seal_cap, seal_words)) return e;
@@ -199,11 +213,64 @@ uint64_t hfb200_total_launches(const hfb200_ctx* ctx) { return ctx ? ctx->p.dev.
 
 // ---- multi-GPU pool ---------------------------------------------------------------------------------
 } // extern "C"
+// Replaces the (sequential) segment loop of upstream's `ProverImpl::prove_session`.  Failure behaviour follows the reference's
+// batch tooling (/root/reference/data/watchdog.sh:58-83: a failed input is set aside, the rest continue) and its prover call
+// site (/root/reference/host/src/main.rs:327-330: the error is surfaced, not swallowed):
+//   * an argument / shape error fails that job only; it is never retried;
+//   * a CUDA error poisons the context that saw it: the context is destroyed and re-created (the device is retired for this
+//     pool if that fails), and the job goes back to the queue for any healthy worker, at most HFB200_POOL_MAX_ATTEMPTS times;
+//   * jobs left when no healthy context remains fail with that reason.
+static constexpr int HFB200_POOL_MAX_ATTEMPTS = 3;
 struct hfb200_pool {
-    std::vector<std::unique_ptr<hfb200_ctx>> ctxs;
-    std::vector<int> device_of;
-    std::map<uint32_t, const uint32_t*> control;  // po2 -> caller-owned control columns (hfb200_pool_load_control)
+    struct Slot { hfb200_ctx* ctx = nullptr; int device = 0; bool retired = false; uint64_t faults = 0; };
+    std::vector<Slot> slots;
+    struct Control { const uint32_t* code; uint64_t gen; };
+    std::map<uint32_t, Control> control;  // po2 -> caller-owned control columns + the load that installed them
+    uint64_t next_gen = 1;
+    // what is needed to re-create a context after a fault
+    uint32_t max_po2 = 0;
+    hfb200_circuit_desc desc{};
+    bool is_ir = false;
+    std::vector<IrTap> ir_taps; std::vector<IrStep> ir_steps; uint32_t ir_ret = 0, ir_n_mix = 0;
+    int blind_mode = BLIND_OS_ENTROPY;
+    // test hook (hfb200_pool_inject_fault): worker `w` reports a CUDA error instead of proving its n-th job from now
+    std::mutex inject_mu;
+    std::map<size_t, std::pair<uint64_t, int>> inject;  // worker -> (jobs to let pass, kind)
+    uint64_t total_faults = 0, total_retries = 0, contexts_recreated = 0;
+
+    hfb200_ctx* make_ctx(int device) const {
+        hfb200_ctx* ctx = new hfb200_ctx();
+        try {
+            if (is_ir) ctx->p.init(device, max_po2, desc.w_code, desc.w_data, desc.w_accum, ir_taps.data(), ir_taps.size(), ir_steps.data(), ir_steps.size(), ir_ret, ir_n_mix);
+            else ctx->p.init(device, max_po2, desc.w_code, desc.w_data, desc.w_accum);
+            ctx->p.blind_mode = blind_mode;
+        } catch (...) { try { ctx->p.destroy(); } catch (...) {} delete ctx; throw; }
+        return ctx;
+    }
+    void drop_ctx(Slot& sl) {
+        if (!sl.ctx) return;
+#ifndef HFB200_EMU
+        cudaSetDevice(sl.device);
+#endif
+        hfb200_destroy(sl.ctx);
+        sl.ctx = nullptr;
+    }
+    ~hfb200_pool() { for (auto& sl : slots) drop_ctx(sl); }
 };
+
+static void pool_fill(hfb200_pool* pool, const int* devices, int n_devices, int contexts_per_device) {
+    // contexts are created up front, serially (cudaSetDevice is per thread); on failure the pool's destructor releases the
+    // contexts already made (arenas, streams, events)
+    for (int i = 0; i < n_devices; i++)
+        for (int s_ = 0; s_ < contexts_per_device; s_++) {
+            hfb200_pool::Slot sl;
+            sl.device = devices[i];
+            sl.ctx = pool->make_ctx(devices[i]);
+            pool->slots.push_back(sl);
+        }
+}
+static bool is_device_fault(const char* msg) { return msg && std::strncmp(msg, "CUDA error", 10) == 0; }
+static const char* control_root_impl(hfb200_ctx* ctx, uint32_t po2, const uint32_t* code, uint32_t* root_out, uint64_t gen);
 extern "C" {
 
 const char* hfb200_pool_create(const int* devices, int n_devices, int contexts_per_device, uint32_t max_po2,
@@ -211,17 +278,53 @@ const char* hfb200_pool_create(const int* devices, int n_devices, int contexts_p
     API_TRY
     if (!out || !devices || n_devices <= 0 || contexts_per_device <= 0) throw Err("hfb200_pool_create: bad argument");
     *out = nullptr;
-    hfb200_circuit_desc d = c ? *c : hfb200_circuit_desc{16, 192, 48, 0};
     std::unique_ptr<hfb200_pool> pool(new hfb200_pool());
-    // contexts are created on their worker threads' devices up front (cudaSetDevice is per thread, init is serial here)
-    for (int i = 0; i < n_devices; i++)
-        for (int s_ = 0; s_ < contexts_per_device; s_++) {
-            std::unique_ptr<hfb200_ctx> ctx(new hfb200_ctx());
-            ctx->p.init(devices[i], max_po2, d.w_code, d.w_data, d.w_accum);
-            pool->ctxs.push_back(std::move(ctx));
-            pool->device_of.push_back(devices[i]);
-        }
+    pool->desc = c ? *c : hfb200_circuit_desc{16, 192, 48, 0};
+    pool->max_po2 = max_po2;
+    pool_fill(pool.get(), devices, n_devices, contexts_per_device);
     *out = pool.release();
+    API_CATCH
+}
+const char* hfb200_pool_create_ir(const int* devices, int n_devices, int contexts_per_device, uint32_t max_po2,
+                                  const hfb200_circuit_ir* c, hfb200_pool** out) {
+    API_TRY
+    if (!out || !devices || !c || n_devices <= 0 || contexts_per_device <= 0) throw Err("hfb200_pool_create_ir: bad argument");
+    *out = nullptr;
+    std::unique_ptr<hfb200_pool> pool(new hfb200_pool());
+    pool->desc = hfb200_circuit_desc{c->w_code, c->w_data, c->w_accum, 0};
+    pool->max_po2 = max_po2;
+    pool->is_ir = true;
+    const IrTap* t = reinterpret_cast<const IrTap*>(c->taps);
+    const IrStep* st = reinterpret_cast<const IrStep*>(c->steps);
+    pool->ir_taps.assign(t, t + c->n_taps);
+    pool->ir_steps.assign(st, st + c->n_steps);
+    pool->ir_ret = c->ret; pool->ir_n_mix = c->n_mix;
+    pool_fill(pool.get(), devices, n_devices, contexts_per_device);
+    *out = pool.release();
+    API_CATCH
+}
+const char* hfb200_pool_set_blinding(hfb200_pool* pool, int mode) {
+    API_TRY
+    if (!pool) throw Err("hfb200_pool_set_blinding: NULL pool");
+    if (mode != BLIND_OS_ENTROPY && mode != BLIND_DETERMINISTIC) throw Err("hfb200_pool_set_blinding: bad mode");
+    pool->blind_mode = mode;
+    for (auto& sl : pool->slots) if (sl.ctx) sl.ctx->p.blind_mode = mode;
+    API_CATCH
+}
+const char* hfb200_pool_inject_fault(hfb200_pool* pool, size_t worker, uint64_t after_jobs, int kind) {
+    API_TRY
+    if (!pool || worker >= pool->slots.size() || kind < 0 || kind > 1) throw Err("hfb200_pool_inject_fault: bad argument");
+    std::lock_guard<std::mutex> lock(pool->inject_mu);
+    pool->inject[worker] = std::make_pair(after_jobs, kind);
+    API_CATCH
+}
+const char* hfb200_pool_stats(const hfb200_pool* pool, hfb200_pool_stats_t* out) {
+    API_TRY
+    if (!pool || !out) throw Err("hfb200_pool_stats: NULL argument");
+    out->contexts = pool->slots.size();
+    out->contexts_retired = 0;
+    for (const auto& sl : pool->slots) if (sl.retired) out->contexts_retired++;
+    out->faults = pool->total_faults; out->retries = pool->total_retries; out->contexts_recreated = pool->contexts_recreated;
     API_CATCH
 }
 
@@ -229,36 +332,109 @@ const char* hfb200_pool_prove(hfb200_pool* pool, hfb200_segment_job* jobs, size_
     API_TRY
     if (!pool || (!jobs && n_jobs)) throw Err("hfb200_pool_prove: bad argument");
     std::vector<size_t> order(n_jobs);
-    for (size_t i = 0; i < n_jobs; i++) { order[i] = i; jobs[i].error = nullptr; jobs[i].seal_words = 0; jobs[i].device = -1; jobs[i].ms = 0; }
+    for (size_t i = 0; i < n_jobs; i++) { order[i] = i; jobs[i].error = nullptr; jobs[i].seal_words = 0; jobs[i].device = -1; jobs[i].ms = 0; jobs[i].attempts = 0; }
     std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return jobs[a].po2 > jobs[b].po2; });  // longest first
-    std::atomic<size_t> next{0};
+    // argument checks up front: a mis-shaped job must not reach cudaMemcpyAsync
+    for (size_t i = 0; i < n_jobs; i++) {
+        hfb200_segment_job& j = jobs[i];
+        const size_t need = hfb200_seal_words(pool->slots.empty() ? nullptr : pool->slots[0].ctx, j.po2);
+        if (!j.globals || !j.data || !j.seal_out) j.error = dup_err("job has a NULL globals / data / seal_out pointer");
+        else if (j.po2 < 12 || j.po2 > pool->max_po2) j.error = dup_err("job po2 " + std::to_string(j.po2) + " outside [12, " + std::to_string(pool->max_po2) + "]");
+        else if (need && j.seal_cap < need) { j.seal_words = need; j.error = dup_err("seal buffer too small: need " + std::to_string(need) + " words"); }
+    }
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<size_t> pending;
+    for (size_t k = 0; k < n_jobs; k++) if (!jobs[order[k]].error) pending.push_back(order[k]);
+    size_t inflight = 0;
+    // contexts in flight per device follow the queue depth: extra contexts only hide copies and host round trips of OTHER
+    // segments; with fewer jobs than contexts they would split the SMs between segments that could have run back to back
+    std::map<int, size_t> per_device_cap;
+    {
+        std::map<int, size_t> live;
+        for (const auto& sl : pool->slots) if (!sl.retired) live[sl.device]++;
+        const size_t n_dev = live.empty() ? 1 : live.size();
+        const size_t jobs_per_device = (pending.size() + n_dev - 1) / n_dev;
+        for (const auto& kv : live) per_device_cap[kv.first] = std::max<size_t>(1, std::min(kv.second, (jobs_per_device + 1) / 2));
+    }
+    std::vector<char> taken(pool->slots.size(), 0);  // slots that have (had) a worker thread in this call
     auto worker = [&](size_t w) {
-        hfb200_ctx* ctx = pool->ctxs[w].get();
-#ifndef HFB200_EMU
-        cudaSetDevice(pool->device_of[w]);
-#endif
         for (;;) {
-            const size_t k = next.fetch_add(1);
-            if (k >= n_jobs) break;
-            hfb200_segment_job& j = jobs[order[k]];
+            hfb200_pool::Slot& sl = pool->slots[w];
+#ifndef HFB200_EMU
+            cudaSetDevice(sl.device);
+#endif
+            size_t idx;
+            {
+                std::unique_lock<std::mutex> lock(mu);
+                cv.wait(lock, [&] { return !pending.empty() || inflight == 0; });
+                if (pending.empty()) return;  // nothing queued and nothing in flight that could come back
+                idx = pending.front(); pending.pop_front();
+                inflight++;
+            }
+            hfb200_segment_job& j = jobs[idx];
             const auto t0 = std::chrono::steady_clock::now();
-            if (!j.code) {
-                // shared control group: (re)commit it on this context when it is not the one resident for this po2
+            j.attempts++;
+            const char* err = nullptr;
+            int injected = -1;
+            {
+                std::lock_guard<std::mutex> lock(pool->inject_mu);
+                auto it = pool->inject.find(w);
+                if (it != pool->inject.end()) { if (it->second.first == 0) { injected = it->second.second; pool->inject.erase(it); } else it->second.first--; }
+            }
+            if (injected == 0) err = dup_err("CUDA error cudaErrorLaunchFailure (injected by hfb200_pool_inject_fault)");
+            else if (injected == 1) err = dup_err("injected non-device failure");
+            if (!err && !j.code) {
+                // shared control group: (re)commit it on this context when the resident one is not the current load for this po2
                 const auto it = pool->control.find(j.po2);
-                if (it == pool->control.end()) { j.error = dup_err("code is NULL and no control group was loaded for this po2 (hfb200_pool_load_control)"); continue; }
-                if (!(ctx->p.control_cached && ctx->p.po2 == j.po2)) {
+                if (it == pool->control.end()) err = dup_err("code is NULL and no control group was loaded for this po2 (hfb200_pool_load_control)");
+                else if (!(sl.ctx->p.control_cached && sl.ctx->p.po2 == j.po2 && sl.ctx->p.control_gen == it->second.gen)) {
                     uint32_t root[8];
-                    if ((j.error = hfb200_control_root(ctx, j.po2, it->second, root))) continue;
+                    err = control_root_impl(sl.ctx, j.po2, it->second.code, root, it->second.gen);
                 }
             }
-            j.error = hfb200_prove_segment(ctx, j.po2, j.globals, j.code, j.data, j.blind_seed, j.seal_out, j.seal_cap, &j.seal_words);
-            j.device = pool->device_of[w];
+            if (!err) err = hfb200_prove_segment(sl.ctx, j.po2, j.globals, j.code, j.data, j.blind_seed, j.seal_out, j.seal_cap, &j.seal_words);
+            j.device = sl.device;
             j.ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            bool requeue = false, retire = false;
+            if (err && is_device_fault(err)) {
+                // the context (streams, in-flight work, possibly the whole device) is suspect: rebuild it before anything else runs on it
+                pool->drop_ctx(sl);
+                try { sl.ctx = pool->make_ctx(sl.device); } catch (...) { sl.ctx = nullptr; retire = true; }
+                requeue = j.attempts < HFB200_POOL_MAX_ATTEMPTS;
+            }
+            {
+                std::lock_guard<std::mutex> lock(mu);
+                if (err && is_device_fault(err)) { pool->total_faults++; sl.faults++; if (!retire) pool->contexts_recreated++; }
+                if (requeue) { hfb200_free_error(err); err = nullptr; pool->total_retries++; pending.push_back(idx); }
+                j.error = err;
+                if (retire) sl.retired = true;
+                inflight--;
+            }
+            cv.notify_all();
+            if (retire) {
+                // this slot is gone: carry on as the worker of a spare healthy slot (one the queue-depth cap left idle), if any
+                std::lock_guard<std::mutex> lock(mu);
+                size_t spare = pool->slots.size();
+                for (size_t k = 0; k < pool->slots.size(); k++) if (!taken[k] && !pool->slots[k].retired && pool->slots[k].ctx) { spare = k; break; }
+                if (spare == pool->slots.size()) return;
+                taken[spare] = 1;
+                w = spare;
+            }
         }
     };
     std::vector<std::thread> th;
-    for (size_t w = 0; w < pool->ctxs.size(); w++) th.emplace_back(worker, w);
+    std::map<int, size_t> started;
+    for (size_t w = 0; w < pool->slots.size(); w++) {
+        const auto& sl = pool->slots[w];
+        if (sl.retired || !sl.ctx) continue;
+        if (started[sl.device] >= per_device_cap[sl.device]) continue;
+        started[sl.device]++;
+        taken[w] = 1;
+        th.emplace_back(worker, w);
+    }
     for (auto& t : th) t.join();
+    for (size_t idx : pending) if (!jobs[idx].error) jobs[idx].error = dup_err("no healthy context left in the pool (every worker retired after CUDA errors)");
     for (size_t i = 0; i < n_jobs; i++)
         if (jobs[i].error) return dup_err(std::string("job ") + std::to_string(i) + ": " + jobs[i].error);
     API_CATCH
@@ -267,20 +443,13 @@ const char* hfb200_pool_prove(hfb200_pool* pool, hfb200_segment_job* jobs, size_
 const char* hfb200_pool_load_control(hfb200_pool* pool, uint32_t po2, const uint32_t* code) {
     API_TRY
     if (!pool) throw Err("hfb200_pool_load_control: NULL pool");
-    if (code) pool->control[po2] = code; else pool->control.erase(po2);
+    // every load gets a new generation: a worker whose resident control group came from an earlier load (even of the same
+    // pointer: the caller may have rewritten the columns) re-commits it before its next code == NULL job
+    if (code) pool->control[po2] = hfb200_pool::Control{code, pool->next_gen++}; else pool->control.erase(po2);
     API_CATCH
 }
 
-void hfb200_pool_destroy(hfb200_pool* pool) {
-    if (!pool) return;
-    for (size_t w = 0; w < pool->ctxs.size(); w++) {
-#ifndef HFB200_EMU
-        cudaSetDevice(pool->device_of[w]);
-#endif
-        try { pool->ctxs[w]->p.destroy(); } catch (...) {}
-    }
-    delete pool;
-}
+void hfb200_pool_destroy(hfb200_pool* pool) { delete pool; }
 
 // ---- HAL-level operators ------------------------------------------------------------------------
 struct DevBuf {
@@ -415,25 +584,114 @@ const char* hfb200_verify_segment(const hfb200_circuit_desc* c, const hfb200_cir
     verify_segment(vc, seal, seal_words, code_root, po2_out);
     API_CATCH
 }
-const char* hfb200_control_root(hfb200_ctx* ctx, uint32_t po2, const uint32_t* code, uint32_t* root_out) {
+// ---- receipt claims (host only) ------------------------------------------------------------------------------------------
+// Upstream's `Receipt::verify(image_id)` (/root/reference/host/src/main.rs:622-624, /root/reference/verifier/src/main.rs:124-126)
+// does more than check seals: it decodes each segment's ReceiptClaim from the seal's globals, chains pre/post state digests from
+// the image id, and ties the journal digest to the last claim's output.  The same structure, over this library's globals layout:
+//   word 0       tied to the trace by the circuit (built-in stand-in)            word 1      exit code (0 Halted, 1 SystemSplit)
+//   words 8..15  pre-state digest     words 16..23  post-state digest            words 24..31  output (journal) digest, 0 if not last
+// Digests are Poseidon2 digests (8 field elements, Montgomery form), so every word is a valid global.
+static Digest8 digest_bytes_impl(const uint8_t* bytes, size_t n) {
+    // length first, then 3 bytes per element (24 bits < p), Montgomery form, unpadded_hash
+    if (n >= P) throw Err("hfb200_digest_bytes: input too long");
+    std::vector<uint32_t> el;
+    el.reserve(1 + (n + 2) / 3);
+    el.push_back(to_mont((uint32_t)n));
+    for (size_t i = 0; i < n; i += 3) {
+        uint32_t v = bytes[i];
+        if (i + 1 < n) v |= (uint32_t)bytes[i + 1] << 8;
+        if (i + 2 < n) v |= (uint32_t)bytes[i + 2] << 16;
+        el.push_back(to_mont(v));
+    }
+    return host_hash_elems(el.data(), el.size());
+}
+static Digest8 digest_pair_impl(const uint32_t* a, const uint32_t* b) {
+    p2_host_consts();
+    uint32_t st[24] = {0};
+    for (int i = 0; i < 8; i++) { st[i] = a[i]; st[8 + i] = b[i]; }
+    p2_mix(st);
+    Digest8 d; for (int i = 0; i < 8; i++) d.w[i] = st[i];
+    return d;
+}
+static void claim_check_words(const uint32_t* w, const char* what) {
+    for (int i = 0; i < 8; i++) if (w[i] >= P) throw Err(std::string("claim: ") + what + " digest holds a non-canonical field element");
+}
+const char* hfb200_digest_bytes(const uint8_t* bytes, size_t n, uint32_t* out8) {
     API_TRY
-    if (!ctx || !code || !root_out) throw Err("hfb200_control_root: NULL argument");
-    Prover& p = ctx->p;
-    if (p.begun) throw Err("hfb200_control_root: a segment is in flight (call hfb200_segment_finish first)");
-    p.bind();
-    p.layout(po2);
-    const size_t N = (size_t)1 << po2, D = 4 * N;
-    const uint32_t w = p.cir.group_width(GROUP_CODE);
-    p.dev.h2d(p.tr[GROUP_CODE], code, (size_t)w * N * 4);
-    p.ntt.lde(p.tr[GROUP_CODE], N, p.ev[GROUP_CODE], D, p.scratch, w, (int)po2);
-    p.merkle.build(p.ev[GROUP_CODE], D, (uint32_t)D, w, p.nodes[GROUP_CODE]);
-    // keep the committed control group for the segments that follow with code == NULL
-    p.commit_tree(Tree{p.ev[GROUP_CODE], D, (uint32_t)D, w, p.nodes[GROUP_CODE]}, "code_root", &p.control_top);
-    p.proof.clear(); p.cps.clear(); p.rng = HostRng();  // commit_tree wrote into the transcript of no segment
-    std::memcpy(root_out, &p.control_top[8], 32);       // heap layout: node 1 is the root
-    p.control_cached = true;
-    p.have_trace = false;  // the resident trace (if any) lost its code group
+    if ((!bytes && n) || !out8) throw Err("hfb200_digest_bytes: NULL argument");
+    const Digest8 d = digest_bytes_impl(bytes, n);
+    std::memcpy(out8, d.w, 32);
     API_CATCH
+}
+const char* hfb200_digest_pair(const uint32_t* a8, const uint32_t* b8, uint32_t* out8) {
+    API_TRY
+    if (!a8 || !b8 || !out8) throw Err("hfb200_digest_pair: NULL argument");
+    claim_check_words(a8, "left"); claim_check_words(b8, "right");
+    const Digest8 d = digest_pair_impl(a8, b8);
+    std::memcpy(out8, d.w, 32);
+    API_CATCH
+}
+const char* hfb200_claim_encode(const hfb200_claim* c, uint32_t* globals) {
+    API_TRY
+    if (!c || !globals) throw Err("hfb200_claim_encode: NULL argument");
+    if (c->exit_code > 1) throw Err("hfb200_claim_encode: exit_code must be HFB200_EXIT_HALTED or HFB200_EXIT_SYSTEM_SPLIT");
+    claim_check_words(c->pre, "pre"); claim_check_words(c->post, "post"); claim_check_words(c->output, "output");
+    globals[1] = c->exit_code ? ONE : 0u;
+    std::memcpy(globals + 8, c->pre, 32); std::memcpy(globals + 16, c->post, 32); std::memcpy(globals + 24, c->output, 32);
+    API_CATCH
+}
+const char* hfb200_claim_decode(const uint32_t* seal, size_t seal_words, hfb200_claim* out) {
+    API_TRY
+    if (!seal || !out) throw Err("hfb200_claim_decode: NULL argument");
+    if (seal_words < N_GLOBAL + 1) throw Err("hfb200_claim_decode: seal truncated");
+    if (seal[1] != 0u && seal[1] != ONE) throw Err("claim: exit code word is neither Halted nor SystemSplit");
+    out->exit_code = seal[1] == ONE ? 1u : 0u;
+    std::memcpy(out->pre, seal + 8, 32); std::memcpy(out->post, seal + 16, 32); std::memcpy(out->output, seal + 24, 32);
+    claim_check_words(out->pre, "pre"); claim_check_words(out->post, "post"); claim_check_words(out->output, "output");
+    API_CATCH
+}
+const char* hfb200_claim_next_state(const uint32_t* pre8, uint32_t index, uint32_t po2, uint32_t* post8) {
+    API_TRY
+    if (!pre8 || !post8) throw Err("hfb200_claim_next_state: NULL argument");
+    claim_check_words(pre8, "pre");
+    // executor stand-in (SURVEY.md section 8f N1 is not built): upstream's post-state is the digest of the memory image after the
+    // segment; here it is a hash chain over (segment index, po2), so that order and count of the segments are bound
+    const uint8_t tag[8] = {(uint8_t)index, (uint8_t)(index >> 8), (uint8_t)(index >> 16), (uint8_t)(index >> 24), (uint8_t)po2, 's', 'e', 'g'};
+    const Digest8 t = digest_bytes_impl(tag, sizeof tag);
+    const Digest8 d = digest_pair_impl(pre8, t.w);
+    std::memcpy(post8, d.w, 32);
+    API_CATCH
+}
+const char* hfb200_verify_claims(const uint32_t* const* seals, const size_t* seal_words, size_t n, const uint32_t* image_id8,
+                                 const uint8_t* journal, size_t journal_len) {
+    API_TRY
+    if (!seals || !seal_words || !image_id8 || (!journal && journal_len)) throw Err("hfb200_verify_claims: NULL argument");
+    if (n == 0) throw Err("verify: composite receipt without segments");
+    const Digest8 jd = digest_bytes_impl(journal, journal_len);
+    uint32_t expect_pre[8];
+    std::memcpy(expect_pre, image_id8, 32);
+    const uint32_t zero[8] = {0};
+    for (size_t i = 0; i < n; i++) {
+        hfb200_claim c;
+        if (const char* e = hfb200_claim_decode(seals[i], seal_words[i], &c)) { const std::string m(e); hfb200_free_error(e); throw Err("segment " + std::to_string(i) + ": " + m); }
+        if (std::memcmp(c.pre, expect_pre, 32) != 0)
+            throw Err(i == 0 ? std::string("verify: segment 0 does not start from the image id (wrong program, or not the first segment)")
+                             : "verify: segment " + std::to_string(i) + " does not continue from the post-state of segment " + std::to_string(i - 1));
+        const bool last = i + 1 == n;
+        if (!last) {
+            if (c.exit_code != 1u) throw Err("verify: segment " + std::to_string(i) + " halts before the last segment");
+            if (std::memcmp(c.output, zero, 32) != 0) throw Err("verify: segment " + std::to_string(i) + " carries an output digest but is not the last segment");
+        } else {
+            if (c.exit_code != 0u) throw Err("verify: the last segment does not halt (receipt truncated)");
+            if (std::memcmp(c.output, jd.w, 32) != 0) throw Err("verify: journal digest does not match the claim of the last segment (journal altered)");
+        }
+        std::memcpy(expect_pre, c.post, 32);
+    }
+    API_CATCH
+}
+
+const char* hfb200_control_root(hfb200_ctx* ctx, uint32_t po2, const uint32_t* code, uint32_t* root_out) {
+    return control_root_impl(ctx, po2, code, root_out, 0);
 }
 const char* hfb200_bench_modmul(hfb200_ctx* ctx, int kind, uint32_t iters, double* products_per_s) {
     API_TRY
@@ -480,3 +738,26 @@ const char* hfb200_mark_elapsed(hfb200_ctx* a, int slot_a, hfb200_ctx* b, int sl
 }
 
 }  // extern "C"
+
+static const char* control_root_impl(hfb200_ctx* ctx, uint32_t po2, const uint32_t* code, uint32_t* root_out, uint64_t gen) {
+    API_TRY
+    if (!ctx || !code || !root_out) throw Err("hfb200_control_root: NULL argument");
+    Prover& p = ctx->p;
+    if (p.begun) throw Err("hfb200_control_root: a segment is in flight (call hfb200_segment_finish first)");
+    p.bind();
+    p.layout(po2);
+    p.control_cached = false; p.control_gen = 0;
+    const size_t N = (size_t)1 << po2, D = 4 * N;
+    const uint32_t w = p.cir.group_width(GROUP_CODE);
+    p.dev.h2d(p.tr[GROUP_CODE], code, (size_t)w * N * 4);
+    p.ntt.lde(p.tr[GROUP_CODE], N, p.ev[GROUP_CODE], D, p.scratch, w, (int)po2);
+    p.merkle.build(p.ev[GROUP_CODE], D, (uint32_t)D, w, p.nodes[GROUP_CODE]);
+    // keep the committed control group for the segments that follow with code == NULL
+    p.commit_tree(Tree{p.ev[GROUP_CODE], D, (uint32_t)D, w, p.nodes[GROUP_CODE]}, "code_root", &p.control_top);
+    p.proof.clear(); p.cps.clear(); p.rng = HostRng();  // commit_tree wrote into the transcript of no segment
+    std::memcpy(root_out, &p.control_top[8], 32);       // heap layout: node 1 is the root
+    p.control_cached = true;
+    p.control_gen = gen;
+    p.have_trace = false;  // the resident trace (if any) lost its code group
+    API_CATCH
+}

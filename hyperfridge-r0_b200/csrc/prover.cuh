@@ -65,6 +65,7 @@ struct Prover {
     // control columns depend on (circuit, po2) only -- upstream's verifier checks their root against a per-po2 table --
     // so their LDE and Merkle tree need not be rebuilt per segment.  Valid while the context stays at this po2.
     bool control_cached = false;
+    uint64_t control_gen = 0;           // which hfb200_pool_load_control call the cached group came from (0: not from a pool)
     std::vector<uint32_t> control_top;  // the tree's top layers as commit_tree reads them
     uint32_t* tr[3] = {nullptr, nullptr, nullptr};  // resident traces: accum, code, data
     uint32_t* ev[3] = {nullptr, nullptr, nullptr};
@@ -74,7 +75,10 @@ struct Prover {
     size_t seg_mark = 0;  // arena offset after the per-po2 fixed buffers
     uint32_t globals[N_GLOBAL];
     std::vector<uint32_t> mix;
-    uint64_t blind_seed = 0;
+    // zero-knowledge blinding (blind.cuh): OS entropy per segment unless the caller opted into the deterministic test mode
+    int blind_mode = BLIND_OS_ENTROPY;
+    BlindKey blind_key{};
+    BlindKey make_blind_key(uint64_t seed) const { return blind_mode == BLIND_DETERMINISTIC ? blind_key_from_seed(seed) : blind_key_from_os(seed); }
     std::vector<uint32_t> proof;
     HostRng rng;
     std::vector<std::pair<std::string, std::vector<uint32_t>>> cps;
@@ -236,9 +240,12 @@ struct Prover {
         proof.clear(); cps.clear(); rng = HostRng(); stats = Stats();
         for (auto& s : stage_ms) s = 0;
         launches_at_begin = dev.launches;
-        blind_seed = blind;
+        blind_key = make_blind_key(blind);
+        // every argument check comes BEFORE the first copy is queued: an error return must not leave DMA from caller memory in flight
+        for (uint32_t i = 0; i < N_GLOBAL; i++) if (globals_h[i] >= P) throw Err("globals: non-canonical field element");
+        if (data_h && !code_h && !control_cached) throw Err("code is NULL and no control group is resident for this po2 (hfb200_control_root)");
+        if (!data_h && !have_trace) throw Err("no trace: pass code/data (code may be NULL after hfb200_control_root) or call hfb200_witgen_synth first");
         std::memcpy(globals, globals_h, sizeof globals);
-        for (uint32_t i = 0; i < N_GLOBAL; i++) if (globals[i] >= P) throw Err("globals: non-canonical field element");
         mark(0);
         bool chunked = false;
         if (code_h) { dev.h2d(tr[GROUP_CODE], code_h, (size_t)cir.cd.w_code * N * 4); }
@@ -258,9 +265,8 @@ struct Prover {
 #endif
         if (data_h) { dev.h2d(tr[GROUP_DATA], data_h, (size_t)cir.cd.w_data * N * 4); }
         const bool use_control = !code_h && data_h && control_cached;
-        if (code_h) control_cached = false;  // the resident control columns change
-        if ((code_h || use_control) && data_h) have_trace = true;
-        if (!have_trace) throw Err("no trace: pass code/data (code may be NULL after hfb200_control_root) or call hfb200_witgen_synth first");
+        if (code_h) { control_cached = false; control_gen = 0; }  // the resident control columns change
+        if (data_h) have_trace = true;
         mark(1);
         const Digest8 gh = host_hash_elems(globals, N_GLOBAL);
         rng.mix(gh.w);
@@ -305,9 +311,9 @@ struct Prover {
         const uint32_t nblk = (uint32_t)((N + ACC_RPB - 1) / ACC_RPB);
         E4* partial = arena.take<E4>((size_t)cir.cd.n_chains * nblk);
         const size_t sm1 = 2 * ACC_ITEMS * sizeof(E4);
-        dev.launch<AccumKernel, 256, 1>(nblk, cir.cd.n_chains, 256, sm1, tr[GROUP_ACCUM], (const uint32_t*)tr[GROUP_DATA], (const uint32_t*)d_mix, partial, cir.cd, po2, blind_seed, 0);
+        dev.launch<AccumKernel, 256, 1>(nblk, cir.cd.n_chains, 256, sm1, tr[GROUP_ACCUM], (const uint32_t*)tr[GROUP_DATA], (const uint32_t*)d_mix, partial, cir.cd, po2, blind_key, 0);
         dev.launch<AccumOffsetsKernel, 256, 1>(1, cir.cd.n_chains, 256, 2 * (size_t)nblk * sizeof(E4), partial, nblk);
-        dev.launch<AccumKernel, 256, 1>(nblk, cir.cd.n_chains, 256, sm1, tr[GROUP_ACCUM], (const uint32_t*)tr[GROUP_DATA], (const uint32_t*)d_mix, partial, cir.cd, po2, blind_seed, 1);
+        dev.launch<AccumKernel, 256, 1>(nblk, cir.cd.n_chains, 256, sm1, tr[GROUP_ACCUM], (const uint32_t*)tr[GROUP_DATA], (const uint32_t*)d_mix, partial, cir.cd, po2, blind_key, 1);
     }
 
     static uint32_t rou_fwd(int k) { uint32_t g = to_mont(137); for (int i = k; i < 27; i++) g = fmul(g, g); return g; }
@@ -662,12 +668,13 @@ struct Prover {
         if (gen.active) throw Err("hfb200_witgen_synth: only for the built-in synthetic circuit");
         bind();
         layout(p);
+        control_cached = false; control_gen = 0;  // the resident control columns are overwritten below
         const size_t N = (size_t)1 << po2;
         for (uint32_t i = 0; i < N_GLOBAL; i++) globals_out[i] = synth_value(trace_seed ^ 0x676C6F62ull, 0xFFFFu, i);
         std::memcpy(globals, globals_out, sizeof globals);
         const CircuitDev& cd = cir.cd;
         dev.launch<GenCodeKernel, 256, 1>((unsigned)(((size_t)cd.w_code * N + 255) / 256), 1, 256, 0, tr[GROUP_CODE], cd.w_code, po2);
-        dev.launch<GenFreeKernel, 256, 1>((unsigned)(((size_t)cd.w_data * N + 255) / 256), 1, 256, 0, tr[GROUP_DATA], cd, po2, trace_seed, blind, globals_out[0]);
+        dev.launch<GenFreeKernel, 256, 1>((unsigned)(((size_t)cd.w_data * N + 255) / 256), 1, 256, 0, tr[GROUP_DATA], cd, po2, trace_seed, make_blind_key(blind), globals_out[0]);
         dev.launch<GenDerivedKernel, 256, 1>((unsigned)(((size_t)cd.n_free * N + 255) / 256), 1, 256, 0, tr[GROUP_DATA], (const uint32_t*)tr[GROUP_CODE], cd, po2);
         dev.sync();
         have_trace = true;

@@ -9,7 +9,8 @@ The two receipts shipped with the reference are dev-mode fakes (`{"inner":"Fake"
 /root/reference/data/test/test.xml-Receipt-test.json:1); `Receipt.from_json` accepts them, which pins the journal
 encoding against reference data.  The Composite form (`{"inner":{"Composite":{"segments":[{"seal":[..u32..],"index":..,
 "hashfn":"poseidon2",..}],..}}`) follows risc0-zkvm 3.0.5's `CompositeReceipt` / `SegmentReceipt` field names (crate not
-vendored: recollection); claims are carried opaquely.
+vendored: recollection).  `claim` = {"pre","post","exit_code","output"} as decoded from the seal's
+globals (hfb200_claim_decode); `Receipt.verify(image_id, control_ids)` checks the whole chain (see its docstring).
 """
 import json
 import struct
@@ -96,13 +97,29 @@ class Receipt:
     def seal_bytes(self) -> int:
         return 0 if isinstance(self.inner, str) else sum(4 * len(s.seal) for s in self.inner.segments)
 
-    def verify(self, control_ids, circuit=(16, 192, 48), ir=None, lib=None) -> None:
+    def verify(self, image_id, control_ids, circuit=(16, 192, 48), ir=None, lib=None) -> None:
         """`receipt.verify(HYPERFRIDGE_ID)` of the reference (/root/reference/host/src/main.rs:622-624,
-        /root/reference/verifier/src/main.rs:124-126) for the part this path owns: every segment seal is checked by
-        `hfb200_verify_segment` against the control id of its po2 (`control_ids`: {po2: 8 words}, the analogue of upstream's
-        per-po2 control-id table), segment indices must run 0..n-1, and a dev-mode `Fake` receipt is refused exactly like
-        upstream refuses it outside RISC0_DEV_MODE.  The claim chain (pre/post state digests, image id) belongs to the
-        executor side and is carried opaquely.  Raises Hfb200Error with the reason."""
+        /root/reference/verifier/src/main.rs:124-126; the verifier trusts `receipt.journal` after this call):
+          1. every segment seal is checked by `hfb200_verify_segment` against the control id of its po2 (`control_ids`:
+             {po2: 8 words}, the analogue of upstream's per-po2 control-id table); segment indices run 0..n-1; a dev-mode
+             `Fake` receipt is refused exactly like upstream refuses it outside RISC0_DEV_MODE;
+          2. the claim chain (`hfb200_verify_claims`): each segment's claim is decoded from its seal's globals, segment 0
+             must start from `image_id`, every segment must continue from its predecessor's post-state, only the last one
+             halts, and its output digest must equal the digest of `journal.bytes` -- a receipt whose journal was replaced,
+             whose segments were swapped or dropped, or that was proved for another image is rejected;
+          3. a `claim` object carried in the JSON must equal the one decoded from the seal.
+        Raises Hfb200Error with the reason."""
+        from .binding import verify_segment, verify_claims, claim_decode, Hfb200Error
+        self.verify_seals(control_ids, circuit=circuit, ir=ir, lib=lib)
+        segs = self.inner.segments
+        verify_claims([s.seal for s in segs], image_id, self.journal.bytes_, lib=lib)
+        for i, s in enumerate(segs):
+            if s.claim is not None and s.claim != claim_decode(s.seal, lib=lib).to_obj():
+                raise Hfb200Error("verify: segment %d: the claim in the receipt differs from the one its seal commits to" % i)
+
+    def verify_seals(self, control_ids, circuit=(16, 192, 48), ir=None, lib=None) -> None:
+        """Step 1 of verify() alone: seals against control ids and index order.  NOT a substitute for verify(): it says
+        nothing about the journal or the image id."""
         from .binding import verify_segment, Hfb200Error
         if isinstance(self.inner, str):
             raise Hfb200Error("verify: %s receipt carries no seal (dev-mode receipts are refused)" % self.inner)

@@ -78,6 +78,15 @@ const char* hfb200_ir_source(const hfb200_circuit_ir* circuit, char* out, size_t
 int hfb200_ir_jit_active(const hfb200_ctx* ctx, float* compile_ms);
 void hfb200_destroy(hfb200_ctx* ctx);
 void hfb200_free_error(const char* msg);
+
+/* Zero-knowledge blinding.  Upstream draws the blinding rows of every proof from a cryptographic RNG (risc0-zkp
+ * `Elem::random(&mut thread_rng())`).  The library does the same by DEFAULT: per segment, a 256-bit key from the OS
+ * (getrandom) expanded by the ChaCha20 block function on the device (csrc/blind.cuh); the `blind_seed` arguments below are
+ * then only mixed into that key and seals are NOT reproducible.  HFB200_BLIND_DETERMINISTIC derives the key from the 64-bit
+ * `blind_seed` alone: reproducible seals for parity tests and benchmarks, NOT zero-knowledge against anyone who can guess
+ * the seed -- never use it for real statements. */
+enum { HFB200_BLIND_OS_ENTROPY = 0, HFB200_BLIND_DETERMINISTIC = 1 };
+const char* hfb200_set_blinding(hfb200_ctx* ctx, int mode);
 const char* hfb200_version(void);
 
 /* Pinned host memory for trace staging (plain pointers are accepted too, just slower over PCIe). */
@@ -126,6 +135,31 @@ const char* hfb200_checkpoint(hfb200_ctx* ctx, const char* name, uint32_t* out, 
  * Returns NULL when the seal is valid, else the reason. */
 const char* hfb200_verify_segment(const hfb200_circuit_desc* circuit, const hfb200_circuit_ir* ir, const uint32_t* seal, size_t seal_words,
                                   const uint32_t* code_root /*[8]*/, uint32_t* po2_out);
+/* ---- receipt claims: the rest of `receipt.verify(image_id)` (host only; no device, no context) -------------------------
+ * Upstream's Receipt::verify also decodes each segment's ReceiptClaim from the seal's globals, chains pre/post state digests
+ * from the image id and ties the journal digest to the last claim's output (/root/reference/verifier/src/main.rs:124-126 trusts
+ * the journal after this call).  Globals layout used here (the rv32im-v2 layout is not obtainable; this is the stand-in's):
+ *   word 1 = exit code (0 Halted / 1 SystemSplit), words 8..15 = pre-state, 16..23 = post-state, 24..31 = output (journal)
+ *   digest, zero unless last.  Digests are Poseidon2 digests: 8 field elements in Montgomery form.
+ * The globals are part of every seal and are absorbed first into the Fiat-Shamir transcript, so a seal that verifies carries
+ * exactly the claim its prover was given. */
+typedef struct { uint32_t pre[8], post[8], output[8]; uint32_t exit_code; } hfb200_claim;
+enum { HFB200_EXIT_HALTED = 0, HFB200_EXIT_SYSTEM_SPLIT = 1 };
+/* Poseidon2 digest of a byte string (length, then 3 bytes per field element): the journal digest. */
+const char* hfb200_digest_bytes(const uint8_t* bytes, size_t n, uint32_t* out8);
+/* Poseidon2 hash_pair of two digests. */
+const char* hfb200_digest_pair(const uint32_t* a8, const uint32_t* b8, uint32_t* out8);
+/* Writes / reads the claim words of a 32-word globals array (a seal starts with its globals). */
+const char* hfb200_claim_encode(const hfb200_claim* claim, uint32_t* globals /*[32]*/);
+const char* hfb200_claim_decode(const uint32_t* seal, size_t seal_words, hfb200_claim* out);
+/* Executor stand-in: the post-state that follows `pre` after segment `index` of size po2 (upstream: digest of the memory image). */
+const char* hfb200_claim_next_state(const uint32_t* pre8, uint32_t index, uint32_t po2, uint32_t* post8);
+/* The claim part of Receipt::verify over n seals in segment order (each already accepted by hfb200_verify_segment): segment 0
+ * starts from image_id, every segment continues from its predecessor's post-state, only the last one halts, and its output equals
+ * hfb200_digest_bytes(journal).  Returns NULL or the reason. */
+const char* hfb200_verify_claims(const uint32_t* const* seals, const size_t* seal_words, size_t n, const uint32_t* image_id8,
+                                 const uint8_t* journal, size_t journal_len);
+
 /* Control id: Merkle root of the x4 LDE of the code (control) columns, u32[w_code][2^po2] on the host.
  * The committed control group stays resident: until the context sees another po2 or another `code` pointer, segments may
  * pass code == NULL to hfb200_prove_segment / hfb200_segment_begin and reuse it (the control columns depend on
@@ -165,15 +199,39 @@ typedef struct {
     size_t seal_words;       /* out */
     const char* error;       /* out: NULL or malloc'd message (hfb200_free_error) */
     int device;              /* out: device that proved the job */
-    float ms;                /* out: host wall time of the job */
+    float ms;                /* out: host wall time of the job (last attempt) */
+    int attempts;            /* out: times the job was started (> 1: re-queued after a CUDA error on another context) */
 } hfb200_segment_job;
 const char* hfb200_pool_create(const int* devices, int n_devices, int contexts_per_device, uint32_t max_po2,
                                const hfb200_circuit_desc* circuit, hfb200_pool** out);
-/* Proves all jobs; returns NULL when every job succeeded, else the first job's error (also left in jobs[i].error). */
+/* Same for a circuit given as data (every worker context is an hfb200_init_ir context; the tables are copied). */
+const char* hfb200_pool_create_ir(const int* devices, int n_devices, int contexts_per_device, uint32_t max_po2,
+                                  const hfb200_circuit_ir* circuit, hfb200_pool** out);
+/* Blinding mode of every worker context (see hfb200_set_blinding; default HFB200_BLIND_OS_ENTROPY). */
+const char* hfb200_pool_set_blinding(hfb200_pool* pool, int mode);
+/* Proves all jobs; returns NULL when every job succeeded, else the first failed job's error (every failed job keeps its own
+ * message in jobs[i].error).  Failure handling (the reference's batch behaviour, /root/reference/data/watchdog.sh:58-83: a
+ * failed input is set aside and the rest continue): a shape / argument error fails that job only; a CUDA error makes the
+ * worker destroy and re-create its context (the context is retired if that fails) and puts the job back on the queue for any
+ * healthy context, at most 3 attempts; jobs left when no healthy context remains fail with that reason.  The number of
+ * contexts in flight per device follows the queue depth (min(contexts_per_device, ceil(jobs per device / 2))). */
 const char* hfb200_pool_prove(hfb200_pool* pool, hfb200_segment_job* jobs, size_t n_jobs);
+typedef struct {
+    size_t contexts;            /* worker contexts created */
+    size_t contexts_retired;    /* contexts that could not be re-created after a CUDA error */
+    uint64_t faults;            /* CUDA errors seen by workers since pool creation */
+    uint64_t retries;           /* jobs put back on the queue */
+    uint64_t contexts_recreated;
+} hfb200_pool_stats_t;
+const char* hfb200_pool_stats(const hfb200_pool* pool, hfb200_pool_stats_t* out);
+/* Test hook: worker `worker` lets `after_jobs` more jobs pass, then reports a failure INSTEAD of proving its next job.
+ * kind 0 = a device fault ("CUDA error ..."): exercises context re-creation + re-queue; kind 1 = a non-device failure: the
+ * job fails, nothing is retried.  Nothing is injected unless this is called. */
+const char* hfb200_pool_inject_fault(hfb200_pool* pool, size_t worker, uint64_t after_jobs, int kind);
 /* Shared control group for the jobs of one po2 (opt-in): `code` = u32[w_code][2^po2], caller-owned, must stay valid while the pool
  * may use it (NULL forgets it).  Jobs of that po2 may then carry code == NULL: every worker context commits the control group once
- * (hfb200_control_root) and reuses it; seals are identical to the ones produced with the columns passed per job. */
+ * per load (each call starts a new generation, so a reload -- same pointer or not -- is re-committed by every worker before its
+ * next code == NULL job) and reuses it; seals are identical to the ones produced with the columns passed per job. */
 const char* hfb200_pool_load_control(hfb200_pool* pool, uint32_t po2, const uint32_t* code);
 void hfb200_pool_destroy(hfb200_pool* pool);
 

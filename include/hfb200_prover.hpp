@@ -46,7 +46,16 @@ struct ProverOpts {
     std::vector<int> devices{0};
     int contexts_per_device = 2;
     bool reuse_control = false;  // opt-in: segments of equal po2 share the control group of the first one (true for rv32im)
+    bool deterministic_blinding = false;  // tests / bench only: blinding from Segment::blind_seed alone (NOT zero-knowledge)
 };
+
+// Stand-in for HYPERFRIDGE_ID (/root/reference/host/src/main.rs:7): the executor is out of scope, so there is no ELF to digest.
+inline Digest default_image_id() {
+    static const char tag[] = "hyperfridge guest image id (stand-in: executor out of scope)";
+    Digest d;
+    ffi_wrap(hfb200_digest_bytes(reinterpret_cast<const uint8_t*>(tag), sizeof tag - 1, d.data()));
+    return d;
+}
 
 // What upstream's `Segment` boils down to at the prover seam: po2 and the witness columns (+ blinding seed).  Host pointers,
 // column-major u32[w][2^po2] Montgomery residues, owned by the caller for the duration of prove().
@@ -60,6 +69,8 @@ struct Segment {
 struct Session {
     std::vector<Segment> segments;
     std::string journal;  // the String the guest committed (risc0 serde: u32-LE length, bytes, zero pad to 4)
+    bool has_image_id = false;
+    Digest image_id{};    // pre-state of segment 0; default_image_id() when has_image_id is false
 };
 
 struct Journal {
@@ -142,6 +153,13 @@ struct Receipt {
     std::vector<SegmentReceipt> segments;  // inner = Composite
     Journal journal;
 
+    // the claim a seal commits to (hfb200_claim_decode), in the shape the Python mirror writes; "null" if the seal is malformed
+    static std::string claim_json(const std::vector<uint32_t>& seal) {
+        hfb200_claim c;
+        if (const char* e = hfb200_claim_decode(seal.data(), seal.size(), &c)) { hfb200_free_error(e); return "null"; }
+        auto arr = [](const uint32_t* w) { std::string a = "["; for (int i = 0; i < 8; i++) { if (i) a += ','; a += std::to_string(w[i]); } return a + "]"; };
+        return std::string("{\"pre\":") + arr(c.pre) + ",\"post\":" + arr(c.post) + ",\"exit_code\":\"" + (c.exit_code ? "SystemSplit" : "Halted") + "\",\"output\":" + arr(c.output) + "}";
+    }
     std::string to_json() const {
         std::string s = "{\"inner\":";
         if (fake) s += "\"Fake\"";
@@ -151,7 +169,7 @@ struct Receipt {
                 if (i) s += ',';
                 s += "{\"seal\":[";
                 for (size_t k = 0; k < segments[i].seal.size(); k++) { if (k) s += ','; s += std::to_string(segments[i].seal[k]); }
-                s += "],\"index\":" + std::to_string(segments[i].index) + ",\"hashfn\":\"" + segments[i].hashfn + "\",\"verifier_parameters\":[0,0,0,0,0,0,0,0],\"claim\":null}";
+                s += "],\"index\":" + std::to_string(segments[i].index) + ",\"hashfn\":\"" + segments[i].hashfn + "\",\"verifier_parameters\":[0,0,0,0,0,0,0,0],\"claim\":" + claim_json(segments[i].seal) + "}";
             }
             s += "],\"assumption_receipts\":[],\"verifier_parameters\":[0,0,0,0,0,0,0,0]}}";
         }
@@ -199,9 +217,21 @@ struct Receipt {
     }
     size_t seal_bytes() const { size_t n = 0; for (const auto& s : segments) n += 4 * s.seal.size(); return n; }
 
-    // `receipt.verify(id)`: every segment seal against the control id of its po2 (upstream's per-po2 control-id table), segment
-    // indices 0..n-1, dev-mode receipts refused.  The claim chain / image id belong to the executor side (out of scope).
-    void verify(const std::map<uint32_t, Digest>& control_ids, const hfb200_circuit_desc& circuit = hfb200_circuit_desc{16, 192, 48, 0}) const {
+    // `receipt.verify(HYPERFRIDGE_ID)` (/root/reference/host/src/main.rs:622-624, /root/reference/verifier/src/main.rs:124-126, which
+    // trusts receipt.journal after this call): (1) every segment seal against the control id of its po2 (upstream's per-po2
+    // control-id table), indices 0..n-1, dev-mode receipts refused; (2) the claim chain (hfb200_verify_claims): segment 0 starts from
+    // image_id, every segment continues from its predecessor's post-state, only the last one halts and its output is the digest of
+    // journal.bytes -- a replaced journal, swapped / dropped segments or another image are rejected.
+    void verify(const Digest& image_id, const std::map<uint32_t, Digest>& control_ids,
+                const hfb200_circuit_desc& circuit = hfb200_circuit_desc{16, 192, 48, 0}) const {
+        verify_seals(control_ids, circuit);
+        std::vector<const uint32_t*> ptrs;
+        std::vector<size_t> lens;
+        for (const auto& s : segments) { ptrs.push_back(s.seal.data()); lens.push_back(s.seal.size()); }
+        ffi_wrap(hfb200_verify_claims(ptrs.data(), lens.data(), ptrs.size(), image_id.data(), journal.bytes.data(), journal.bytes.size()));
+    }
+    // step (1) alone; NOT a substitute for verify(): it says nothing about the journal or the image id
+    void verify_seals(const std::map<uint32_t, Digest>& control_ids, const hfb200_circuit_desc& circuit = hfb200_circuit_desc{16, 192, 48, 0}) const {
         if (fake) throw Error("verify: Fake receipt carries no seal (dev-mode receipts are refused)");
         if (segments.empty()) throw Error("verify: composite receipt without segments");
         for (size_t want = 0; want < segments.size(); want++) {
@@ -233,6 +263,10 @@ class Prover {
         if (o.receipt_kind != "composite") throw Error("succinct / groth16 receipts need the recursion circuit: out of scope");
         if (o.devices.empty()) throw Error("ProverOpts: no devices");
         ffi_wrap(hfb200_pool_create(o.devices.data(), (int)o.devices.size(), o.contexts_per_device, o.max_segment_po2, &o.circuit, &pool_));
+        if (o.deterministic_blinding) {
+            const char* e = hfb200_pool_set_blinding(pool_, HFB200_BLIND_DETERMINISTIC);
+            if (e) { hfb200_pool_destroy(pool_); pool_ = nullptr; ffi_wrap(e); }
+        }
     }
     ~Prover() { hfb200_pool_destroy(pool_); }
     Prover(const Prover&) = delete;
@@ -240,7 +274,8 @@ class Prover {
     const ProverOpts& opts() const { return opts_; }
 
     // prover.prove(env, elf) -> ProveInfo
-    ProveInfo prove(const Session& session, size_t seal_cap_words = (size_t)1 << 18) {
+    // n_total_segments: segments of the whole session when this call proves only a share of it (multi-process operation); 0 = all
+    ProveInfo prove(const Session& session, size_t seal_cap_words = (size_t)1 << 18, size_t n_total_segments = 0) {
         for (const Segment& s : session.segments)
             if (s.po2 > opts_.max_segment_po2) throw Error("segment po2 " + std::to_string(s.po2) + " exceeds max_segment_po2 " + std::to_string(opts_.max_segment_po2));
         const size_t n = session.segments.size();
@@ -248,13 +283,45 @@ class Prover {
         std::vector<hfb200_segment_job> jobs(n);
         if (opts_.reuse_control) {
             std::map<uint32_t, const uint32_t*> first;
-            for (const Segment& s : session.segments) first.emplace(s.po2, s.code);
+            for (const Segment& s : session.segments) {
+                const auto it = first.find(s.po2);
+                if (it == first.end()) first.emplace(s.po2, s.code);
+                else if (it->second != s.code && std::memcmp(it->second, s.code, ((size_t)opts_.circuit.w_code << s.po2) * 4) != 0)
+                    throw Error("reuse_control: segments of po2 " + std::to_string(s.po2) + " carry different control columns");
+            }
             for (const auto& kv : first) ffi_wrap(hfb200_pool_load_control(pool_, kv.first, kv.second));
+        }
+        // what upstream's executor does for the prover: every segment's globals carry its claim (state chain from the image id,
+        // SystemSplit for all but the last segment, the journal digest as the last one's output)
+        const size_t n_total = n_total_segments ? n_total_segments : n;
+        const Journal journal = Journal::encode(session.journal);
+        Digest journal_digest;
+        ffi_wrap(hfb200_digest_bytes(journal.bytes.data(), journal.bytes.size(), journal_digest.data()));
+        std::map<uint32_t, uint32_t> po2_of;
+        for (const Segment& s : session.segments) po2_of[s.index] = s.po2;
+        std::vector<Digest> states(n_total + 1);
+        states[0] = session.has_image_id ? session.image_id : default_image_id();
+        for (size_t i = 0; i < n_total; i++) {
+            const auto it = po2_of.find((uint32_t)i);
+            const uint32_t p2 = it != po2_of.end() ? it->second : (n ? session.segments[0].po2 : 0);
+            ffi_wrap(hfb200_claim_next_state(states[i].data(), (uint32_t)i, p2, states[i + 1].data()));
+        }
+        std::vector<std::array<uint32_t, HFB200_N_GLOBAL>> globals(n);
+        for (size_t i = 0; i < n; i++) {
+            const Segment& s = session.segments[i];
+            if (s.index >= n_total) throw Error("segment index " + std::to_string(s.index) + " outside the session");
+            std::memcpy(globals[i].data(), s.globals, sizeof globals[i]);
+            hfb200_claim c{};
+            const bool last = s.index + 1 == n_total;
+            std::memcpy(c.pre, states[s.index].data(), 32); std::memcpy(c.post, states[s.index + 1].data(), 32);
+            if (last) std::memcpy(c.output, journal_digest.data(), 32);
+            c.exit_code = last ? HFB200_EXIT_HALTED : HFB200_EXIT_SYSTEM_SPLIT;
+            ffi_wrap(hfb200_claim_encode(&c, globals[i].data()));
         }
         for (size_t i = 0; i < n; i++) {
             const Segment& s = session.segments[i];
             std::memset(&jobs[i], 0, sizeof jobs[i]);
-            jobs[i].po2 = s.po2; jobs[i].globals = s.globals; jobs[i].code = opts_.reuse_control ? nullptr : s.code; jobs[i].data = s.data;
+            jobs[i].po2 = s.po2; jobs[i].globals = globals[i].data(); jobs[i].code = opts_.reuse_control ? nullptr : s.code; jobs[i].data = s.data;
             jobs[i].blind_seed = s.blind_seed; jobs[i].seal_out = seals[i].data(); jobs[i].seal_cap = seal_cap_words;
         }
         const char* e = hfb200_pool_prove(pool_, jobs.data(), n);
@@ -272,7 +339,7 @@ class Prover {
             info.devices.push_back(jobs[i].device);
             info.segment_ms.push_back(jobs[i].ms);
         }
-        info.receipt.journal = Journal::encode(session.journal);
+        info.receipt.journal = journal;
         return info;
     }
 

@@ -13,7 +13,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "liboracle.so")
-_SRCS = ["prover.cpp", "capi.cpp", "fp.h", "poseidon2.h", "poseidon2_consts.inc", "ntt.h", "merkle_iop.h", "circuit.h", "prover.h", "Makefile"]
+_SRCS = ["prover.cpp", "capi.cpp", "fp.h", "poseidon2.h", "poseidon2_consts.inc", "ntt.h", "merkle_iop.h", "blind.h", "circuit.h", "prover.h", "Makefile"]
 
 
 def build(force=False):
@@ -90,6 +90,9 @@ def lib():
         L.orc_h_seal_words_model.argtypes = [vp, C.c_uint]
         L.orc_h_prove_segment.argtypes = [vp, C.c_uint, vp, vp, vp, C.c_uint64, C.POINTER(vp)]
         L.orc_h_verify_segment.argtypes = [vp, vp, C.c_size_t, vp, vp]
+        L.orc_chacha20_block.argtypes = [vp, C.c_uint32, vp, vp]
+        L.orc_blind_value.restype = C.c_uint32
+        L.orc_blind_value.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
         _lib = L
     return _lib
 
@@ -121,6 +124,18 @@ def decode(m):
     rinv = pow(1 << 32, P - 2, P)
     hi = (m * np.uint64(rinv >> 16)) % np.uint64(P)
     return ((hi * np.uint64(1 << 16) + m * np.uint64(rinv & 0xFFFF)) % np.uint64(P)).astype(np.uint32)
+
+
+def chacha20_block(key8, counter, nonce3):
+    """RFC 8439 section 2.3 block function (the blinding-noise PRF): 16 output words."""
+    key8, nonce3 = _u32(key8), _u32(nonce3)
+    out = np.zeros(16, np.uint32)
+    lib().orc_chacha20_block(_p(key8), counter, _p(nonce3), _p(out))
+    return out
+
+
+def blind_value(seed, group, col, row):
+    return lib().orc_blind_value(seed, group, col, row)
 
 
 def poseidon2_mix(state24):

@@ -18,6 +18,10 @@ const char* orc_last_error() { return g_err.c_str(); }
 int orc_num_threads() { return omp_get_max_threads(); }
 void orc_set_threads(int n) { omp_set_num_threads(n); }
 
+// ---- blinding PRF (RFC 8439 block function; pinned by the RFC's test vector in tests/) ----
+void orc_chacha20_block(const uint32_t* key8, uint32_t counter, const uint32_t* nonce3, uint32_t* out16) { chacha20_block(key8, counter, nonce3, out16); }
+uint32_t orc_blind_value(uint64_t seed, uint32_t group, uint32_t col, uint32_t row) { return blind_value(BlindKey(seed), group, col, row).v; }
+
 // ---- field ----
 uint32_t orc_mont_mul(uint32_t a, uint32_t b) { return Fp::mont_mul(a, b); }
 uint32_t orc_encode(uint32_t x) { return Fp::from_u32(x).v; }

@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <tuple>
 #include "merkle_iop.h"
+#include "blind.h"
 
 namespace orc {
 
@@ -29,19 +30,6 @@ static inline uint64_t splitmix64(uint64_t z) {
 static inline Fp synth_value(uint64_t seed, uint32_t col, uint32_t row) {
     return Fp::from_u64(splitmix64(seed ^ (((uint64_t)col << 32) | row)));
 }
-// Blinding noise, counter based so CPU and GPU need no shared stream state.  Shape follows
-// `Elem::random` (six u32 draws folded mod p).
-static inline Fp blind_value(uint64_t seed, uint32_t group, uint32_t col, uint32_t row) {
-    uint64_t key = splitmix64(seed ^ 0x6E6F697365ull) ^ ((uint64_t)group << 60) ^ ((uint64_t)col << 32) ^ row;
-    uint64_t v = 0;
-    for (int i = 0; i < 3; i++) {
-        uint64_t d = splitmix64(key + (uint64_t)i * 0xD1342543DE82EF95ull);
-        v = ((v << 32) + (uint32_t)d) % P;
-        v = ((v << 32) + (uint32_t)(d >> 32)) % P;
-    }
-    return Fp::from_u32((uint32_t)v);
-}
-
 struct Tap { uint32_t group, offset, back, combo; };
 
 // Constraint polynomial as data: upstream's verifier-side representation `risc0_zkp::adapter::PolyExtStepDef`
@@ -168,7 +156,7 @@ struct Circuit {
         for (long c = 0; c < (long)w_data; c++) {
             Fp* col = data + (size_t)c * n;
             if ((uint32_t)c < n_free) for (size_t r = 0; r < act; r++) col[r] = synth_value(trace_seed, (uint32_t)c, (uint32_t)r);
-            for (size_t r = act; r < n; r++) col[r] = blind_value(blind_seed, GROUP_DATA, (uint32_t)c, (uint32_t)r);
+            for (size_t r = act; r < n; r++) col[r] = blind_value(BlindKey(blind_seed), GROUP_DATA, (uint32_t)c, (uint32_t)r);
         }
         data[0] = globals[0];
         #pragma omp parallel for schedule(static)
@@ -193,7 +181,7 @@ struct Circuit {
                     acc = acc * (Fp4(src[i]) + m);
                     for (int k = 0; k < 4; k++) accum[(size_t)(4 * r + k) * n + i] = acc.c[k];
                 } else {
-                    for (int k = 0; k < 4; k++) accum[(size_t)(4 * r + k) * n + i] = blind_value(blind_seed, GROUP_ACCUM, (uint32_t)(4 * r + k), (uint32_t)i);
+                    for (int k = 0; k < 4; k++) accum[(size_t)(4 * r + k) * n + i] = blind_value(BlindKey(blind_seed), GROUP_ACCUM, (uint32_t)(4 * r + k), (uint32_t)i);
                 }
             }
         }

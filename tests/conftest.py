@@ -6,6 +6,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# Parity tests compare seals with the CPU oracle, so they need reproducible blinding: the binding switches every context it
+# creates to HFB200_BLIND_DETERMINISTIC.  The C ABI's default stays OS entropy (tests/test_blinding.py checks both).
+os.environ.setdefault("HFB200_DETERMINISTIC_BLINDING", "1")
 
 
 def pytest_configure(config):

@@ -33,6 +33,7 @@ int main(int argc, char** argv) {
         {
             hfb200_ctx* ctx = nullptr;
             ffi_wrap(hfb200_init(device, max_po2, &circuit, &ctx));
+            ffi_wrap(hfb200_set_blinding(ctx, HFB200_BLIND_DETERMINISTIC));  // reproducible seals: this demo compares them across runs
             for (size_t i = 0; i < po2s.size(); i++) {
                 const size_t n = (size_t)1 << po2s[i];
                 globals[i].resize(HFB200_N_GLOBAL); code[i].resize(circuit.w_code * n); data[i].resize(circuit.w_data * n);
@@ -54,6 +55,8 @@ int main(int argc, char** argv) {
         }
         ProverOpts opts;
         opts.max_segment_po2 = max_po2; opts.circuit = circuit; opts.devices = {device, device}; opts.contexts_per_device = 1;
+        opts.deterministic_blinding = true;
+        const Digest image_id = default_image_id();
         auto prover = default_prover(opts);
         const Receipt receipt = prover->prove(session).receipt;
 
@@ -62,20 +65,34 @@ int main(int argc, char** argv) {
         if (back.segments.size() != po2s.size() || back.journal.decode() != session.journal) { std::fprintf(stderr, "round trip lost data\n"); return 2; }
         for (size_t i = 0; i < back.segments.size(); i++)
             if (back.segments[i].seal != receipt.segments[i].seal || back.segments[i].index != i) { std::fprintf(stderr, "round trip changed a seal\n"); return 2; }
-        back.verify(control_ids, circuit);
+        back.verify(image_id, control_ids, circuit);
 
         // error behaviour of the surface
         Receipt bad = back;
         bad.segments.back().seal[bad.segments.back().seal.size() / 2] ^= 1u;
-        EXPECT_THROW(bad.verify(control_ids, circuit), "segment");
+        EXPECT_THROW(bad.verify(image_id, control_ids, circuit), "segment");
         bad = back;
         bad.segments[0].index = 7;
-        EXPECT_THROW(bad.verify(control_ids, circuit), "segment index");
+        EXPECT_THROW(bad.verify(image_id, control_ids, circuit), "segment index");
         std::map<uint32_t, Digest> none;
-        EXPECT_THROW(back.verify(none, circuit), "no control id");
+        EXPECT_THROW(back.verify(image_id, none, circuit), "no control id");
+        // the claim chain: a replaced journal, another image id, swapped or dropped segments are all refused
+        bad = back;
+        bad.journal = Journal::encode("{\"iban\":\"CH0000000000000000000\"}");
+        EXPECT_THROW(bad.verify(image_id, control_ids, circuit), "journal digest");
+        { Digest other = image_id; other[0] ^= 1u; EXPECT_THROW(back.verify(other, control_ids, circuit), "image id"); }
+        if (back.segments.size() >= 2) {
+            bad = back;
+            bad.segments.pop_back();
+            EXPECT_THROW(bad.verify(image_id, control_ids, circuit), "does not halt");
+            bad = back;
+            std::swap(bad.segments[0].seal, bad.segments[1].seal);
+            EXPECT_THROW(bad.verify(image_id, control_ids, circuit), "");
+        }
+        back.verify_seals(control_ids, circuit);
         Receipt fake; fake.fake = true; fake.journal = back.journal;
         if (Receipt::from_json(fake.to_json()).journal.decode() != session.journal) return 2;
-        EXPECT_THROW(Receipt::from_json(fake.to_json()).verify(control_ids, circuit), "Fake");
+        EXPECT_THROW(Receipt::from_json(fake.to_json()).verify(image_id, control_ids, circuit), "Fake");
         { ProverOpts o = opts; o.hashfn = "sha-256"; EXPECT_THROW(Prover p(o), "poseidon2"); }
         { ProverOpts o = opts; o.receipt_kind = "groth16"; EXPECT_THROW(Prover p(o), "recursion"); }
         { ProverOpts o = opts; o.max_segment_po2 = 12; Prover p(o); if (max_po2 > 12) EXPECT_THROW(p.prove(session), "exceeds max_segment_po2"); }
