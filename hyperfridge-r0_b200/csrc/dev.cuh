@@ -27,7 +27,8 @@ struct KCtx {
     int bar_id = 0;           // 0: whole-CTA barrier; k > 0: named barrier k over `nt` threads (a "unit")
     HD void sync() const {
 #ifdef __CUDA_ARCH__
-        if (bar_id) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nt) : "memory");
+        if (bar_id && nt == 32) __syncwarp();  // a one-warp unit needs no hardware barrier
+        else if (bar_id) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nt) : "memory");
         else __syncthreads();
 #endif
     }
@@ -62,7 +63,7 @@ HD KCtx unit_ctx(const KCtx& cx, int unit, int UT) {
 
 // ---- TMA bulk copies (cp.async.bulk, global -> shared, completion on an mbarrier) -------------------------------------
 // Device only; the host emulator takes plain loops instead (callers switch on __CUDA_ARCH__).
-#ifdef __CUDA_ARCH__
+#if defined(__CUDACC__) && !defined(HFB200_EMU)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -70,6 +71,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(

@@ -249,101 +249,112 @@ struct GlobStridedIO {  // element (pos, batch) of a strided tile: row pos at st
 // SHP: the table holds canonical (w, w' = floor(w 2^32 / p)) pairs at tw[2 i], tw[2 i + 1] and multiplies use Shoup's form.
 // PF: software-pipelined loads (two register sets): the loads of the thread's next item are issued before the
 // butterflies of the current one, so a global-facing round does not sit on the long scoreboard.
-template <int R, bool INV, int K, int C, int L0, bool TWL = false, bool HF = false, bool SHP = false, bool PF = false, typename LD, typename ST>
-HD void round_t(const KCtx& cx, const uint32_t* tw, int k_, int c_, int l0_, const LD& L, const ST& S) {
-    const int k = K >= 0 ? K : k_, c = C >= 0 ? C : c_, l0 = L0 >= 0 ? L0 : l0_;
-    const uint32_t items = 1u << (k - R + c);
-    const uint32_t cmask = (1u << c) - 1u, lmask = (1u << l0) - 1u;
-    const bool laff = L.affine(l0, c), saff = S.affine(l0, c);
-    const uint32_t lstep = L.step(l0, c), sstep = S.step(l0, c);
-    const uint32_t nhigh_mask = (items >> (l0 + c)) - 1u;
-    auto split = [&](uint32_t it, uint32_t& batch, uint32_t& low, uint32_t& base) {
+// geometry of one item of a radix-2^R round
+template <int R, int K, int C, int L0, bool HF>
+struct RoundGeom {
+    int k, c, l0;
+    uint32_t items, cmask, lmask, nhigh_mask;
+    HD RoundGeom(int k_, int c_, int l0_) : k(K >= 0 ? K : k_), c(C >= 0 ? C : c_), l0(L0 >= 0 ? L0 : l0_) {
+        items = 1u << (k - R + c);
+        cmask = (1u << c) - 1u; lmask = (1u << l0) - 1u;
+        nhigh_mask = (items >> (l0 + c)) - 1u;
+    }
+    HD void split(uint32_t it, uint32_t& batch, uint32_t& low, uint32_t& base) const {
         batch = it & cmask;
         const uint32_t t = it >> c;
         low = HF ? (t >> (k - R - l0)) : (t & lmask);
         const uint32_t high = HF ? (t & nhigh_mask) : (t >> l0);
         base = (high << (l0 + R)) | low;
-    };
-    auto load = [&](uint32_t it, uint32_t* v) {
-        uint32_t batch, low, base;
-        split(it, batch, low, base);
-        if (laff) {
-            const uint32_t i0 = L.base(base, batch, c);
+    }
+};
+template <int R, int K, int C, int L0, bool HF, typename LD>
+HD void round_load_item(const RoundGeom<R, K, C, L0, HF>& g, uint32_t it, uint32_t* v, const LD& L) {
+    uint32_t batch, low, base;
+    g.split(it, batch, low, base);
+    if (L.affine(g.l0, g.c)) {
+        const uint32_t i0 = L.base(base, batch, g.c), lstep = L.step(g.l0, g.c);
 #pragma unroll
-            for (int j = 0; j < (1 << R); j++) v[j] = L.ld_i(i0 + (uint32_t)j * lstep);
-        } else {
+        for (int j = 0; j < (1 << R); j++) v[j] = L.ld_i(i0 + (uint32_t)j * lstep);
+    } else {
 #pragma unroll
-            for (int j = 0; j < (1 << R); j++) v[j] = L.ld_i(L.base(base + ((uint32_t)j << l0), batch, c));
-        }
-    };
-    auto compute_store = [&](uint32_t it, uint32_t* v) {
-        uint32_t batch, low, base;
-        split(it, batch, low, base);
-        if (!INV) {
+        for (int j = 0; j < (1 << R); j++) v[j] = L.ld_i(L.base(base + ((uint32_t)j << g.l0), batch, g.c));
+    }
+}
+// butterflies of levels l0+1..l0+R on the 2^R values of item `it` (already in v), then the store through S
+template <int R, bool INV, int K, int C, int L0, bool TWL, bool HF, bool SHP, typename ST>
+HD void round_compute_store_item(const RoundGeom<R, K, C, L0, HF>& g, const uint32_t* tw, uint32_t it, uint32_t* v, const ST& S) {
+    const int k = g.k, c = g.c, l0 = g.l0;
+    uint32_t batch, low, base;
+    g.split(it, batch, low, base);
+    if (!INV) {
 #pragma unroll
-            for (int q = 1; q <= R; q++) {
-                const int h = 1 << (q - 1);
+        for (int q = 1; q <= R; q++) {
+            const int h = 1 << (q - 1);
 #pragma unroll
-                for (int j = 0; j < (1 << R); j++) {
-                    if (j & h) continue;
-                    uint32_t x = v[j + h];
-                    if (!(L0 == 0 && (j & (h - 1)) == 0)) {
-                        const uint32_t ti = TWL ? (1u << (l0 + q - 1)) + ((uint32_t)(j & (h - 1)) << l0) + low : (low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q);
-                        x = SHP ? fmul_pair(x, tw, ti) : fmul(x, tw[ti]);
-                    }
-                    // an output that the next level multiplies by a twiddle stays in [0, 2p): both product forms take any
-                    // 32-bit first operand, so its range correction is dropped (decided at compile time)
-                    const int hn = h << 1;
-                    const bool lz0 = q < R && (j & hn) && !(L0 == 0 && (j & (hn - 1)) == 0);
-                    const bool lz1 = q < R && ((j + h) & hn) && !(L0 == 0 && ((j + h) & (hn - 1)) == 0);
-                    v[j + h] = lz1 ? fsub_lazy(v[j], x) : fsub(v[j], x);
-                    v[j] = lz0 ? fadd_lazy(v[j], x) : fadd(v[j], x);
+            for (int j = 0; j < (1 << R); j++) {
+                if (j & h) continue;
+                uint32_t x = v[j + h];
+                if (!(L0 == 0 && (j & (h - 1)) == 0)) {
+                    const uint32_t ti = TWL ? (1u << (l0 + q - 1)) + ((uint32_t)(j & (h - 1)) << l0) + low : (low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q);
+                    x = SHP ? fmul_pair(x, tw, ti) : fmul(x, tw[ti]);
                 }
-            }
-        } else {
-#pragma unroll
-            for (int q = R; q >= 1; q--) {
-                const int h = 1 << (q - 1);
-#pragma unroll
-                for (int j = 0; j < (1 << R); j++) {
-                    if (j & h) continue;
-                    const uint32_t a = v[j], b = v[j + h];
-                    v[j] = fadd(a, b);
-                    uint32_t d;
-                    if (!(L0 == 0 && (j & (h - 1)) == 0)) {
-                        const uint32_t ti = TWL ? (1u << (l0 + q - 1)) + ((uint32_t)(j & (h - 1)) << l0) + low : (low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q);
-                        d = fsub_lazy(a, b);  // in (0, 2p): the product takes any 32-bit first operand
-                        d = SHP ? fmul_pair(d, tw, ti) : fmul(d, tw[ti]);
-                    } else d = fsub(a, b);
-                    v[j + h] = d;
-                }
+                // an output that the next level multiplies by a twiddle stays in [0, 2p): both product forms take any
+                // 32-bit first operand, so its range correction is dropped (decided at compile time)
+                const int hn = h << 1;
+                const bool lz0 = q < R && (j & hn) && !(L0 == 0 && (j & (hn - 1)) == 0);
+                const bool lz1 = q < R && ((j + h) & hn) && !(L0 == 0 && ((j + h) & (hn - 1)) == 0);
+                v[j + h] = lz1 ? fsub_lazy(v[j], x) : fsub(v[j], x);
+                v[j] = lz0 ? fadd_lazy(v[j], x) : fadd(v[j], x);
             }
         }
-        if (saff) {
-            const uint32_t i0 = S.base(base, batch, c);
+    } else {
 #pragma unroll
-            for (int j = 0; j < (1 << R); j++) S.st_i(i0 + (uint32_t)j * sstep, v[j]);
-        } else {
+        for (int q = R; q >= 1; q--) {
+            const int h = 1 << (q - 1);
 #pragma unroll
-            for (int j = 0; j < (1 << R); j++) S.st_i(S.base(base + ((uint32_t)j << l0), batch, c), v[j]);
+            for (int j = 0; j < (1 << R); j++) {
+                if (j & h) continue;
+                const uint32_t a = v[j], b = v[j + h];
+                v[j] = fadd(a, b);
+                uint32_t d;
+                if (!(L0 == 0 && (j & (h - 1)) == 0)) {
+                    const uint32_t ti = TWL ? (1u << (l0 + q - 1)) + ((uint32_t)(j & (h - 1)) << l0) + low : (low + ((uint32_t)(j & (h - 1)) << l0)) << (k - l0 - q);
+                    d = fsub_lazy(a, b);  // in (0, 2p): the product takes any 32-bit first operand
+                    d = SHP ? fmul_pair(d, tw, ti) : fmul(d, tw[ti]);
+                } else d = fsub(a, b);
+                v[j + h] = d;
+            }
         }
-    };
+    }
+    if (S.affine(l0, c)) {
+        const uint32_t i0 = S.base(base, batch, c), sstep = S.step(l0, c);
+#pragma unroll
+        for (int j = 0; j < (1 << R); j++) S.st_i(i0 + (uint32_t)j * sstep, v[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < (1 << R); j++) S.st_i(S.base(base + ((uint32_t)j << l0), batch, c), v[j]);
+    }
+}
+template <int R, bool INV, int K, int C, int L0, bool TWL = false, bool HF = false, bool SHP = false, bool PF = false, typename LD, typename ST>
+HD void round_t(const KCtx& cx, const uint32_t* tw, int k_, int c_, int l0_, const LD& L, const ST& S) {
+    const RoundGeom<R, K, C, L0, HF> g(k_, c_, l0_);
+    const uint32_t items = g.items;
     if constexpr (PF) {
         const uint32_t nt = (uint32_t)cx.nt;
         uint32_t v0[1 << R], v1[1 << R];
         uint32_t it = (uint32_t)cx.tid;
-        if (it < items) load(it, v0);
+        if (it < items) round_load_item(g, it, v0, L);
         for (; it < items; it += 2 * nt) {
-            if (it + nt < items) load(it + nt, v1);
-            compute_store(it, v0);
-            if (it + 2 * nt < items) load(it + 2 * nt, v0);
-            if (it + nt < items) compute_store(it + nt, v1);
+            if (it + nt < items) round_load_item(g, it + nt, v1, L);
+            round_compute_store_item<R, INV, K, C, L0, TWL, HF, SHP>(g, tw, it, v0, S);
+            if (it + 2 * nt < items) round_load_item(g, it + 2 * nt, v0, L);
+            if (it + nt < items) round_compute_store_item<R, INV, K, C, L0, TWL, HF, SHP>(g, tw, it + nt, v1, S);
         }
     } else {
         for (uint32_t it = cx.tid; it < items; it += cx.nt) {
             uint32_t v[1 << R];
-            load(it, v);
-            compute_store(it, v);
+            round_load_item(g, it, v, L);
+            round_compute_store_item<R, INV, K, C, L0, TWL, HF, SHP>(g, tw, it, v, S);
         }
     }
 }
@@ -450,6 +461,18 @@ struct StridedKernel2 {
 };
 
 static constexpr int MID_UT = 64;  // threads per unit of the chunk-stage kernel for chunks up to 2^10 (larger chunks: 128 / 256)
+// MID_R5 = 1 (experiment, kept as a build option): the main-group chunk stage (a = 10, e = 2) as ONE WARP per (column, chunk):
+// radix-32 register rounds (32 values per lane), one shared-memory round trip for the inverse part and one for the x4 forward
+// part (instead of two each with radix 8/16), __syncwarp instead of named barriers, next column prefetched into registers.
+// Measured on B200 (profiles/r2_mid_r5_ncu_summary.txt): 14 % fewer warp instructions (1564 M against 1813 M per 192 columns)
+// but 254 registers -> 8 warps per SM; issue-active falls from 66 % to 56 % (stall "wait": two warps per scheduler cannot keep
+// the heavy-multiply and ALU pipes both fed) and the stage takes 4.86 ms per 192-column LDE against 4.74 ms.  Default stays 0.
+#ifndef MID_R5
+#define MID_R5 0
+#endif
+#ifndef MID_R5_UNITS
+#define MID_R5_UNITS 8
+#endif
 
 struct Mid2Args {
     const uint32_t* in;
@@ -489,7 +512,7 @@ struct Mid2Layout {
 template <int MA, int ME>
 struct MiddleKernel2 {
     static constexpr bool kBarrier = true;
-    static constexpr int PSB = (MA == 10 && ME == 2) ? 6 : 5;  // pad shift of the forward buffer B
+    static constexpr int PSB = (MA == 10 && ME == 2) ? (MID_R5 ? 7 : 6) : 5;  // pad shift of the forward buffer B
     static constexpr bool SHP = (MA == 10 && ME == 2);         // Shoup (w, w') pairs in twI / twF / G2 (host sets p.shp alike)
     HD static int A_(const Mid2Args& p) { return MA >= 0 ? MA : p.a; }
     HD static int E_(const Mid2Args& p) { return ME >= 0 ? ME : p.e; }
@@ -651,6 +674,17 @@ struct MiddleKernel2 {
             uint32_t* ubase = sm + L.unit0 + (uint32_t)u * L.unit_words;
             uint32_t* B = ubase + L.B;
             uint32_t* A = (fwd && p.alias) ? B : ubase + L.A;
+#if MID_R5 && defined(__CUDA_ARCH__)
+            uint32_t pf[32];
+            if constexpr (MA == 10 && ME == 2) {
+                const uint32_t col0 = cx.by * p.cols_per_block + (uint32_t)u;
+                if (intt && col0 < col_end) {
+                    const uint32_t* src0 = p.in + (uint64_t)col0 * p.in_stride + ((uint64_t)hi << p.a);
+#pragma unroll
+                    for (int j = 0; j < 32; j++) pf[j] = src0[(uint32_t)ux.tid + 32u * j];
+                }
+            }
+#endif
             for (uint32_t col = cx.by * p.cols_per_block + (uint32_t)u; col < col_end; col += (uint32_t)p.units) {
                 const SrcIO G{p.in + (uint64_t)col * p.in_stride + ((uint64_t)hi << p.a), G3, p.rt.i_lo, p.rt.i_hi, rb, 24 - p.n, intt ? gmode : 0};
                 const DstIO D{p.out + (uint64_t)col * p.out_stride + ((uint64_t)hi << (p.a + p.e)), G2, p.rt.f_lo, p.rt.f_hi, rb, 24 - p.n - p.e, gmode};
@@ -659,6 +693,29 @@ struct MiddleKernel2 {
                 if constexpr (MA == 10 && ME == 2) {  // host dispatches this instantiation for the fused iNTT+LDE and the expand-only LDE
                     // main-group schedule, all sizes compile-time: DIF 3+3 (+4 in registers), DIT (4 in registers +) 3+3
                     const SmemIOT<PSB> SB6{B};
+#if MID_R5
+                    if (intt) {
+                        const RoundGeom<5, 10, 0, 5, false> g1(10, 0, 5);
+#ifdef __CUDA_ARCH__
+                        // one item per lane: raw values of THIS column were fetched during the previous column (pf), the next
+                        // column's are requested before the butterflies start
+                        uint32_t v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j++) v[j] = gmode == 1 ? fmul(pf[j], G3[(uint32_t)ux.tid + 32u * j]) : (gmode == 2 ? fmul(pf[j], g3(p, rb, (uint32_t)ux.tid + 32u * j)) : pf[j]);
+                        if (col + (uint32_t)p.units < col_end) {
+                            const uint32_t* nsrc = p.in + (uint64_t)(col + (uint32_t)p.units) * p.in_stride + ((uint64_t)hi << p.a);
+#pragma unroll
+                            for (int j = 0; j < 32; j++) pf[j] = nsrc[(uint32_t)ux.tid + 32u * j];
+                        }
+                        round_compute_store_item<5, true, 10, 0, 5, true, false, true>(g1, twI, (uint32_t)ux.tid, v, SA);
+#else
+                        round_t<5, true, 10, 0, 5, true, false, true>(ux, twI, 10, 0, 5, G, SA);
+#endif
+                        ux.sync();
+                    }
+                    tail<5>(ux, p, rb, !intt, G, A, twI, twF, Gs, B, dst_coef, D); ux.sync();  // expand-only: coefficients straight from global
+                    round_t<5, false, 12, 0, 7, true, false, true>(ux, twF, 12, 0, 7, SB6, D);
+#else
                     if (intt) {
                         round_t<3, true, 10, 0, 7, true, false, true>(ux, twI, 10, 0, 7, G, SA); ux.sync();
                         round_t<3, true, 10, 0, 4, true, true, true>(ux, twI, 10, 0, 4, SA, SA); ux.sync();
@@ -666,6 +723,7 @@ struct MiddleKernel2 {
                     tail<4>(ux, p, rb, !intt, G, A, twI, twF, Gs, B, dst_coef, D); ux.sync();  // expand-only: coefficients straight from global
                     round_t<3, false, 12, 0, 6, true, false, true>(ux, twF, 12, 0, 6, SB6, SB6); ux.sync();
                     round_t<3, false, 12, 0, 9, true, false, true>(ux, twF, 12, 0, 9, SB6, D);
+#endif
                 } else {
                 bool from_global = true;
                 if (intt) {
@@ -703,6 +761,10 @@ struct MiddleKernel2 {
         }
     }
 };
+
+}  // namespace hf
+#include "ntt_tma.cuh"  // strided stages of the 2^10-row plans through TMA tensor maps (device builds only)
+namespace hf {
 
 // ---- host-side planning / launching ---------------------------------------------------------------
 struct NttPlan { int a, b, c; };
@@ -779,6 +841,9 @@ struct Ntt {
 
     void strided(const uint32_t* in, uint64_t in_stride, uint32_t* out, uint64_t out_stride, uint32_t ncols, int a, int b, int c, bool inv) {
         if (b == 0) { if (in != out) throw Err("ntt: strided pass with b = 0 must be in place"); return; }
+#ifndef HFB200_EMU
+        if (strided_tma(dev, rt, in, in_stride, out, out_stride, ncols, a, b, inv)) return;  // 2^10 rows: TMA-pipelined kernel (ntt_tma.cuh)
+#endif
         Str2Args p{};
         p.in = in; p.out = out; p.in_stride = in_stride; p.out_stride = out_stride; p.ncols = ncols;
         p.a = a; p.b = b; p.c = c; p.inv = inv ? 1 : 0; p.rt = rt;
@@ -847,6 +912,9 @@ struct Ntt {
 #else
         p.ut = a <= 10 ? MID_UT : (a == 11 ? 128 : 256);
         p.alias = (intt && fwd && (1 << (a - RF)) <= p.ut) ? 1 : 0;
+#if MID_R5
+        if (a == 10 && e == 2 && fwd && !(p.flags & MID_GFLY)) { p.ut = 32; p.alias = intt ? 1 : 0; }  // one warp per (column, chunk), 32 values per lane
+#endif
 #endif
 #ifdef HFB200_EMU
         p.ut = MID_UT;
@@ -858,6 +926,9 @@ struct Ntt {
         // 256-thread CTAs per SM for chunks up to 2^10
         const size_t budget = main_cfg ? 226 * 1024 : (a <= 10 ? 112 * 1024 : 200 * 1024);
         int units = (main_cfg ? 512 : 256) / p.ut;
+#if MID_R5 && !defined(HFB200_EMU)
+        if (main_cfg) units = MID_R5_UNITS;
+#endif
         for (;; units >>= 1) {
             p.units = units;
             if ((size_t)Mid2Layout(p).total * 4 <= budget || units == 1) break;
@@ -869,7 +940,11 @@ struct Ntt {
         if (groups > max_groups) groups = max_groups;
         p.cols_per_block = (ncols + groups - 1) / groups;
         groups = (ncols + p.cols_per_block - 1) / p.cols_per_block;
+#if MID_R5
+        if (main_cfg) dev->launch<MiddleKernel2<10, 2>, 32 * MID_R5_UNITS, 1>((unsigned)chunks, groups, p.units * p.ut, (size_t)Mid2Layout(p).total * 4, p);
+#else
         if (main_cfg) dev->launch<MiddleKernel2<10, 2>, 512, 1>((unsigned)chunks, groups, p.units * p.ut, (size_t)Mid2Layout(p).total * 4, p);
+#endif
         else dev->launch<MiddleKernel2<-1, -1>, 256, 2>((unsigned)chunks, groups, p.units * p.ut, (size_t)Mid2Layout(p).total * 4, p);
     }
 
