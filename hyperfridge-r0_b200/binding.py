@@ -49,7 +49,7 @@ class CircuitDesc(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("ms_total", C.c_float), ("ms_device", C.c_float), ("ms_h2d", C.c_float), ("ms_ntt_main", C.c_float), ("ms_hash_main", C.c_float),
                 ("ms_accum", C.c_float), ("ms_check", C.c_float), ("ms_deep", C.c_float), ("ms_fri", C.c_float),
-                ("launches", C.c_uint64), ("ntt_main_bytes", C.c_uint64)]
+                ("launches", C.c_uint64), ("ntt_main_bytes", C.c_uint64), ("host_syncs", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -206,7 +206,7 @@ const char* hfb200_last_stats(hfb200_ctx* ctx, hfb200_stats* out) {
     const Stats& s = ctx->p.stats;
     out->ms_total = s.ms_total; out->ms_device = s.ms_device; out->ms_h2d = s.ms_h2d; out->ms_ntt_main = s.ms_ntt_main; out->ms_hash_main = s.ms_hash_main;
     out->ms_accum = s.ms_accum; out->ms_check = s.ms_check; out->ms_deep = s.ms_deep; out->ms_fri = s.ms_fri;
-    out->launches = s.launches; out->ntt_main_bytes = s.ntt_main_bytes;
+    out->launches = s.launches; out->ntt_main_bytes = s.ntt_main_bytes; out->host_syncs = s.host_syncs;
     API_CATCH
 }
 uint64_t hfb200_total_launches(const hfb200_ctx* ctx) { return ctx ? ctx->p.dev.launches : 0; }

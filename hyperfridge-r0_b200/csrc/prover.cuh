@@ -11,8 +11,21 @@
 #include "circuit.cuh"
 #include "deep.cuh"
 #include "jit.cuh"
+#ifndef HFB200_EMU
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges are no-ops unless a tool (nsys) injects the NVTX library
+#endif
 
 namespace hf {
+
+// NVTX range per prover stage on the host thread that enqueues it (tracing).  Stage names match hfb200_stats.
+struct StageRange {
+#ifndef HFB200_EMU
+    explicit StageRange(const char* name) { nvtxRangePushA(name); }
+    ~StageRange() { nvtxRangePop(); }
+#else
+    explicit StageRange(const char*) {}
+#endif
+};
 
 static constexpr uint32_t QUERIES = 50, INV_RATE = 4, FRI_FOLD = 16, FRI_MIN_DEGREE = 256, CHECK_SIZE = 16;
 
@@ -41,7 +54,7 @@ struct Arena {
 
 struct Stats {
     float ms_total = 0, ms_device = 0, ms_h2d = 0, ms_ntt_main = 0, ms_hash_main = 0, ms_accum = 0, ms_check = 0, ms_deep = 0, ms_fri = 0;
-    uint64_t launches = 0, ntt_main_bytes = 0;
+    uint64_t launches = 0, ntt_main_bytes = 0, host_syncs = 0;
 };
 
 struct Tree { uint32_t* matrix; uint64_t col_stride; uint32_t rows, cols; uint32_t* nodes; };
@@ -99,6 +112,13 @@ struct Prover {
     cudaEvent_t copy_gate = nullptr;
 #endif
     float stage_ms[8] = {0};
+    // small host->device parameter uploads (mix powers, weights, descriptors) go through a pinned staging area so that the
+    // copy is truly asynchronous and the source needs no stream synchronisation to stay alive
+    uint8_t* stage_h = nullptr;
+    size_t stage_cap = 0, stage_off = 0;
+    std::string metrics_path;     // HFB200_METRICS=<file|stderr>: one JSON line per proved segment
+    double metrics_peak_gbs = 0;  // HFB200_HBM_PEAK_GBS: denominator for the NTT/LDE roofline fraction in that line
+    uint64_t host_syncs = 0, host_syncs_at_begin = 0;
 
     void init(int device, uint32_t max_po2_, uint32_t wc, uint32_t wd, uint32_t wa, const IrTap* taps = nullptr, size_t n_taps = 0,
               const IrStep* steps = nullptr, size_t n_steps = 0, uint32_t ret = 0, uint32_t n_mix_ir = 0) {
@@ -136,9 +156,37 @@ struct Prover {
         arena.cap = arena_bytes(max_po2);
         arena.base = (uint8_t*)dev.alloc(arena.cap);
         if (const char* env = std::getenv("HFB200_DEBUG_CHECKPOINTS")) debug_checkpoints = std::atoi(env) != 0;
+        if (const char* env = std::getenv("HFB200_METRICS")) metrics_path = env;
+        if (const char* env = std::getenv("HFB200_HBM_PEAK_GBS")) metrics_peak_gbs = std::atof(env);
+        stage_cap = (size_t)4 << 20;
+        if (gen.active) stage_cap += (size_t)gen.n_mixpow * sizeof(E4);
+#ifndef HFB200_EMU
+        CUDA_CHECK(cudaHostAlloc((void**)&stage_h, stage_cap, cudaHostAllocDefault));
+#else
+        stage_h = (uint8_t*)std::malloc(stage_cap);
+#endif
     }
+    // asynchronous upload of a small host array: staged in pinned memory when it fits (no sync needed), else copy + sync
+    void h2d_small(void* d, const void* h, size_t bytes) {
+        const size_t need = (bytes + 63) & ~(size_t)63;
+        if (stage_h && stage_off + need <= stage_cap) {
+            std::memcpy(stage_h + stage_off, h, bytes);
+            dev.h2d(d, stage_h + stage_off, bytes);
+            stage_off += need;
+        } else {
+            dev.h2d(d, h, bytes);
+            sync();
+        }
+    }
+    void sync() { dev.sync(); host_syncs++; }
     void destroy() {
         dev.free(arena.base);
+#ifndef HFB200_EMU
+        if (stage_h) cudaFreeHost(stage_h);
+#else
+        std::free(stage_h);
+#endif
+        stage_h = nullptr;
         jit.destroy();
         gen.destroy(&dev);
         cir.destroy(&dev);
@@ -181,6 +229,38 @@ struct Prover {
 #endif
     }
 
+    static void nvtx_push(const char* name) {
+#ifndef HFB200_EMU
+        nvtxRangePushA(name);
+#else
+        (void)name;
+#endif
+    }
+    static void nvtx_pop() {
+#ifndef HFB200_EMU
+        nvtxRangePop();
+#endif
+    }
+    // one JSON line per segment: po2, stage milliseconds, algorithmic bytes and GB/s of the NTT/LDE
+    // pipeline, its fraction of the HBM peak when HFB200_HBM_PEAK_GBS is given, launches and host synchronisations
+    void emit_metrics() const {
+        if (metrics_path.empty()) return;
+        char buf[1024];
+        const double gbs = stats.ms_ntt_main > 0 ? (double)stats.ntt_main_bytes / (stats.ms_ntt_main * 1e-3) / 1e9 : 0.0;
+        int n = std::snprintf(buf, sizeof buf,
+            "{\"po2\": %u, \"columns\": %u, \"device\": %d, \"ms_total\": %.3f, \"ms_device\": %.3f, \"ms_h2d\": %.3f, \"ms_ntt_main\": %.3f, \"ms_hash_main\": %.3f, "
+            "\"ms_accum\": %.3f, \"ms_check\": %.3f, \"ms_deep\": %.3f, \"ms_fri\": %.3f, \"launches\": %llu, \"host_syncs\": %llu, \"ntt_main_bytes\": %llu, \"ntt_main_gbs\": %.1f",
+            po2, cir.n_regs(), device_id, stats.ms_total, stats.ms_device, stats.ms_h2d, stats.ms_ntt_main, stats.ms_hash_main, stats.ms_accum, stats.ms_check, stats.ms_deep,
+            stats.ms_fri, (unsigned long long)stats.launches, (unsigned long long)stats.host_syncs, (unsigned long long)stats.ntt_main_bytes, gbs);
+        if (metrics_peak_gbs > 0 && n > 0 && (size_t)n < sizeof buf) n += std::snprintf(buf + n, sizeof buf - n, ", \"hbm_peak_gbs\": %.1f, \"ntt_main_frac\": %.4f", metrics_peak_gbs, gbs / metrics_peak_gbs);
+        if (n <= 0 || (size_t)n >= sizeof buf - 3) return;
+        buf[n++] = '}'; buf[n++] = '\n'; buf[n] = 0;
+        static std::mutex mu;  // contexts on several threads share the sink
+        std::lock_guard<std::mutex> lock(mu);
+        if (metrics_path == "stderr") { std::fputs(buf, stderr); return; }
+        if (FILE* f = std::fopen(metrics_path.c_str(), "a")) { std::fputs(buf, f); std::fclose(f); }
+    }
+
     void cp_add(const std::string& name, const uint32_t* w, size_t n) { cps.emplace_back(name, std::vector<uint32_t>(w, w + n)); }
     void cp_add(const std::string& name, const E4& e) { cp_add(name, e.c, 4); }
 
@@ -212,7 +292,7 @@ struct Prover {
             top = *cached;
         } else {
             dev.d2h(top.data(), t.nodes, top.size() * 4);
-            dev.sync();
+            sync();  // the root feeds the transcript: a true dependency
         }
         if (keep) *keep = top;
         proof.insert(proof.end(), top.begin() + (size_t)ms.top_size * 8, top.end());
@@ -240,6 +320,8 @@ struct Prover {
         proof.clear(); cps.clear(); rng = HostRng(); stats = Stats();
         for (auto& s : stage_ms) s = 0;
         launches_at_begin = dev.launches;
+        host_syncs_at_begin = host_syncs;
+        stage_off = 0;
         blind_key = make_blind_key(blind);
         // every argument check comes BEFORE the first copy is queued: an error return must not leave DMA from caller memory in flight
         for (uint32_t i = 0; i < N_GLOBAL; i++) if (globals_h[i] >= P) throw Err("globals: non-canonical field element");
@@ -278,8 +360,10 @@ struct Prover {
             const size_t D = 4 * N;
             commit_tree(Tree{ev[GROUP_CODE], D, (uint32_t)D, cir.cd.w_code, nodes[GROUP_CODE]}, "code_root", nullptr, &control_top);
         } else {
+            StageRange r("hfb200:commit_code");
             commit_group(GROUP_CODE, "code_root", 1, 2, 3);
         }
+        StageRange r_data("hfb200:commit_data");
         if (chunked) {
 #ifndef HFB200_EMU
             const size_t D = 4 * N;
@@ -369,17 +453,18 @@ struct Prover {
         const uint32_t W = cir.n_regs(), T = cir.n_taps;
 
         mark(5);
-        dev.h2d(d_mix, mix.data(), mix.size() * 4);
+        h2d_small(d_mix, mix.data(), mix.size() * 4);
         if (accum_h) dev.h2d(tr[GROUP_ACCUM], accum_h, (size_t)cd.w_accum * N * 4);
         else if (gen.active) throw Err("data-defined circuit: step_accum is the caller's (pass the accum columns to hfb200_segment_finish)");
         else step_accum();
         mark(6);
-        commit_group(GROUP_ACCUM, "accum_root", 6, 7, 8);  // ends with a stream sync: events 5..8 are complete
+        { StageRange r("hfb200:commit_accum"); commit_group(GROUP_ACCUM, "accum_root", 6, 7, 8); }  // ends with a stream sync: events 5..8 are complete
         stage_ms[3] = between(5, 6);
         stage_ms[1] += between(6, 7);
         stage_ms[2] += between(7, 8);
 
         // ---- check polynomial ----
+        nvtx_push("hfb200:check");
         const E4 poly_mix = rng.random_ext();
         cp_add("poly_mix", poly_mix);
         uint32_t yinv4[4];
@@ -393,16 +478,15 @@ struct Prover {
             E4 cur = e4_one();
             for (auto& m : mp) { m = cur; cur = e4_mul(cur, poly_mix); }
             E4* d_mp = arena.take<E4>(mp.size());
-            dev.h2d(d_mp, mp.data(), mp.size() * sizeof(E4));
+            h2d_small(d_mp, mp.data(), mp.size() * sizeof(E4));
             uint32_t* d_gl = arena.take<uint32_t>(N_GLOBAL);
-            dev.h2d(d_gl, globals, N_GLOBAL * 4);
+            h2d_small(d_gl, globals, N_GLOBAL * 4);
             if (jit.ready) {
                 JitEvalArgs ja{};
                 ja.ev[0] = ev[GROUP_ACCUM]; ja.ev[1] = ev[GROUP_CODE]; ja.ev[2] = ev[GROUP_DATA];
                 ja.check = check; ja.mixpow = d_mp; ja.mix = d_mix; ja.globals = d_gl; ja.po2 = po2;
                 for (int s_ = 0; s_ < 4; s_++) ja.yinv[s_] = yinv4[s_];
                 jit.launch(dev, ja, D);
-                dev.sync();
             } else {
             GenEvalArgs a{};
             a.ev[0] = ev[GROUP_ACCUM]; a.ev[1] = ev[GROUP_CODE]; a.ev[2] = ev[GROUP_DATA];
@@ -416,7 +500,6 @@ struct Prover {
             if (per_row * R + (N_GLOBAL + gen.n_mix) * 4 > 220 * 1024) throw Err("data-defined circuit: too many live values for the interpreter's shared-memory slot file");
             a.rows_per_block = R;
             dev.launch<GenEvalCheckKernel, 128, 1>((unsigned)((D + R - 1) / R), 1, (int)R, per_row * R + (N_GLOBAL + gen.n_mix) * 4 + 16, a);
-            dev.sync();
             }
         } else {
             const uint32_t nc = cd.n_constraints();
@@ -424,7 +507,7 @@ struct Prover {
             E4 cur = e4_one();
             for (auto& m : mp) { m = cur; cur = e4_mul(cur, poly_mix); }
             E4* d_mp = arena.take<E4>(nc);
-            dev.h2d(d_mp, mp.data(), nc * sizeof(E4));
+            h2d_small(d_mp, mp.data(), nc * sizeof(E4));
             EvalCheckArgs a{};
             a.ev_accum = ev[GROUP_ACCUM]; a.ev_code = ev[GROUP_CODE]; a.ev_data = ev[GROUP_DATA];
             a.check = check; a.mixpow = d_mp; a.mix = d_mix; a.global0 = globals[0];
@@ -432,7 +515,6 @@ struct Prover {
             a.po2 = po2; a.cd = cd;
             a.rows_per_block = 128;
             dev.launch<EvalCheckKernel, 128, 1>((unsigned)((D + 127) / 128), 1, 128, (size_t)nc * sizeof(E4) + (size_t)6 * cd.n_free * 2 + 16, a);
-            dev.sync();  // mp must outlive the copy
         }
         // 4 polys of 4N evaluations -> coefficients (no zk_shift); bit-reversed order makes them 16 polys of N
         ntt.interpolate(check, D, check, D, 4, (int)po2 + 2, false);
@@ -441,6 +523,8 @@ struct Prover {
         mark(9);
         commit_tree(Tree{ev_check, D, (uint32_t)D, CHECK_SIZE, nodes_check}, "check_root");
         stage_ms[4] = between(8, 9);
+        nvtx_pop();
+        nvtx_push("hfb200:deep");
 
         // ---- DEEP: evaluations at z ----
         const E4 z = rng.random_ext();
@@ -456,9 +540,8 @@ struct Prover {
             E4 cur = z4;
             for (uint32_t k = 0; k < po2; k++) { xs[k] = cur; cur = e4_mul(cur, cur); }
             E4* d_xs = arena.take<E4>(po2);
-            dev.h2d(d_xs, xs.data(), po2 * sizeof(E4));
+            h2d_small(d_xs, xs.data(), po2 * sizeof(E4));
             dev.launch<PowBitrevKernel, 256, 1>((unsigned)((N + 255) / 256), 1, 256, 0, W4, (const E4*)d_xs, po2);
-            dev.sync();
         }
         std::vector<E4> coeff_u(T + CHECK_SIZE);
         std::vector<uint32_t> reg_tap(W);
@@ -477,7 +560,7 @@ struct Prover {
             std::vector<E4> h_ev((size_t)GEN_MAX_BACKS * W), h_evc((size_t)2 * CHECK_SIZE);
             dev.d2h(h_ev.data(), d_ev, h_ev.size() * sizeof(E4));
             dev.d2h(h_evc.data(), d_evc, h_evc.size() * sizeof(E4));
-            dev.sync();
+            sync();
             for (const GenReg& r : gen.regs) {
                 E4 xs[4], ys[4];
                 for (uint32_t k = 0; k < r.size; k++) {
@@ -495,7 +578,7 @@ struct Prover {
         dot_group(check, CHECK_SIZE, 0, W4, d_evals + goff[3]);
         std::vector<E4> h_evals((size_t)2 * (W + CHECK_SIZE));
         dev.d2h(h_evals.data(), d_evals, h_evals.size() * sizeof(E4));
-        dev.sync();
+        sync();  // the tap evaluations feed the transcript: a true dependency
         // taps order: (group, column, back).  coeff_u: per register, interpolant through its tap points.
         {
             const E4 x0 = z, x1 = e4_scale(z, back_one);
@@ -530,7 +613,7 @@ struct Prover {
         E4 Vc = e4_zero();
         for (uint32_t c = 0; c < CHECK_SIZE; c++) Vc = e4_add(Vc, e4_mul(reg_mix[n_regs + c], coeff_u[T + c]));
         E4* d_regmix = arena.take<E4>(n_regs + CHECK_SIZE);
-        dev.h2d(d_regmix, reg_mix.data(), reg_mix.size() * sizeof(E4));
+        h2d_small(d_regmix, reg_mix.data(), reg_mix.size() * sizeof(E4));
         uint32_t* S0 = arena.take<uint32_t>(4 * N);
         uint32_t* S1 = arena.take<uint32_t>(4 * N);
         uint32_t* fin = arena.take<uint32_t>(4 * N);
@@ -561,12 +644,11 @@ struct Prover {
             ga.combo_start[C] = (uint32_t)rc_sorted.size();
             uint32_t* d_rc = arena.take<uint32_t>(rc_sorted.size());
             E4* d_rm = arena.take<E4>(rm_sorted.size());
-            dev.h2d(d_rc, rc_sorted.data(), rc_sorted.size() * 4);
-            dev.h2d(d_rm, rm_sorted.data(), rm_sorted.size() * sizeof(E4));
+            h2d_small(d_rc, rc_sorted.data(), rc_sorted.size() * 4);
+            h2d_small(d_rm, rm_sorted.data(), rm_sorted.size() * sizeof(E4));
             for (int g = 0; g < 3; g++) ga.tr[g] = tr[g];
             ga.regcol = d_rc; ga.regmix = d_rm; ga.S = S1; ga.INV = INV; ga.INV4 = INV4; ga.out = fin; ga.po2 = po2; ga.rt = ntt.rt;
             dev.launch<DeepMixKernelG, 256, 1>((unsigned)((N + 255) / 256), 1, 256, 0, ga);
-            dev.sync();
         } else {
             DeepMixArgs da{};
             da.U0 = da.U1a = da.U1b = e4_zero();
@@ -581,11 +663,11 @@ struct Prover {
         }
         ntt.interpolate(fin, N, fin, N, 4, (int)po2, true);  // bit-reversed coefficients of the FRI polynomial
         mark(10);
-        dev.sync();  // reg_mix upload done; stage boundary
-        stage_ms[5] = between(9, 10);
+        nvtx_pop();
+        nvtx_push("hfb200:fri");
         if (debug_checkpoints) {
             std::vector<uint32_t> fc(4 * N);
-            dev.d2h(fc.data(), fin, fc.size() * 4); dev.sync();
+            dev.d2h(fc.data(), fin, fc.size() * 4); sync();
             const Digest8 d = host_hash_elems(fc.data(), fc.size());
             cp_add("final_poly_hash", d.w, 8);
         }
@@ -619,7 +701,7 @@ struct Prover {
             uint32_t* nat = arena.take<uint32_t>(4 * n);
             dev.launch<BitRevKernel, 256, 1>((unsigned)((4 * n + 255) / 256), 1, 256, 0, (const uint32_t*)coeffs, nat, 4u, (uint32_t)ilog2(n));
             std::vector<uint32_t> fc(4 * n);
-            dev.d2h(fc.data(), nat, fc.size() * 4); dev.sync();
+            dev.d2h(fc.data(), nat, fc.size() * 4); sync();  // the final coefficients feed the transcript
             proof.insert(proof.end(), fc.begin(), fc.end());
             const Digest8 d = host_hash_elems(fc.data(), fc.size());
             rng.mix(d.w);
@@ -646,14 +728,16 @@ struct Prover {
             cp_add("query_positions", positions.data(), positions.size());
             OpenDesc* d_descs = arena.take<OpenDesc>(descs.size());
             uint32_t* d_out = arena.take<uint32_t>(off);
-            dev.h2d(d_descs, descs.data(), descs.size() * sizeof(OpenDesc));
+            h2d_small(d_descs, descs.data(), descs.size() * sizeof(OpenDesc));
             dev.launch<OpenKernel, 128, 1>((unsigned)descs.size(), 1, 128, 0, (const OpenDesc*)d_descs, d_out);
             const size_t at = proof.size();
             proof.resize(at + off);
             mark(11);
             dev.d2h(proof.data() + at, d_out, (size_t)off * 4);
-            dev.sync();
+            sync();
         }
+        nvtx_pop();
+        stage_ms[5] = between(9, 10);
         stage_ms[6] = between(10, 11);
         stats.ms_h2d = stage_ms[0]; stats.ms_ntt_main = stage_ms[1]; stats.ms_hash_main = stage_ms[2]; stats.ms_accum = stage_ms[3];
         stats.ms_check = stage_ms[4]; stats.ms_deep = stage_ms[5]; stats.ms_fri = stage_ms[6];
@@ -661,6 +745,8 @@ struct Prover {
         stats.ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
         stats.launches = dev.launches - launches_at_begin;
         stats.ntt_main_bytes = 28ull * W * N;
+        stats.host_syncs = host_syncs - host_syncs_at_begin;
+        emit_metrics();
         seal_out = proof;
     }
 

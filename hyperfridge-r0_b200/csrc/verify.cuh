@@ -234,7 +234,7 @@ static inline void verify_segment(const VCircuit& vc, const uint32_t* seal, size
     uint32_t globals[N_GLOBAL];
     iop.read_elems(globals, N_GLOBAL);
     const uint32_t po2 = iop.read_u32();
-    if (po2 < 11 || po2 > 24) vfail("po2 out of range");
+    if (po2 < 12 || po2 > 24) vfail("po2 out of range");  // the prover (and the oracle) start at 12
     if (po2_out) *po2_out = po2;
     iop.commit(host_hash_elems(globals, N_GLOBAL));
     const size_t N = (size_t)1 << po2, domain = N * V_INV_RATE;

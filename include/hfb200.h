@@ -179,7 +179,13 @@ typedef struct {
     float ms_fri;          /* FRI rounds + query openings                                                 */
     uint64_t launches;     /* kernels launched for the segment                                            */
     uint64_t ntt_main_bytes; /* algorithmic bytes of ms_ntt_main: 28 * w * N (8 iNTT + 20 LDE)            */
+    uint64_t host_syncs;   /* stream synchronisations of the segment (each one a transcript dependency: a root, the tap  */
+                           /* evaluations, the final FRI coefficients, the openings)                                       */
 } hfb200_stats;
+/* Tracing: every stage is an NVTX range on the enqueuing host thread ("hfb200:commit_code", "...:commit_data",
+ * "...:commit_accum", "...:check", "...:deep", "...:fri"), visible in nsys; with HFB200_METRICS=<file|stderr> in the environment every
+ * proved segment appends one JSON line {po2, columns, device, stage ms, launches, host_syncs, ntt_main_bytes, ntt_main_gbs[, hbm_peak_gbs,
+ * ntt_main_frac when HFB200_HBM_PEAK_GBS is set]}. */
 const char* hfb200_last_stats(hfb200_ctx* ctx, hfb200_stats* out);
 uint64_t hfb200_total_launches(const hfb200_ctx* ctx);
 
