@@ -28,7 +28,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "po2=20 segments/sec (synthetic rv32im-shaped segment, W=256); camt53 proof seconds = 37 segments / value"
+METRIC = "po2=20 segments/sec (synthetic rv32im-shaped segment, W=256); camt53 proof seconds measured on a 37-segment proof (camt53.proof_seconds)"
 UNIT = "segments/s"
 WIDTHS = (16, 192, 48)
 CAMT53_SEGMENTS = 37  # /root/reference/docs/runtime.md:50 (segment_count of the test camt53 proof)
@@ -120,7 +120,9 @@ def run_oracle_sample(po2, repeats=1):
 
 def reference_arm(args):
     """`--impl reference`: the reference's CPU implementation of the path on the box's host cores.  The real one
-    (risc0 3.0.5 Rust crates) cannot be built here, so this is the oracle port (kind = "port")."""
+    (risc0 3.0.5 Rust crates) cannot be built here, so this is the oracle port (kind = "port").  Every step proves a bounded
+    sample segment (2^sample_po2 cycles, W = 256); after the K timed steps ONE real po2 = 20, W = 256 segment -- bench.py's own
+    configuration -- is proved and timed, and `value` is that measurement (the scaled sample is reported beside it)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -128,14 +130,23 @@ def reference_arm(args):
     run_oracle_sample(po2, max(0, args.warmup)) if args.warmup else None
     t0 = time.perf_counter()
     times, cores = run_oracle_sample(po2, args.steps)
-    wall = time.perf_counter() - t0
     per = sum(times) / len(times)
-    scale = float(1 << (20 - po2))
-    value = 1.0 / (per * scale)
-    sample = "oracle CPU restatement (kind=port), %d threads, one W=256 segment of 2^%d cycles per step, scaled x%d linearly in cycles to po2=20" % (cores, po2, int(scale))
+    scale = float(1 << (args.po2 - po2))
+    sample_value = 1.0 / (per * scale)
+    full = None
+    if not args.no_full_size:
+        full_times, _ = run_oracle_sample(args.po2, 1)
+        full = full_times[0]
+    wall = time.perf_counter() - t0
+    value = 1.0 / full if full else sample_value
+    sample = "oracle CPU restatement (kind=port), %d threads: K steps of one W=256 segment of 2^%d cycles (%.2f s each; x%d linear in cycles = %.4f segments/s)" % (
+        cores, po2, per, int(scale), sample_value)
+    if full:
+        sample += "; then ONE real po2=%d W=256 segment: %.1f s = the value reported" % (args.po2, full)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (BabyBear mod p)", "data": "synthetic",
-            "config": {"workload": "configs[1]: single synthetic rv32im-shaped segment, po2=20, W=256 (16 code + 192 data + 48 accum)", "sample_po2": po2,
+            "config": {"workload": "configs[1]: single synthetic rv32im-shaped segment, po2=%d, W=256 (16 code + 192 data + 48 accum)" % args.po2, "po2": args.po2,
+                       "sample_po2": po2, "full_size_measured": bool(full), "full_size_seconds": full, "scaled_sample_segments_per_s": sample_value,
                        "camt53_proof_seconds": CAMT53_SEGMENTS / value, "camt53_segments": CAMT53_SEGMENTS},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -209,6 +220,7 @@ def main():
     ap.add_argument("--po2", type=int, default=20)
     ap.add_argument("--sample-po2", type=int, default=0, help="reference arm: size of the CPU sample segment (default: chosen from steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-size", action="store_true", help="CPU legs: skip the one real po2-sized oracle segment (sample only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-control-cache", action="store_true", help="skip the informational e2e leg with the control group kept on the device")
     ap.add_argument("--no-camt53", action="store_true", help="skip the measured 37-segment proof")
@@ -364,7 +376,7 @@ def main():
         e2e_value = world * F * args.steps / wall_e
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(F * ((WIDTHS[0] + WIDTHS[1]) * N * 4 + 128 + 4 * WIDTHS[2])),
                "d2h_bytes_per_step": int(F * len(seal_h[0]) * 4), "ms_per_step": wall_e * 1e3 / args.steps, "host_wall_ms_per_step": host_wall_e * 1e3 / args.steps, "ms_code_h2d_span_per_segment": h2d_ms[0] / args.steps, "h2d_note": "span of the code-column copy on context 0's stream (it queues behind the other contexts' data copies on the copy engine; those contexts keep the SMs busy meanwhile)",
-               "camt53_proof_seconds": CAMT53_SEGMENTS / e2e_value, "host_memory": "pinned (hfb200_host_alloc)"}
+               "host_memory": "pinned (hfb200_host_alloc)"}
         # ---------------- the same e2e call with the control group kept on the device (opt-in, informational) ----------------
         # The control (code) columns depend on (circuit, po2) only; hfb200_control_root commits them once and segments then
         # pass code == NULL: identical seals, one LDE + Merkle tree of 16 columns and 64 MiB of H2D less per segment.  NOT the
@@ -404,14 +416,14 @@ def main():
     achieved = ntt_bytes / (ntt_ms * 1e-3) / 1e9 if ntt_ms > 0 else 0.0
     traffic = None
     try:  # measured DRAM bytes per trace element of the three NTT/LDE kernels (one ncu --set full capture, profiles/)
-        with open(os.path.join(ROOT, "profiles", "r1_ntt_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_ntt_traffic.json")) as f:
             traffic = float(json.load(f)["bytes_per_trace_element"]) * W * N
     except Exception:
         pass
-    roofline = {"kernel": "NTT/LDE pipeline of the 3 main groups: StridedKernel(DIF) + MiddleKernel(fused iNTT.zk_shift.expand.NTT chunk stage) + StridedKernel(DIT), 9 launches/segment",
+    roofline = {"kernel": "NTT/LDE pipeline of the 3 main groups: strided_tma_kernel<inverse> (TMA tensor-map tiles, 3-buffer pipeline) + MiddleKernel2 (fused iNTT.zk_shift.expand.NTT chunk stage) + strided_tma_kernel<forward>, 9 launches/segment",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes": ntt_bytes, "ms": ntt_ms, "peak_source": peak_src,
-                "note": "traffic = dram__bytes_read+write of the 3 kernels from ncu (profiles/r1_ntt_traffic.json) scaled to W*N elements; by design 60*W*N (8+20+32 B per element over the three passes) vs 28*W*N algorithmic; the binding unit is the integer-multiply pipe, not HBM (DESIGN.md section 5)"}
+                "note": "traffic = dram__bytes_read+write of the 3 kernels from one ncu --set full capture of THIS round's kernels (profiles/r2_ntt_traffic.json, 59.2 B per trace element) scaled to W*N elements; by design 60*W*N (8+20+32 B per element over the three passes) vs 28*W*N algorithmic; the binding units are the integer-multiply and ALU pipes, not HBM (DESIGN.md section 5)"}
     # Poseidon2 (integer-ALU bound, no HBM roofline): permutations/s
     perms = 4 * N * sum((w + 15) // 16 for w in WIDTHS) + 3 * 4 * N
     hash_ms = stage["ms_hash_main"] / args.steps
@@ -421,14 +433,18 @@ def main():
     peak_sbox = ctx.bench_modmul(2)
     peak_shoup = ctx.bench_modmul(1)
     ideal_ms = perms * (852.0 / peak_sbox + 504.0 / peak_shoup) * 1e3 if peak_sbox > 0 and peak_shoup > 0 else 0.0
+    hash_ncu = None
+    try:  # pipe utilisation of HashRowsKernel from this round's ncu capture (profiles/r2_hash_ncu.json; not re-measured by this run)
+        with open(os.path.join(ROOT, "profiles", "r2_hash_ncu.json")) as f:
+            hash_ncu = json.load(f)
+    except Exception:
+        pass
     poseidon = {"kernel": "HashRowsKernel + HashFoldKernel (Poseidon2 t=24) over the 3 main trees", "bound": "integer multiply pipe (FMA-heavy)", "permutations": perms,
                 "ms": hash_ms, "gperm_per_s": perms / (hash_ms * 1e-3) / 1e9 if hash_ms > 0 else 0.0,
                 "modmul_per_permutation": {"montgomery_sbox": 852, "shoup_const": 504},
                 "modmul_peak_measured_gmul_s": {"sbox_chain": peak_sbox / 1e9, "shoup": peak_shoup / 1e9},
                 "ms_at_modmul_peak": ideal_ms, "frac_of_modmul_peak": ideal_ms / hash_ms if hash_ms > 0 else 0.0,
-                "ncu": {"source": "profiles/r1_v6_hash_ncu_summary.txt (one --set full capture of HashRowsKernel, 192 columns; static, not re-measured by this run)",
-                        "sm__pipe_alu_cycles_active_pct": 52.3, "sm__pipe_fma_cycles_active_pct": 48.1, "fma_heavy_half_pct": 96.0,
-                        "smsp__issue_active_pct": 61.9, "dram_throughput_pct": 1.7},
+                "ncu": hash_ncu,
                 "note": "multiplications only: the 2160 modular additions per permutation share the issue slots (ALU pipe); integer multiplies issue on the heavy half of the FMA pipe only (fmalite = 0), which is ~96 % busy"}
 
     # the NTT/LDE pipeline against the bound that binds it on sm_100a: 50 butterflies + 6 plain products per trace element,
@@ -445,9 +461,15 @@ def main():
         spo2 = 16
         times, cores = run_oracle_sample(spo2, 1)
         scale = float(1 << (po2 - spo2))
-        cpu_value = 1.0 / (times[0] * scale)
+        scaled_value = 1.0 / (times[0] * scale)
+        full = None
+        if not args.no_full_size and po2 <= 20:
+            full = run_oracle_sample(po2, 1)[0][0]   # ONE real segment of bench.py's own size (tens of seconds on the box's cores)
+        cpu_value = 1.0 / full if full else scaled_value
         cpu = {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "oracle CPU restatement, %d threads: one W=256 segment of 2^%d cycles (%.2f s), scaled x%d linearly in cycles to po2=%d" % (cores, spo2, times[0], int(scale), po2)}
+               "sample": "oracle CPU restatement, %d threads: " % cores + (("ONE real W=256 segment of 2^%d cycles: %.1f s (the value); " % (po2, full)) if full else "") +
+                         "one W=256 segment of 2^%d cycles: %.2f s, x%d linear in cycles = %.4f segments/s" % (spo2, times[0], int(scale), scaled_value),
+               "full_size_seconds": full, "scaled_sample_segments_per_s": scaled_value}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -458,7 +480,10 @@ def main():
                            "po2": po2, "segments_per_step": world * F, "inflight_per_gpu": F,
                            "parallelism": "segments sharded across %d GPU(s), %d prover contexts in flight per GPU, no collectives" % (world, F),
                            "cache": "inputs (1 GiB trace, 4 GiB LDE) are larger than L2; no flush needed", "seal_words": seal_words,
-                           "camt53_segments": CAMT53_SEGMENTS, "camt53_proof_seconds": CAMT53_SEGMENTS / value},
+                           "camt53_segments": CAMT53_SEGMENTS,
+                           "camt53_proof_seconds": (camt53 or {}).get("proof_seconds"), "camt53_proof_seconds_is": "MEASURED: wall clock of one 37-segment proof with host trace buffers (camt53 object); null when --no-camt53 / --no-e2e",
+                           "blinding": "library default: a fresh 256-bit key from OS entropy per segment, ChaCha20-expanded on the device (the seeds passed are only mixed in)" if os.environ.get("HFB200_DETERMINISTIC_BLINDING", "0") != "1" else "deterministic test mode (HFB200_DETERMINISTIC_BLINDING=1)",
+                           "host_syncs_per_segment": stage.get("host_syncs", 0.0) / args.steps},
                 "stages_ms_per_segment": {k: v / args.steps for k, v in stage.items() if k.startswith("ms_")},
                 "stages_note": "CUDA events on the library stream, one context in flight (kernel durations undisturbed); value/e2e use %d contexts in flight" % F,
                 "roofline": roofline, "poseidon2": poseidon, "cpu_baseline": cpu, "e2e": e2e, "camt53": camt53,

@@ -104,3 +104,72 @@ def build(widths, variant=0, nest=False):
     m = mixv(7, m, mul(first, sub(get(DATA, 0), glob(0, 0))))
     return {"taps": np.array(taps, np.uint32), "steps": np.array(steps, np.uint32), "ret": m, "n_globals": 32, "n_mix": 4 * nch,
             "widths": tuple(widths)}
+
+
+def build_scaled(widths=(24, 320, 56), n_groups=420, per_group=16, seed=7):
+    """A synthetic circuit at the SCALE of rv32im-v2 (thousands of constraints, W ~ 400, taps at several
+    `back` distances): ~n_groups * per_group constraints of degree <= 5 over random taps, grouped under AND_COND selectors the way
+    zirgen's major/minor muxes are, written in the same PolyExtStep shape.  It exercises the data-defined path (hfb200_init_ir:
+    bytecode compiler, NVRTC specialisation, generic DEEP kernels) at the limits the library declares: 4 distinct back values,
+    8 distinct tap sets, up to 4 taps per register.  NOT satisfiable by construction -- the prover does not need a satisfying
+    witness to be timed or compared with the oracle (the seal then fails verification at the constraint check, as it must)."""
+    import random
+    rnd = random.Random(seed)
+    wc, wd, wa = widths
+    tap_sets = [(0,), (0, 1), (0, 1, 2), (0, 1, 2, 3), (0, 2), (0, 3), (0, 1, 3), (0, 2, 3)]   # 8 sets, backs {0, 1, 2, 3}
+    taps = []
+    for c in range(wa):
+        taps += [(ACCUM, c, 0), (ACCUM, c, 1)]
+    for c in range(wc):
+        taps.append((CODE, c, 0))
+    data_sets = {}
+    for c in range(wd):
+        ts = tap_sets[c % len(tap_sets)] if c % 3 else (0, 1, 2, 3)
+        data_sets[c] = ts
+        for b in ts:
+            taps.append((DATA, c, b))
+    tap_index = {t: i for i, t in enumerate(taps)}
+    steps, nfp, nmix, cache = [], [0], [0], {}
+
+    def fp(op, a=0, b=0, c=0):
+        steps.append((op, a, b, c)); nfp[0] += 1
+        return nfp[0] - 1
+
+    def mixv(op, a=0, b=0, c=0):
+        steps.append((op, a, b, c)); nmix[0] += 1
+        return nmix[0] - 1
+
+    def get(g, off, back=0):
+        k = (g, off, back)
+        if k not in cache:
+            cache[k] = fp(1, tap_index[k])
+        return cache[k]
+
+    def rnd_data():
+        c = rnd.randrange(wd)
+        return get(DATA, c, rnd.choice(data_sets[c]))
+
+    add = lambda a, b: fp(3, a, b)
+    sub = lambda a, b: fp(4, a, b)
+    mul = lambda a, b: fp(5, a, b)
+    m = mixv(6)
+    n_cons = 0
+    for g in range(n_groups):
+        sel = get(CODE, g % wc)
+        inner = mixv(6)
+        for k in range(per_group):
+            A, B, Cc, D, E = rnd_data(), rnd_data(), rnd_data(), rnd_data(), rnd_data()
+            f = (g + k) & 3
+            if f == 0:
+                e = sub(add(mul(A, B), Cc), D)
+            elif f == 1:
+                e = sub(mul(mul(A, B), Cc), mul(D, E))
+            elif f == 2:
+                e = mul(mul(mul(add(A, fp(2, 1, (g + k) % wa)), B), Cc), sub(D, E))
+            else:
+                e = add(add(mul(A, get(ACCUM, (g + k) % wa, 1)), mul(Cc, D)), fp(2, 0, (g + k) % 32))
+            inner = mixv(7, inner, e)
+            n_cons += 1
+        m = mixv(8, m, sel, inner)
+    return {"taps": np.array(taps, np.uint32), "steps": np.array(steps, np.uint32), "ret": m, "n_globals": 32, "n_mix": wa,
+            "widths": tuple(widths), "n_constraints": n_cons}
