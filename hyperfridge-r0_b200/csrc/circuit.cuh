@@ -312,8 +312,15 @@ struct GenericCircuitHost {
     std::vector<std::vector<uint32_t>> combos;
     std::vector<uint32_t> combo_begin;
     std::vector<uint32_t> backs;             // distinct back values, sorted (slot s <-> backs[s])
-    std::vector<BcIns> prog;
+    std::vector<BcIns> prog;   // the whole constraint polynomial as ONE program (verifier, reference for the chunks)
     uint32_t n_fp_slots = 0, n_mix_slots = 0, ret_slot = 0, n_mixpow = 0;
+    // The same polynomial cut along its top-level AndEqz / AndCond chain into CHUNKS of ~400 steps: the sum
+    // tot = sum_k mix^e_k * term_k splits anywhere, so every chunk is a self-contained program (its Gets re-issued, its chain head
+    // starting at the exponent the prefix reached) that adds its partial sum into the check buffer.  At rv32im scale (tens of
+    // thousands of steps, a thousand taps) one straight-line kernel does not compile in useful time and keeps ~1000 values
+    // live; chunks compile in parallel in seconds and keep the live set small (upstream splits its generated eval_check the same way).
+    struct Chunk { std::vector<BcIns> prog; uint32_t n_fp_slots = 0, n_mix_slots = 0, ret_slot = 0; BcIns* d_prog = nullptr; };
+    std::vector<Chunk> chunks;
     // device copies
     BcIns* d_prog = nullptr;
     uint8_t* d_colmask[3] = {nullptr, nullptr, nullptr};  // per column: bit s set <=> tapped at backs[s]
@@ -365,6 +372,10 @@ struct GenericCircuitHost {
         // device tables
         d_prog = (BcIns*)dev->alloc(prog.size() * sizeof(BcIns));
         dev->h2d(d_prog, prog.data(), prog.size() * sizeof(BcIns));
+        for (Chunk& c : chunks) {
+            c.d_prog = (BcIns*)dev->alloc(c.prog.size() * sizeof(BcIns));
+            dev->h2d(c.d_prog, c.prog.data(), c.prog.size() * sizeof(BcIns));
+        }
         for (int g = 0; g < 3; g++) {
             std::vector<uint8_t> m(w[g], 0);
             for (const IrTap& t : taps) if ((int)t.group == g) m[t.offset] |= (uint8_t)(1u << back_slot(t.back));
@@ -384,12 +395,22 @@ struct GenericCircuitHost {
     void destroy(Dev* dev) {
         if (!active) return;
         dev->free(d_prog); for (auto& p : d_colmask) dev->free(p);
+        for (Chunk& c : chunks) { dev->free(c.d_prog); c.d_prog = nullptr; }
         dev->free(d_regcombo); dev->free(d_regcol);
         active = false;
     }
 
     // SSA step list -> slot-allocated bytecode.
     void compile(const IrStep* st, size_t n, uint32_t ret) {
+        std::vector<uint32_t> mix_exp;
+        compile_list(st, n, ret, (size_t)-1, 0, prog, n_fp_slots, n_mix_slots, ret_slot, &mix_exp, true);
+        n_mixpow = 0;
+        for (uint32_t e : mix_exp) if (e + 1 > n_mixpow) n_mixpow = e + 1;
+        make_chunks(st, n, ret, mix_exp);
+    }
+    // `head_idx`: step index of the TRUE that heads the top-level chain of a chunk; its exponent is `base_exp` instead of 0.
+    void compile_list(const IrStep* st, size_t n, uint32_t ret, size_t head_idx, uint32_t base_exp, std::vector<BcIns>& out, uint32_t& out_fp_slots,
+                      uint32_t& out_mix_slots, uint32_t& out_ret_slot, std::vector<uint32_t>* mix_exp_out, bool validate) const {
         std::vector<int> is_fp(n);                 // 1: pushes an fp var, 0: pushes a mix var
         std::vector<uint32_t> fp_of, mix_of;       // var index -> step index
         for (size_t i = 0; i < n; i++) {
@@ -407,9 +428,9 @@ struct GenericCircuitHost {
             const IrStep& s = st[i];
             switch (s.op) {
                 case IR_ADD: case IR_SUB: case IR_MUL: chk_fp(s.a, i); chk_fp(s.b, i); fp_last[s.a] = i; fp_last[s.b] = i; break;
-                case IR_GET: if (s.a >= taps.size()) throw Err("circuit: Get of an unknown tap"); break;
-                case IR_GET_GLOBAL: if (s.a > 1 || s.b >= (s.a == 0 ? N_GLOBAL : n_mix)) throw Err("circuit: GetGlobal out of range"); break;
-                case IR_TRUE: mix_exp[nm++] = 0; break;
+                case IR_GET: if (validate && s.a >= taps.size()) throw Err("circuit: Get of an unknown tap"); break;
+                case IR_GET_GLOBAL: if (validate && (s.a > 1 || s.b >= (s.a == 0 ? N_GLOBAL : n_mix))) throw Err("circuit: GetGlobal out of range"); break;
+                case IR_TRUE: mix_exp[nm++] = i == head_idx ? base_exp : 0; break;
                 case IR_AND_EQZ: chk_mx(s.a, i); chk_fp(s.b, i); mix_last[s.a] = i; fp_last[s.b] = i; mix_exp[nm] = mix_exp[s.a] + 1; nm++; break;
                 case IR_AND_COND: chk_mx(s.a, i); chk_fp(s.b, i); chk_mx(s.c, i); mix_last[s.a] = i; mix_last[s.c] = i; fp_last[s.b] = i;
                                   mix_exp[nm] = mix_exp[s.a] + mix_exp[s.c]; nm++; break;
@@ -417,13 +438,11 @@ struct GenericCircuitHost {
             }
         }
         mix_last[ret] = n;  // live to the end
-        n_mixpow = 0;
-        for (uint32_t e : mix_exp) if (e + 1 > n_mixpow) n_mixpow = e + 1;
         std::vector<uint32_t> fp_slot(fp_of.size()), mix_slot(mix_of.size());
         std::vector<uint32_t> fp_free, mix_free;
         uint32_t fp_hi = 0, mix_hi = 0, nf = 0; nm = 0;
         auto take = [](std::vector<uint32_t>& fr, uint32_t& hi) { if (!fr.empty()) { uint32_t s = fr.back(); fr.pop_back(); return s; } return hi++; };
-        prog.clear();
+        out.clear();
         for (size_t i = 0; i < n; i++) {
             const IrStep& s = st[i];
             BcIns ins{};
@@ -459,9 +478,110 @@ struct GenericCircuitHost {
                 nm++;
             }
             if (fp_hi > 4096 || mix_hi > 4096) throw Err("circuit: too many live values");
-            prog.push_back(ins);
+            out.push_back(ins);
         }
-        n_fp_slots = fp_hi ? fp_hi : 1; n_mix_slots = mix_hi ? mix_hi : 1; ret_slot = mix_slot[ret];
+        out_fp_slots = fp_hi ? fp_hi : 1; out_mix_slots = mix_hi ? mix_hi : 1; out_ret_slot = mix_slot[ret];
+        if (mix_exp_out) *mix_exp_out = mix_exp;
+    }
+    // cut the top-level chain into chunks of about GEN_CHUNK_STEPS steps (HFB200_IR_CHUNK overrides) and compile each
+    void make_chunks(const IrStep* st, size_t n, uint32_t ret, const std::vector<uint32_t>& mix_exp) {
+        // ~400 steps (~2500 SASS instructions, 40 KB) per chunk: the kernel body then stays resident in the instruction cache while
+        // every warp loops over its rows; at 3000 steps the stage is bound by instruction fetch from L2 (measured on B200 at
+        // po2 = 18, 51 k steps: 104 ms per check stage with 3000-step chunks, 42 ms with 600, 38 ms with 300)
+        size_t limit = 400;
+        if (const char* env = std::getenv("HFB200_IR_CHUNK")) { const long v = std::atol(env); if (v >= 64) limit = (size_t)v; }
+        chunks.clear();
+        std::vector<uint32_t> fp_of, mix_of, var_of(n);
+        for (size_t i = 0; i < n; i++) { auto& v = st[i].op <= IR_MUL ? fp_of : mix_of; var_of[i] = (uint32_t)v.size(); v.push_back((uint32_t)i); }
+        std::vector<uint32_t> chain;  // mix vars of the top-level chain, head first
+        for (uint32_t v = ret;;) { chain.push_back(v); const IrStep& s = st[mix_of[v]]; if (s.op == IR_TRUE) break; v = s.a; }
+        std::reverse(chain.begin(), chain.end());
+        if (n <= limit || chain.size() <= 2) {  // small circuit: the whole program is the one chunk
+            Chunk c; c.prog = prog; c.n_fp_slots = n_fp_slots; c.n_mix_slots = n_mix_slots; c.ret_slot = ret_slot;
+            chunks.push_back(std::move(c));
+            return;
+        }
+        std::vector<uint32_t> stamp(n, 0);
+        std::vector<uint32_t> stack;
+        // marks the steps element `var` needs (its own step, its fp operands, its inner chain) -- not its chain predecessor
+        auto mark = [&](uint32_t var, uint32_t id) {
+            size_t added = 0;
+            stack.clear();
+            const uint32_t self = mix_of[var];
+            if (stamp[self] != id) { stamp[self] = id; added++; }
+            const IrStep& e = st[self];
+            stack.push_back(fp_of[e.b]);
+            if (e.op == IR_AND_COND) stack.push_back(mix_of[e.c]);
+            while (!stack.empty()) {
+                const uint32_t i = stack.back(); stack.pop_back();
+                if (stamp[i] == id) continue;
+                stamp[i] = id; added++;
+                const IrStep& s = st[i];
+                switch (s.op) {
+                    case IR_ADD: case IR_SUB: case IR_MUL: stack.push_back(fp_of[s.a]); stack.push_back(fp_of[s.b]); break;
+                    case IR_AND_EQZ: stack.push_back(mix_of[s.a]); stack.push_back(fp_of[s.b]); break;
+                    case IR_AND_COND: stack.push_back(mix_of[s.a]); stack.push_back(fp_of[s.b]); stack.push_back(mix_of[s.c]); break;
+                    default: break;
+                }
+            }
+            return added;
+        };
+        size_t k = 1;
+        uint32_t id = 0;
+        while (k < chain.size()) {
+            id++;
+            const size_t k0 = k;
+            size_t count = 0;
+            while (k < chain.size()) {
+                // tentative: does element k still fit?  (marking is idempotent within the id, so an overshoot only costs the re-mark below)
+                const size_t add = mark(chain[k], id);
+                if (k > k0 && count + add > limit) { break; }
+                count += add; k++;
+            }
+            if (k < chain.size()) {  // the element that did not fit was marked with this id: redo the group cleanly
+                id++;
+                for (size_t q = k0; q < k; q++) mark(chain[q], id);
+            }
+            // sub-list: synthetic head TRUE, then the marked steps in their original order, operands renumbered
+            std::vector<IrStep> sub;
+            std::vector<uint32_t> fp_new(fp_of.size(), 0xFFFFFFFFu), mix_new(mix_of.size(), 0xFFFFFFFFu);
+            uint32_t nfp = 0, nmx = 0;
+            sub.push_back(IrStep{IR_TRUE, 0, 0, 0}); nmx = 1;
+            std::vector<char> is_elem(n, 0);
+            for (size_t q = k0; q < k; q++) is_elem[mix_of[chain[q]]] = 1;
+            uint32_t prev_elem_new = 0;  // the synthetic head
+            uint32_t sub_ret = 0;
+            // Leaves (Get / Const / GetGlobal) are emitted where they are USED, not where the whole program first used them (that
+            // would hoist every tap of a late chunk to its top and keep ~all taps live), and are re-issued when their last copy in
+            // this chunk lies more than GEN_REMAT steps back: a Get is one coalesced load of LDE data that later chunks touch
+            // anyway, a live value is a register for hundreds of instructions.
+            const size_t GEN_REMAT = 192;
+            std::vector<size_t> leaf_pos(fp_of.size(), 0);
+            auto need_fp = [&](uint32_t v) {
+                const IrStep& l = st[fp_of[v]];
+                if (l.op > IR_GET_GLOBAL) return;  // computed value: already emitted (original order)
+                if (fp_new[v] != 0xFFFFFFFFu && sub.size() - leaf_pos[v] <= GEN_REMAT) return;
+                fp_new[v] = nfp++; leaf_pos[v] = sub.size();
+                sub.push_back(l);
+            };
+            for (size_t i = 0; i < n; i++) {
+                if (stamp[i] != id) continue;
+                IrStep s = st[i];
+                if (s.op <= IR_GET_GLOBAL) continue;
+                switch (s.op) {
+                    case IR_ADD: case IR_SUB: case IR_MUL: need_fp(s.a); need_fp(s.b); s.a = fp_new[s.a]; s.b = fp_new[s.b]; break;
+                    case IR_AND_EQZ: need_fp(s.b); s.a = is_elem[i] ? prev_elem_new : mix_new[s.a]; s.b = fp_new[s.b]; break;
+                    case IR_AND_COND: need_fp(s.b); s.a = is_elem[i] ? prev_elem_new : mix_new[s.a]; s.b = fp_new[s.b]; s.c = mix_new[s.c]; break;
+                    default: break;
+                }
+                if (s.op <= IR_MUL) fp_new[var_of[i]] = nfp++;
+                else { mix_new[var_of[i]] = nmx; if (is_elem[i]) { prev_elem_new = nmx; sub_ret = nmx; } nmx++; }
+                sub.push_back(s);
+            }
+            Chunk c;
+            compile_list(sub.data(), sub.size(), sub_ret, 0, mix_exp[chain[k0 - 1]], c.prog, c.n_fp_slots, c.n_mix_slots, c.ret_slot, nullptr, false);
+            chunks.push_back(std::move(c));
+        }
     }
 };
 
@@ -475,6 +595,7 @@ struct GenEvalArgs {
     uint32_t n_mix;
     uint32_t yinv[4];
     uint32_t po2, rows_per_block, n_fp_slots, n_mix_slots, ret_slot;
+    uint32_t accumulate;     // 0: store tot / Z; 1: add it to what an earlier chunk left in `check`
 };
 // One thread per LDE row; fp slots [slot][row] and mix slots in shared memory; the program is read uniformly.
 struct GenEvalCheckKernel {
@@ -512,7 +633,10 @@ struct GenEvalCheckKernel {
             }
             const E4 tot = mslot[p.ret_slot * R + rr];
             const uint32_t yi = p.yinv[i & 3];
-            for (int k = 0; k < 4; k++) p.check[(uint64_t)k * domain + i] = fmul(tot.c[k], yi);
+            for (int k = 0; k < 4; k++) {
+                const uint32_t v = fmul(tot.c[k], yi);
+                p.check[(uint64_t)k * domain + i] = p.accumulate ? fadd(p.check[(uint64_t)k * domain + i], v) : v;
+            }
         }
     }
 };

@@ -8,7 +8,11 @@
 // through the runtime's library API.  The interpreter kernel (`GenEvalCheckKernel`) stays as the path for builds or
 // boxes without libnvrtc and as the cross-check in the tests (HFB200_IR_JIT=0 selects it).
 #pragma once
+#include <map>
 #include <string>
+#include <thread>
+#include <atomic>
+#include <mutex>
 #include "circuit.cuh"
 
 #ifndef HFB200_EMU
@@ -67,23 +71,48 @@ FI E4 e4a_redc(const E4A& a) { E4 r; r.c[0] = redc(a.c[0]); r.c[1] = redc(a.c[1]
 struct JitEvalArgs { const uint32_t* ev[3]; uint32_t* check; const E4* mixpow; const uint32_t* mix; const uint32_t* globals; uint32_t yinv[4]; uint32_t po2; };
 )JIT";
 
-// straight-line CUDA for the bytecode of one circuit
-static inline std::string jit_source(const GenericCircuitHost& g) {
-    std::string s = JIT_PRELUDE;
-    s += "extern \"C\" __global__ void __launch_bounds__(128) hfb200_eval_check_jit(JitEvalArgs p) {\n";
-    s += "  const uint64_t domain = 4ull << p.po2, dmask = domain - 1ull;\n";
-    s += "  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i >= domain) return;\n";
+#ifndef JIT_FENCE_EVERY
+#define JIT_FENCE_EVERY 2u
+#endif
+// straight-line CUDA for the bytecode of chunk `k` of one circuit (kernel hfb200_eval_check_jit_<k>); chunk 0 stores its partial
+// sum (times 1 / Z), the others add theirs
+// The kernel is specialised for the segment size as well: with `domain` a literal, a tap read is `ev[<column * domain> + row_b]` -- a
+// constant offset from four row indices.  With `domain` a run-time value ptxas treats every `column * domain` product as a common
+// subexpression worth keeping (hundreds of 64-bit values per chunk): 3 KB of spills per thread and ~50 s of compile time per chunk.
+static inline std::string jit_kernel_source(const GenericCircuitHost& g, size_t k, uint32_t po2) {
+    const GenericCircuitHost::Chunk& c = g.chunks[k];
+    const uint64_t domain = 4ull << po2;
+    std::string s;
+    // tuning knobs of the generated code (experiments: profiles/r2_ir_scale.txt)
+    static const int minb = [] { const char* e = std::getenv("HFB200_IR_JIT_MINB"); const int v = e ? std::atoi(e) : 4; return v >= 1 && v <= 8 ? v : 4; }();
+    static const uint32_t fence_every = [] { const char* e = std::getenv("HFB200_IR_JIT_FENCE"); const int v = e ? std::atoi(e) : (int)JIT_FENCE_EVERY; return (uint32_t)(v >= 0 ? v : 2); }();
+    s += "extern \"C\" __global__ void __launch_bounds__(128, " + std::to_string(minb) + ") hfb200_eval_check_jit_" + std::to_string(k) + "(JitEvalArgs p) {\n";
+    s += "  const uint64_t domain = " + std::to_string(domain) + "ull, dmask = domain - 1ull;\n";
+    s += "  if (p.po2 != " + std::to_string(po2) + "u) return;\n";
     s += "  const uint32_t* __restrict__ ev0 = p.ev[0]; const uint32_t* __restrict__ ev1 = p.ev[1]; const uint32_t* __restrict__ ev2 = p.ev[2];\n";
-    for (uint32_t k = 0; k < g.n_fp_slots; k++) s += "  uint32_t f" + std::to_string(k) + " = 0;\n";
-    for (uint32_t k = 0; k < g.n_mix_slots; k++) s += "  E4A m" + std::to_string(k) + " = e4a_zero();\n";
-    auto F = [](uint32_t k) { return "f" + std::to_string(k); };
-    auto M = [](uint32_t k) { return "m" + std::to_string(k); };
-    for (const BcIns& ins : g.prog) {
+    // grid-stride loop over the rows: the straight-line body is executed many times by every warp, so its instructions come from the
+    // instruction cache instead of being streamed from L2 once per warp (what bounds a one-row-per-thread kernel of this size)
+    s += "  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < domain; i += (uint64_t)gridDim.x * blockDim.x) {\n";
+    for (uint32_t b : g.backs) s += "  const uint64_t r" + std::to_string(b) + " = (i + domain - " + std::to_string(4ull * b) + "ull) & dmask;\n";
+    // q<b>: the row indices the loads actually use; made opaque again at every fence so that ptxas cannot keep the ADDRESS of a tap
+    // read in a register pair until the same tap is read again hundreds of steps later (that alone was ~450 live values per chunk)
+    std::string reopaque;
+    for (uint32_t b : g.backs) { s += "  uint64_t q" + std::to_string(b) + " = r" + std::to_string(b) + ";\n"; reopaque += "  q" + std::to_string(b) + " = r" + std::to_string(b) + "; asm volatile(\"\" : \"+l\"(q" + std::to_string(b) + "));\n"; }
+    for (uint32_t q = 0; q < c.n_fp_slots; q++) s += "  uint32_t f" + std::to_string(q) + " = 0;\n";
+    for (uint32_t q = 0; q < c.n_mix_slots; q++) s += "  E4A m" + std::to_string(q) + " = e4a_zero();\n";
+    auto F = [](uint32_t q) { return "f" + std::to_string(q); };
+    auto M = [](uint32_t q) { return "m" + std::to_string(q); };
+    uint32_t since_fence = 0;
+    for (const BcIns& ins : c.prog) {
         const std::string d = std::to_string(ins.dst);
+        // a compiler-level memory fence after every few constraints: without it ptxas hoists the (independent) loads of a whole
+        // chunk -- hundreds of tap reads and mix powers -- to the top of the kernel and spills them (3 KB of stack per thread,
+        // 50 s of compile time per chunk); latency is hidden by the other warps of the SM, not by this thread's own loads
+        if (fence_every && (ins.op == BC_MEQZ || ins.op == BC_MCOND) && ++since_fence >= fence_every) { s += "  asm volatile(\"\" ::: \"memory\");\n" + reopaque; since_fence = 0; }
         switch (ins.op) {
             case BC_CONST: s += "  f" + d + " = " + std::to_string(ins.a) + "u;\n"; break;
             case BC_GET:
-                s += "  f" + d + " = ev" + std::to_string(ins.a) + "[" + std::to_string(ins.b) + "ull * domain + ((i + domain - " + std::to_string(4ull * ins.c) + "ull) & dmask)];\n";
+                s += "  f" + d + " = ev" + std::to_string(ins.a) + "[" + std::to_string((uint64_t)ins.b * domain) + "ull + q" + std::to_string(ins.c) + "];\n";
                 break;
             case BC_GETG: s += "  f" + d + " = " + (ins.a == 0 ? "p.globals[" : "p.mix[") + std::to_string(ins.b) + "];\n"; break;
             case BC_ADD: s += "  f" + d + " = fadd(" + F(ins.a) + ", " + F(ins.b) + ");\n"; break;
@@ -100,8 +129,15 @@ static inline std::string jit_source(const GenericCircuitHost& g) {
                 break;
         }
     }
-    s += "  const E4 tot = e4a_redc(m" + std::to_string(g.ret_slot) + ");\n  const uint32_t yi = p.yinv[i & 3];\n";
-    s += "  for (int k = 0; k < 4; k++) p.check[(uint64_t)k * domain + i] = fmul(tot.c[k], yi);\n}\n";
+    s += "  const E4 tot = e4a_redc(m" + std::to_string(c.ret_slot) + ");\n  const uint32_t yi = p.yinv[i & 3];\n";
+    if (k == 0) s += "  for (int k = 0; k < 4; k++) p.check[(uint64_t)k * domain + i] = fmul(tot.c[k], yi);\n  }\n}\n";
+    else s += "  for (int k = 0; k < 4; k++) p.check[(uint64_t)k * domain + i] = fadd(p.check[(uint64_t)k * domain + i], fmul(tot.c[k], yi));\n  }\n}\n";
+    return s;
+}
+// every chunk kernel in one translation unit (hfb200_ir_source; the library itself compiles one unit per chunk, in parallel)
+static inline std::string jit_source(const GenericCircuitHost& g, uint32_t po2 = 20) {
+    std::string s = JIT_PRELUDE;
+    for (size_t k = 0; k < g.chunks.size(); k++) s += jit_kernel_source(g, k, po2);
     return s;
 }
 
@@ -131,44 +167,83 @@ struct NvrtcApi {
 };
 
 struct JitEvalCheck {
-    cudaLibrary_t lib = nullptr;
-    cudaKernel_t kernel = nullptr;
+    struct Compiled { std::vector<cudaLibrary_t> libs; std::vector<cudaKernel_t> kernels; };  // one kernel per chunk, launched in order
+    std::map<uint32_t, Compiled> by_po2;  // specialised per segment size, compiled when a size is first proved (or at init for max_po2)
+    const GenericCircuitHost* g = nullptr;
     bool ready = false;
     std::string note;   // why the JIT is not in use (empty when ready)
-    float compile_ms = 0;
+    float compile_ms = 0;  // the most recent specialisation
 
-    void init(const GenericCircuitHost& g) {
+    static NvrtcApi& api() { static NvrtcApi a; return a; }
+    void init(const GenericCircuitHost& gen, uint32_t first_po2) {
         if (const char* env = std::getenv("HFB200_IR_JIT")) if (std::atoi(env) == 0) { note = "disabled by HFB200_IR_JIT=0"; return; }
-        static NvrtcApi api;
-        if (!api.load()) { note = "libnvrtc.so.12 not found"; return; }
-        const auto t0 = std::chrono::steady_clock::now();
-        const std::string src = jit_source(g);
-        nvrtcProgram prog = nullptr;
-        if (api.CreateProgram(&prog, src.c_str(), "hfb200_eval_check_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { note = "nvrtcCreateProgram failed"; return; }
-        const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
-        const nvrtcResult rc = api.CompileProgram(prog, 3, opts);
-        if (rc != NVRTC_SUCCESS) {
-            size_t n = 0; api.GetProgramLogSize(prog, &n);
-            std::string log(n, '\0'); if (n) api.GetProgramLog(prog, &log[0]);
-            api.DestroyProgram(&prog);
-            throw Err("data-defined circuit: NVRTC compilation of eval_check failed: " + log.substr(0, 2000));
-        }
-        size_t nb = 0; api.GetCUBINSize(prog, &nb);
-        std::vector<char> cubin(nb);
-        api.GetCUBIN(prog, cubin.data());
-        api.DestroyProgram(&prog);
-        CUDA_CHECK(cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
-        CUDA_CHECK(cudaLibraryGetKernel(&kernel, lib, "hfb200_eval_check_jit"));
-        compile_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        static std::mutex api_mu;
+        { std::lock_guard<std::mutex> lock(api_mu); if (!api().load()) { note = "libnvrtc.so.12 not found"; return; } }
+        g = &gen;
         ready = true;
+        ensure(first_po2);
     }
-    void destroy() { if (lib) cudaLibraryUnload(lib); lib = nullptr; kernel = nullptr; ready = false; }
+    void ensure(uint32_t po2) {
+        if (!ready || by_po2.count(po2)) return;
+        const auto t0 = std::chrono::steady_clock::now();
+        const size_t K = g->chunks.size();
+        std::vector<std::vector<char>> cubins(K);
+        std::vector<std::string> errors(K);
+        // one NVRTC program per chunk, compiled on up to 8 host threads (NVRTC is thread-safe across programs)
+        std::atomic<size_t> next{0};
+        auto work = [&] {
+            NvrtcApi& a = api();
+            for (;;) {
+                const size_t k = next.fetch_add(1);
+                if (k >= K) return;
+                const std::string src = std::string(JIT_PRELUDE) + jit_kernel_source(*g, k, po2);
+                nvrtcProgram prog = nullptr;
+                if (a.CreateProgram(&prog, src.c_str(), "hfb200_eval_check_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { errors[k] = "nvrtcCreateProgram failed"; continue; }
+                const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+                if (a.CompileProgram(prog, 3, opts) != NVRTC_SUCCESS) {
+                    size_t n = 0; a.GetProgramLogSize(prog, &n);
+                    std::string log(n, '\0'); if (n) a.GetProgramLog(prog, &log[0]);
+                    a.DestroyProgram(&prog);
+                    errors[k] = "NVRTC compilation of eval_check chunk " + std::to_string(k) + " failed: " + log.substr(0, 2000);
+                    continue;
+                }
+                size_t nb = 0; a.GetCUBINSize(prog, &nb);
+                cubins[k].resize(nb);
+                a.GetCUBIN(prog, cubins[k].data());
+                a.DestroyProgram(&prog);
+            }
+        };
+        unsigned nthreads = std::thread::hardware_concurrency();
+        if (nthreads == 0) nthreads = 1;
+        nthreads = (unsigned)std::min<size_t>(std::min<unsigned>(nthreads, 8u), K);
+        if (const char* env = std::getenv("HFB200_IR_JIT_THREADS")) { const int v = std::atoi(env); if (v >= 1) nthreads = (unsigned)v; }
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nthreads; t++) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
+        for (const std::string& e : errors) if (!e.empty()) throw Err("data-defined circuit: " + e);
+        Compiled c;
+        c.libs.resize(K, nullptr); c.kernels.resize(K, nullptr);
+        for (size_t k = 0; k < K; k++) {
+            CUDA_CHECK(cudaLibraryLoadData(&c.libs[k], cubins[k].data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+            const std::string name = "hfb200_eval_check_jit_" + std::to_string(k);
+            CUDA_CHECK(cudaLibraryGetKernel(&c.kernels[k], c.libs[k], name.c_str()));
+        }
+        by_po2[po2] = std::move(c);
+        compile_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    void destroy() { for (auto& kv : by_po2) for (auto& l : kv.second.libs) if (l) cudaLibraryUnload(l); by_po2.clear(); ready = false; }
     void launch(Dev& dev, const JitEvalArgs& a, uint64_t domain) {
+        ensure(a.po2);
         JitEvalArgs args = a;
         void* params[] = {&args};
-        const unsigned block = 128, grid = (unsigned)((domain + block - 1) / block);
-        CUDA_CHECK(cudaLaunchKernel((const void*)kernel, dim3(grid), dim3(block), params, 0, dev.stream));
-        dev.launches++;
+        static const unsigned per_sm = [] { const char* e = std::getenv("HFB200_IR_JIT_BLOCKS_PER_SM"); const int v = e ? std::atoi(e) : 8; return (unsigned)(v >= 1 ? v : 8); }();
+        const unsigned block = 128;
+        const unsigned grid = (unsigned)std::min<uint64_t>((domain + block - 1) / block, (uint64_t)dev.sm_count * per_sm);
+        for (cudaKernel_t k : by_po2.at(a.po2).kernels) {
+            CUDA_CHECK(cudaLaunchKernel((const void*)k, dim3(grid), dim3(block), params, 0, dev.stream));
+            dev.launches++;
+        }
     }
 };
 #else
@@ -176,7 +251,7 @@ struct JitEvalCheck {
     bool ready = false;
     std::string note = "host emulator build";
     float compile_ms = 0;
-    void init(const GenericCircuitHost&) {}
+    void init(const GenericCircuitHost&, uint32_t) {}
     void destroy() {}
     void launch(Dev&, const JitEvalArgs&, uint64_t) {}
 };

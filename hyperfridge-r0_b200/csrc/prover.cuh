@@ -148,7 +148,7 @@ struct Prover {
         merkle.init(&dev);
         if (taps) {
             gen.init(&dev, wc, wd, wa, n_mix_ir, taps, n_taps, steps, n_steps, ret);
-            jit.init(gen);
+            jit.init(gen, max_po2);  // specialised for the context's largest segment size now, for other sizes on first use
             cir.init_widths(wc, wd, wa, (uint32_t)gen.taps.size(), n_mix_ir);
         } else {
             cir.init(&dev, wc, wd, wa);
@@ -488,18 +488,24 @@ struct Prover {
                 for (int s_ = 0; s_ < 4; s_++) ja.yinv[s_] = yinv4[s_];
                 jit.launch(dev, ja, D);
             } else {
-            GenEvalArgs a{};
-            a.ev[0] = ev[GROUP_ACCUM]; a.ev[1] = ev[GROUP_CODE]; a.ev[2] = ev[GROUP_DATA];
-            a.check = check; a.prog = gen.d_prog; a.n_ins = (uint32_t)gen.prog.size(); a.mixpow = d_mp; a.mix = d_mix; a.globals = d_gl;
-            a.n_mix = gen.n_mix; a.po2 = po2; a.n_fp_slots = gen.n_fp_slots; a.n_mix_slots = gen.n_mix_slots; a.ret_slot = gen.ret_slot;
-            for (int s_ = 0; s_ < 4; s_++) a.yinv[s_] = yinv4[s_];
-            // rows per block: as many as fit the slot files in shared memory
-            const size_t per_row = (size_t)gen.n_mix_slots * sizeof(E4) + (size_t)gen.n_fp_slots * 4;
-            uint32_t R = 128;
-            while (R > 32 && per_row * R + (N_GLOBAL + gen.n_mix) * 4 > 160 * 1024) R >>= 1;
-            if (per_row * R + (N_GLOBAL + gen.n_mix) * 4 > 220 * 1024) throw Err("data-defined circuit: too many live values for the interpreter's shared-memory slot file");
-            a.rows_per_block = R;
-            dev.launch<GenEvalCheckKernel, 128, 1>((unsigned)((D + R - 1) / R), 1, (int)R, per_row * R + (N_GLOBAL + gen.n_mix) * 4 + 16, a);
+            // interpreter kernel, one launch per chunk (same chunks as the JIT: small slot files, more rows per block)
+            bool first = true;
+            for (const GenericCircuitHost::Chunk& ck : gen.chunks) {
+                GenEvalArgs a{};
+                a.ev[0] = ev[GROUP_ACCUM]; a.ev[1] = ev[GROUP_CODE]; a.ev[2] = ev[GROUP_DATA];
+                a.check = check; a.prog = ck.d_prog; a.n_ins = (uint32_t)ck.prog.size(); a.mixpow = d_mp; a.mix = d_mix; a.globals = d_gl;
+                a.n_mix = gen.n_mix; a.po2 = po2; a.n_fp_slots = ck.n_fp_slots; a.n_mix_slots = ck.n_mix_slots; a.ret_slot = ck.ret_slot;
+                a.accumulate = first ? 0u : 1u;
+                first = false;
+                for (int s_ = 0; s_ < 4; s_++) a.yinv[s_] = yinv4[s_];
+                // rows per block: as many as fit the slot files in shared memory
+                const size_t per_row = (size_t)ck.n_mix_slots * sizeof(E4) + (size_t)ck.n_fp_slots * 4;
+                uint32_t R = 128;
+                while (R > 32 && per_row * R + (N_GLOBAL + gen.n_mix) * 4 > 160 * 1024) R >>= 1;
+                if (per_row * R + (N_GLOBAL + gen.n_mix) * 4 > 220 * 1024) throw Err("data-defined circuit: too many live values for the interpreter's shared-memory slot file");
+                a.rows_per_block = R;
+                dev.launch<GenEvalCheckKernel, 128, 1>((unsigned)((D + R - 1) / R), 1, (int)R, per_row * R + (N_GLOBAL + gen.n_mix) * 4 + 16, a);
+            }
             }
         } else {
             const uint32_t nc = cd.n_constraints();

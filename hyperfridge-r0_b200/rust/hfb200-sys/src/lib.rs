@@ -63,6 +63,31 @@ pub struct hfb200_segment_job {
     pub error: *const c_char,
     pub device: c_int,
     pub ms: f32,
+    pub attempts: c_int,
+}
+
+/// What upstream's `ReceiptClaim` boils down to on this path (include/hfb200.h: receipt claims).
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct hfb200_claim {
+    pub pre: [u32; 8],
+    pub post: [u32; 8],
+    pub output: [u32; 8],
+    pub exit_code: u32,
+}
+pub const HFB200_EXIT_HALTED: u32 = 0;
+pub const HFB200_EXIT_SYSTEM_SPLIT: u32 = 1;
+pub const HFB200_BLIND_OS_ENTROPY: c_int = 0;
+pub const HFB200_BLIND_DETERMINISTIC: c_int = 1;
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct hfb200_pool_stats_t {
+    pub contexts: usize,
+    pub contexts_retired: usize,
+    pub faults: u64,
+    pub retries: u64,
+    pub contexts_recreated: u64,
 }
 
 extern "C" {
@@ -88,7 +113,22 @@ extern "C" {
         devices: *const c_int, n_devices: c_int, contexts_per_device: c_int, max_po2: u32, circuit: *const hfb200_circuit_desc,
         out: *mut *mut hfb200_pool,
     ) -> *const c_char;
+    pub fn hfb200_pool_create_ir(
+        devices: *const c_int, n_devices: c_int, contexts_per_device: c_int, max_po2: u32, circuit: *const hfb200_circuit_ir,
+        out: *mut *mut hfb200_pool,
+    ) -> *const c_char;
+    pub fn hfb200_pool_set_blinding(pool: *mut hfb200_pool, mode: c_int) -> *const c_char;
+    pub fn hfb200_pool_stats(pool: *const hfb200_pool, out: *mut hfb200_pool_stats_t) -> *const c_char;
+    pub fn hfb200_set_blinding(ctx: *mut hfb200_ctx, mode: c_int) -> *const c_char;
     pub fn hfb200_pool_prove(pool: *mut hfb200_pool, jobs: *mut hfb200_segment_job, n_jobs: usize) -> *const c_char;
+    pub fn hfb200_digest_bytes(bytes: *const u8, n: usize, out8: *mut u32) -> *const c_char;
+    pub fn hfb200_digest_pair(a8: *const u32, b8: *const u32, out8: *mut u32) -> *const c_char;
+    pub fn hfb200_claim_encode(claim: *const hfb200_claim, globals: *mut u32) -> *const c_char;
+    pub fn hfb200_claim_decode(seal: *const u32, seal_words: usize, out: *mut hfb200_claim) -> *const c_char;
+    pub fn hfb200_claim_next_state(pre8: *const u32, index: u32, po2: u32, post8: *mut u32) -> *const c_char;
+    pub fn hfb200_verify_claims(
+        seals: *const *const u32, seal_words: *const usize, n: usize, image_id8: *const u32, journal: *const u8, journal_len: usize,
+    ) -> *const c_char;
     pub fn hfb200_pool_load_control(pool: *mut hfb200_pool, po2: u32, code: *const u32) -> *const c_char;
     pub fn hfb200_pool_destroy(pool: *mut hfb200_pool);
     /// `Receipt::verify` for one segment seal (host code, no device needed).  Exactly one of `circuit` / `ir` is non-null.

@@ -68,13 +68,16 @@ typedef struct {
 /* Replaces `segment_prover(hashfn)` / HAL construction.  Allocates the device arena for segments up to
  * 2^max_po2 cycles (12 <= max_po2 <= 22) and registers the circuit. */
 const char* hfb200_init(int device, uint32_t max_po2, const hfb200_circuit_desc* circuit, hfb200_ctx** out);
-/* Same, for a circuit given as data. */
 const char* hfb200_init_ir(int device, uint32_t max_po2, const hfb200_circuit_ir* circuit, hfb200_ctx** out);
-/* The CUDA source hfb200_init_ir compiles (NVRTC, sm_100a) for the circuit's eval_check: straight-line code, one thread
- * per LDE row.  Needs no device.  Writes at most `cap` bytes including the terminating NUL; *need = bytes required. */
+/* Same, for a circuit given as data.  The constraint polynomial is cut along its top-level AndEqz / AndCond chain into chunks of
+ * ~400 steps (HFB200_IR_CHUNK); every chunk becomes one straight-line kernel (its body looped over the rows, so that it runs out of the
+ * instruction cache), specialised with NVRTC for sm_100a AND for the segment
+ * size (tap offsets become literals): compiled on up to 8 host threads at init for max_po2, for other sizes when first proved. */
+/* The CUDA source of those kernels for po2 = 20 (one thread per LDE row, one kernel per chunk).  Needs no device.  Writes at most
+ * `cap` bytes including the terminating NUL; *need = bytes required. */
 const char* hfb200_ir_source(const hfb200_circuit_ir* circuit, char* out, size_t cap, size_t* need);
 /* 1 when the context's eval_check runs the NVRTC-specialised kernel, 0 when it runs the interpreter kernel (built-in
- * circuit: 0).  *compile_ms (may be NULL) = time hfb200_init_ir spent generating + compiling + loading it. */
+ * circuit: 0).  *compile_ms (may be NULL) = wall time of the most recent specialisation (source + NVRTC on <= 8 threads + load). */
 int hfb200_ir_jit_active(const hfb200_ctx* ctx, float* compile_ms);
 void hfb200_destroy(hfb200_ctx* ctx);
 void hfb200_free_error(const char* msg);

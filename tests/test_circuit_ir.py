@@ -102,3 +102,49 @@ def test_jit_source_compiles_for_sm100a(pkg, tmp_path, variant, nest):
     with pytest.raises(pkg.Hfb200Error):
         bad = dict(ir); bad["ret"] = 10 ** 6
         pkg.ir_source(bad, widths)
+
+
+def test_chunked_program_equals_the_monolithic_one(pkg, emu_lib, orc, monkeypatch):
+    """The constraint polynomial cut into chunks along its top-level AndEqz / AndCond chain (what lets rv32im-sized circuits compile)
+    gives the same seal as one program: chunk limit forced down to 64 steps so that the stand-in circuit splits into ~20 chunks,
+    including cuts inside runs of AND_COND groups."""
+    from oracle import synth_ir
+    widths, po2 = (16, 64, 16), 12
+    cir = orc.Circuit(*widths, variant=1)
+    code = cir.gen_code(po2); g = cir.gen_globals(5); data = cir.gen_data(po2, code, g, 5, 1)
+    ir = synth_ir.build(widths, 1, nest=True)
+    cir_ir = orc.Circuit(*widths, variant=1)
+    cir_ir.set_ir(ir["taps"], ir["steps"], ir["ret"])
+    oseal, ocps, _ = cir_ir.prove(po2, g, code, data, 1)
+    for chunk in ("64", "150", "100000"):
+        monkeypatch.setenv("HFB200_IR_CHUNK", chunk)
+        with pkg.Context(0, po2, widths, lib=emu_lib, ir=ir) as c:
+            mix = c.segment_begin(po2, g, code, data, 1)
+            seal = c.segment_finish(cir.step_accum(po2, data, mix, 1))
+            assert len(seal) == len(oseal) and (seal == oseal).all(), chunk
+        src = pkg.ir_source(ir, widths, lib=emu_lib)
+        n_kernels = src.count("__global__")
+        assert (n_kernels == 1) == (chunk == "100000") and (chunk != "64" or n_kernels >= 10)
+
+
+def test_data_defined_circuit_at_rv32im_scale(pkg, emu_lib, orc):
+    """the data-defined path at the SCALE of rv32im-v2 -- ~13 k PolyExtSteps here (the 51 k-step variant runs on
+    the GPU tier), W = 400 columns, ~1100 taps with 4 distinct back values and 8 distinct tap sets (the library's declared limits):
+    the kernels (emulator build) interpreting the chunked bytecode produce the oracle's seal word for word."""
+    from oracle import synth_ir
+    ir = synth_ir.build_scaled(n_groups=140)
+    W, po2 = ir["widths"], 12
+    assert len(ir["steps"]) > 12000 and len(ir["taps"]) > 1000
+    rng = np.random.default_rng(3)
+    cir = orc.Circuit(*W)
+    code = cir.gen_code(po2); g = cir.gen_globals(9)
+    data = rng.integers(0, orc.P, size=(W[1], 1 << po2), dtype=np.uint32)
+    cir_ir = orc.Circuit(*W)
+    cir_ir.set_ir(ir["taps"], ir["steps"], ir["ret"])
+    oseal, ocps, _ = cir_ir.prove(po2, g, code, data, 1)
+    with pkg.Context(0, po2, W, lib=emu_lib, ir=ir) as c:
+        mix = c.segment_begin(po2, g, code, data, 1)
+        assert (mix == ocps["accum_mix"]).all()
+        seal = c.segment_finish(cir.step_accum(po2, data, mix, 1))
+        assert len(seal) == len(oseal) and (seal == oseal).all()
+        assert (c.checkpoint("check_root") == ocps["check_root"]).all()

@@ -332,3 +332,35 @@ def test_jit_and_interpreter_agree_on_gpu(pkg, gpu_lib, orc, monkeypatch):
             mix = c.segment_begin(po2, g, code, data, 1)
             seals[mode] = c.segment_finish(cir.step_accum(po2, data, mix, 1))
     assert (seals["1"] == oseal).all() and (seals["0"] == oseal).all()
+
+
+@pytest.mark.gpu
+def test_data_defined_circuit_at_rv32im_scale_on_gpu(pkg, gpu_lib, orc, monkeypatch):
+    """~51 k PolyExtSteps, W = 400, ~1100 taps at the declared limits (4 back values, 8 tap sets).  The NVRTC-specialised
+    chunk kernels (default) and the interpreter kernel (HFB200_IR_JIT=0) both give the oracle's seal; the pool over a data-defined circuit
+    (hfb200_pool_create_ir) refuses one-shot jobs with the documented reason."""
+    from oracle import synth_ir
+    ir = synth_ir.build_scaled(n_groups=560)
+    W, po2 = ir["widths"], 12
+    assert len(ir["steps"]) > 50000
+    rng = np.random.default_rng(3)
+    cir = orc.Circuit(*W)
+    code = cir.gen_code(po2); g = cir.gen_globals(9)
+    data = rng.integers(0, orc.P, size=(W[1], 1 << po2), dtype=np.uint32)
+    cir_ir = orc.Circuit(*W)
+    cir_ir.set_ir(ir["taps"], ir["steps"], ir["ret"])
+    oseal, ocps, _ = cir_ir.prove(po2, g, code, data, 1)
+    for mode in ("1", "0"):
+        monkeypatch.setenv("HFB200_IR_JIT", mode)
+        with pkg.Context(0, po2, W, lib=gpu_lib, ir=ir) as c:
+            active, ms = c.ir_jit_active()
+            assert active == (mode == "1")
+            if active:
+                print("rv32im-scale IR: %d steps, NVRTC %.1f s" % (len(ir["steps"]), ms / 1e3))
+            mix = c.segment_begin(po2, g, code, data, 1)
+            seal = c.segment_finish(cir.step_accum(po2, data, mix, 1))
+            assert len(seal) == len(oseal) and (seal == oseal).all(), mode
+    monkeypatch.setenv("HFB200_IR_JIT", "0")
+    with pkg.Pool(devices=(0,), contexts_per_device=1, max_po2=po2, circuit=W, lib=gpu_lib, ir=ir) as pool:
+        _, _, _, errs = pool.prove([(po2, g, code, data, 1)], 1 << 18, return_errors=True)
+        assert errs[0] is not None and "step_accum is the caller's" in errs[0]
