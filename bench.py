@@ -224,6 +224,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-control-cache", action="store_true", help="skip the informational e2e leg with the control group kept on the device")
     ap.add_argument("--no-camt53", action="store_true", help="skip the measured 37-segment proof")
+    ap.add_argument("--ir-scale", action="store_true", help="run tools/ir_scale_probe.py live (51 k-step data-defined circuit; ~1 min) instead of quoting profiles/r2_ir_scale.json")
     ap.add_argument("--inflight", type=int, default=4, help="prover contexts (segments in flight) per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -471,6 +472,24 @@ def main():
                          "one W=256 segment of 2^%d cycles: %.2f s, x%d linear in cycles = %.4f segments/s" % (spo2, times[0], int(scale), scaled_value),
                "full_size_seconds": full, "scaled_sample_segments_per_s": scaled_value}
 
+    # the data-defined circuit path at rv32im-v2 scale (51 k PolyExtSteps, W = 400): a static capture of tools/ir_scale_probe.py on this
+    # pool's B200 (profiles/r2_ir_scale.json) unless --ir-scale asks for a live run
+    ir_obj = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_ir_scale.json")) as f:
+            ir_obj = json.load(f)
+            ir_obj["measured_by_this_run"] = False
+    except Exception:
+        pass
+    if args.ir_scale and rank == 0:
+        for c in ctxs[1:]:
+            c.close()
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ir_scale_probe.py"), "run", str(min(po2, 20))], capture_output=True, text=True)
+        try:
+            ir_obj = json.loads(r.stdout.strip().splitlines()[-1])
+            ir_obj["measured_by_this_run"] = True
+        except Exception:
+            ir_obj = {"error": (r.stderr or r.stdout)[-400:]}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "host_wall_ms_per_step": host_wall * 1e3 / args.steps, "timing": "CUDA events on the prover streams (hfb200_mark), earliest start to latest end over the contexts, max over ranks",
@@ -486,7 +505,7 @@ def main():
                            "host_syncs_per_segment": stage.get("host_syncs", 0.0) / args.steps},
                 "stages_ms_per_segment": {k: v / args.steps for k, v in stage.items() if k.startswith("ms_")},
                 "stages_note": "CUDA events on the library stream, one context in flight (kernel durations undisturbed); value/e2e use %d contexts in flight" % F,
-                "roofline": roofline, "poseidon2": poseidon, "cpu_baseline": cpu, "e2e": e2e, "camt53": camt53,
+                "roofline": roofline, "poseidon2": poseidon, "cpu_baseline": cpu, "e2e": e2e, "camt53": camt53, "ir": ir_obj,
                 "gpu_launches": launches_all, "clocks": clocks}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
