@@ -189,6 +189,7 @@ struct DeepMixArgs {
     const E4 *INV, *INV4;
     uint32_t* out;           // [4][n]
     E4 U0, U1a, U1b, Vc;     // combo_u: {0} -> U0 ; {0,1} -> U1a + U1b*y ; check -> Vc
+    const E4* uvec;          // when non-NULL: the same four values in device memory (transcript on the device)
     uint32_t omega;          // w_N (Montgomery)
     uint32_t po2;
     RootTables rt;
@@ -217,11 +218,12 @@ struct DeepMixKernel {
         const uint32_t m3 = fneg(THREE);
         const E4 d0 = e4_scale(p.INV[i], m3);
         const E4 d1 = e4_scale(p.INV[(i + 1) & (n - 1)], fmul(m3, p.omega));
-        E4 r = e4_mul(e4_sub(c0, p.U0), d0);
-        const E4 u1 = e4_add(p.U1a, e4_scale(p.U1b, y));
+        const E4 U0 = p.uvec ? p.uvec[0] : p.U0, U1a = p.uvec ? p.uvec[1] : p.U1a, U1b = p.uvec ? p.uvec[2] : p.U1b, Vc = p.uvec ? p.uvec[3] : p.Vc;
+        E4 r = e4_mul(e4_sub(c0, U0), d0);
+        const E4 u1 = e4_add(U1a, e4_scale(U1b, y));
         r = e4_add(r, e4_mul(e4_mul(e4_sub(c1, u1), d0), d1));
         const E4 s = e4(p.S[i], p.S[n + i], p.S[2 * n + i], p.S[3 * n + i]);
-        r = e4_add(r, e4_mul(e4_sub(s, p.Vc), p.INV4[i]));
+        r = e4_add(r, e4_mul(e4_sub(s, Vc), p.INV4[i]));
         for (int k = 0; k < 4; k++) p.out[(uint64_t)k * n + i] = r.c[k];
     }
 };

@@ -108,6 +108,14 @@ const char* hfb200_set_blinding(hfb200_ctx* ctx, int mode) {
     API_CATCH
 }
 
+const char* hfb200_set_transcript(hfb200_ctx* ctx, int on_device) {
+    API_TRY
+    if (!ctx) throw Err("hfb200_set_transcript: NULL ctx");
+    if (ctx->p.begun) throw Err("hfb200_set_transcript: a segment is in flight");
+    ctx->p.transcript_mode = on_device ? 1 : 0;
+    API_CATCH
+}
+
 const char* hfb200_host_alloc(size_t bytes, void** out) {
     API_TRY
     if (!out) throw Err("hfb200_host_alloc: out is NULL");
@@ -131,8 +139,8 @@ const char* hfb200_prove_segment(hfb200_ctx* ctx, uint32_t po2, const uint32_t* 
                                  uint64_t blind_seed, uint32_t* seal_out, size_t seal_cap, size_t* seal_words) {
     API_TRY
     if (!ctx || !globals || !data) throw Err("hfb200_prove_segment: NULL argument");
-    ctx->p.begin(po2, globals, code, data, blind_seed);
-    ctx->p.finish(nullptr, ctx->seal);
+    if (ctx->p.device_transcript()) ctx->p.prove_device(po2, globals, code, data, blind_seed, ctx->seal);
+    else { ctx->p.begin(po2, globals, code, data, blind_seed); ctx->p.finish(nullptr, ctx->seal); }
     if (const char* e = emit_seal(ctx, seal_out, seal_cap, seal_words)) return e;
     API_CATCH
 }
@@ -169,8 +177,8 @@ const char* hfb200_prove_resident(hfb200_ctx* ctx, uint64_t blind_seed, uint32_t
     if (!ctx->p.have_trace) throw Err("hfb200_prove_resident: no resident trace (call hfb200_witgen_synth)");
     uint32_t g[N_GLOBAL];
     std::memcpy(g, ctx->p.globals, sizeof g);
-    ctx->p.begin(ctx->p.po2, g, nullptr, nullptr, blind_seed);
-    ctx->p.finish(nullptr, ctx->seal);
+    if (ctx->p.device_transcript()) ctx->p.prove_device(ctx->p.po2, g, nullptr, nullptr, blind_seed, ctx->seal);
+    else { ctx->p.begin(ctx->p.po2, g, nullptr, nullptr, blind_seed); ctx->p.finish(nullptr, ctx->seal); }
     if (const char* e = emit_seal(ctx, seal_out, seal_cap, seal_words)) return e;
     API_CATCH
 }

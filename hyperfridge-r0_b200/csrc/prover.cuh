@@ -11,6 +11,7 @@
 #include "circuit.cuh"
 #include "deep.cuh"
 #include "jit.cuh"
+#include "transcript.cuh"
 #ifndef HFB200_EMU
 #include <nvtx3/nvToolsExt.h>  // header-only; ranges are no-ops unless a tool (nsys) injects the NVTX library
 #endif
@@ -310,8 +311,10 @@ struct Prover {
         commit_tree(Tree{ev[g], D, (uint32_t)D, w, nodes[g]}, cp_name);
     }
 
-    // ---- SegmentProver::prove, phase 1: header + CODE + DATA commits, returns the accum mix ----
-    void begin(uint32_t p, const uint32_t* globals_h, const uint32_t* code_h, const uint32_t* data_h, uint64_t blind) {
+    // checks the arguments, resets the per-segment state and queues the host->device copies of the trace (data columns in
+    // H2D_CHUNKS slices on the copy stream).  Returns whether the data copy is chunked / the cached control group is used.
+    struct Staged { bool chunked, use_control; };
+    Staged stage_inputs(uint32_t p, const uint32_t* globals_h, const uint32_t* code_h, const uint32_t* data_h, uint64_t blind) {
         t_begin = std::chrono::steady_clock::now();
         bind();
         layout(p);
@@ -349,6 +352,30 @@ struct Prover {
         const bool use_control = !code_h && data_h && control_cached;
         if (code_h) { control_cached = false; control_gen = 0; }  // the resident control columns change
         if (data_h) have_trace = true;
+        return Staged{chunked, use_control};
+    }
+    // LDE of the data group, slice by slice as the chunked copies land (or in one piece)
+    void lde_data(bool chunked) {
+        const size_t N = (size_t)1 << po2, D = 4 * N;
+#ifndef HFB200_EMU
+        if (chunked) {
+            for (int k = 0; k < H2D_CHUNKS; k++) {
+                const uint32_t c0 = cir.cd.w_data * k / H2D_CHUNKS, c1 = cir.cd.w_data * (k + 1) / H2D_CHUNKS;
+                CUDA_CHECK(cudaStreamWaitEvent(dev.stream, chunk_ev[k], 0));
+                ntt.lde(tr[GROUP_DATA] + (size_t)c0 * N, N, ev[GROUP_DATA] + (size_t)c0 * D, D, scratch, c1 - c0, (int)po2);
+            }
+            return;
+        }
+#endif
+        (void)chunked;
+        ntt.lde(tr[GROUP_DATA], N, ev[GROUP_DATA], D, scratch, cir.cd.w_data, (int)po2);
+    }
+
+    // ---- SegmentProver::prove, phase 1: header + CODE + DATA commits, returns the accum mix ----
+    void begin(uint32_t p, const uint32_t* globals_h, const uint32_t* code_h, const uint32_t* data_h, uint64_t blind) {
+        const Staged sg = stage_inputs(p, globals_h, code_h, data_h, blind);
+        const bool chunked = sg.chunked, use_control = sg.use_control;
+        const size_t N = (size_t)1 << po2;
         mark(1);
         const Digest8 gh = host_hash_elems(globals, N_GLOBAL);
         rng.mix(gh.w);
@@ -364,22 +391,14 @@ struct Prover {
             commit_group(GROUP_CODE, "code_root", 1, 2, 3);
         }
         StageRange r_data("hfb200:commit_data");
-        if (chunked) {
-#ifndef HFB200_EMU
+        {
             const size_t D = 4 * N;
             mark(3);
-            for (int k = 0; k < H2D_CHUNKS; k++) {
-                const uint32_t c0 = cir.cd.w_data * k / H2D_CHUNKS, c1 = cir.cd.w_data * (k + 1) / H2D_CHUNKS;
-                CUDA_CHECK(cudaStreamWaitEvent(dev.stream, chunk_ev[k], 0));
-                ntt.lde(tr[GROUP_DATA] + (size_t)c0 * N, N, ev[GROUP_DATA] + (size_t)c0 * D, D, scratch, c1 - c0, (int)po2);
-            }
+            lde_data(chunked);
             mark(4);
             merkle.build(ev[GROUP_DATA], D, (uint32_t)D, cir.cd.w_data, nodes[GROUP_DATA]);
             mark(5);
             commit_tree(Tree{ev[GROUP_DATA], D, (uint32_t)D, cir.cd.w_data, nodes[GROUP_DATA]}, "data_root");
-#endif
-        } else {
-            commit_group(GROUP_DATA, "data_root", 3, 4, 5);
         }
         stage_ms[0] = between(0, 1);
         stage_ms[1] = between(1, 2) + between(3, 4);
@@ -754,6 +773,225 @@ struct Prover {
         stats.host_syncs = host_syncs - host_syncs_at_begin;
         emit_metrics();
         seal_out = proof;
+    }
+
+    // ---- SegmentProver::prove with the transcript on the device (built-in circuit, one-shot entries) -------------------------
+    // Same kernels and the same seal as begin() + finish(); what differs is WHO runs the transcript: every Fiat-Shamir step is a
+    // one-warp kernel on the stream (transcript.cuh), the parameters it derives stay in device memory, the seal is assembled in
+    // a device buffer.  The host enqueues the whole segment and synchronises ONCE, for the seal (10 times on the host path).
+    // OPT-IN (HFB200_DEVICE_TRANSCRIPT=1 or hfb200_set_transcript): measured on B200 it is ~1 % SLOWER than the host transcript
+    // at 1, 2 and 4 contexts in flight (18.74 / 19.47 / 19.81 against 18.95 / 19.54 / 19.86 segments/s at po2 = 20; 6.19 against
+    // 5.54 ms for one po2 = 16 segment): a segment's transcript is ~170 SEQUENTIAL Poseidon2 permutations (92 for hash_u, 64 for the
+    // final coefficients, 13 for the query draws), a warp-cooperative permutation takes ~3.3 us on the GPU against ~1 us on a host
+    // core, and the stream synchronisations it removes cost less than that.  It pays where host threads are the scarce resource.
+    int transcript_mode = -1;  // -1: environment, 0: host, 1: device
+    bool device_transcript() const {
+        static const bool env_on = [] { const char* e = std::getenv("HFB200_DEVICE_TRANSCRIPT"); return e && std::atoi(e) != 0; }();
+        return (transcript_mode < 0 ? env_on : transcript_mode == 1) && !gen.active;
+    }
+    void prove_device(uint32_t p, const uint32_t* globals_h, const uint32_t* code_h, const uint32_t* data_h, uint64_t blind, std::vector<uint32_t>& seal_out) {
+        const Staged sg = stage_inputs(p, globals_h, code_h, data_h, blind);
+        begun = false;
+        const size_t N = (size_t)1 << po2, D = 4 * N;
+        const CircuitDev& cd = cir.cd;
+        const uint32_t W = cir.n_regs(), T = cir.n_taps, n_mix = cir.n_mix();
+        const size_t words = seal_words(po2);
+        uint32_t* d_seal = arena.take<uint32_t>(words);
+        uint32_t* d_cp = arena.take<uint32_t>(CP_WORDS);
+        TxState* d_tx = arena.take<TxState>(1);
+        TxParams* d_tp = arena.take<TxParams>(1);
+        if (n_mix > 4096) throw Err("internal: accum mix larger than the checkpoint buffer");
+        // header: the globals are the caller's, so their hash and the RNG state after mixing it are computed here and uploaded
+        const Digest8 gh = host_hash_elems(globals, N_GLOBAL);
+        {
+            HostRng r0; r0.mix(gh.w);
+            TxState h{};
+            std::memcpy(h.cells, r0.cells, sizeof h.cells);
+            h2d_small(d_tx, &h, sizeof h);
+            uint32_t head[N_GLOBAL + 1];
+            std::memcpy(head, globals, sizeof globals); head[N_GLOBAL] = po2;
+            h2d_small(d_seal, head, sizeof head);
+        }
+        size_t off = N_GLOBAL + 1;
+        const MerkleShape ms0((uint32_t)D);
+        auto commit = [&](const uint32_t* nd, const MerkleShape& ms, uint32_t cp_off) {
+            dev.launch<TxCommitKernel, 32, 1>(1, 1, 32, 0, d_tx, nd, ms.top_size, d_seal + off, d_cp + cp_off);
+            off += (size_t)8 * ms.top_size;
+        };
+        mark(1);
+        // CODE
+        if (sg.use_control) { mark(2); mark(3); }
+        else {
+            StageRange r("hfb200:commit_code");
+            ntt.lde(tr[GROUP_CODE], N, ev[GROUP_CODE], D, scratch, cd.w_code, (int)po2);
+            mark(2);
+            merkle.build(ev[GROUP_CODE], D, (uint32_t)D, cd.w_code, nodes[GROUP_CODE]);
+            mark(3);
+        }
+        commit(nodes[GROUP_CODE], ms0, CP_CODE_ROOT);
+        // DATA
+        {
+            StageRange r("hfb200:commit_data");
+            lde_data(sg.chunked);
+            mark(4);
+            merkle.build(ev[GROUP_DATA], D, (uint32_t)D, cd.w_data, nodes[GROUP_DATA]);
+            mark(5);
+            commit(nodes[GROUP_DATA], ms0, CP_DATA_ROOT);
+            dev.launch<TxDrawElemsKernel, 32, 1>(1, 1, 32, 0, d_tx, d_mix, n_mix, d_cp + CP_ACCUM_MIX);
+        }
+        // ACCUM
+        {
+            StageRange r("hfb200:commit_accum");
+            step_accum();
+            mark(6);
+            ntt.lde(tr[GROUP_ACCUM], N, ev[GROUP_ACCUM], D, scratch, cd.w_accum, (int)po2);
+            mark(7);
+            merkle.build(ev[GROUP_ACCUM], D, (uint32_t)D, cd.w_accum, nodes[GROUP_ACCUM]);
+            mark(8);
+            commit(nodes[GROUP_ACCUM], ms0, CP_ACCUM_ROOT);
+        }
+        // check polynomial
+        nvtx_push("hfb200:check");
+        uint32_t yinv4[4];
+        {
+            const uint32_t three_n = fpow(THREE, N), w4 = rou_fwd(2);
+            uint32_t y = three_n;
+            for (int s = 0; s < 4; s++) { yinv4[s] = finv(fsub(y, ONE)); y = fmul(y, w4); }
+        }
+        {
+            const uint32_t nc = cd.n_constraints();
+            E4* d_mp = arena.take<E4>(nc);
+            dev.launch<TxPolyMixKernel, 32, 1>(1, 1, 32, 0, d_tx, d_tp, d_mp, nc, d_cp + CP_POLY_MIX);
+            EvalCheckArgs a{};
+            a.ev_accum = ev[GROUP_ACCUM]; a.ev_code = ev[GROUP_CODE]; a.ev_data = ev[GROUP_DATA];
+            a.check = check; a.mixpow = d_mp; a.mix = d_mix; a.global0 = globals[0];
+            for (int s_ = 0; s_ < 4; s_++) a.yinv[s_] = yinv4[s_];
+            a.po2 = po2; a.cd = cd;
+            a.rows_per_block = 128;
+            dev.launch<EvalCheckKernel, 128, 1>((unsigned)((D + 127) / 128), 1, 128, (size_t)nc * sizeof(E4) + (size_t)6 * cd.n_free * 2 + 16, a);
+        }
+        ntt.interpolate(check, D, check, D, 4, (int)po2 + 2, false);
+        ntt.expand_evaluate(check, N, ev_check, D, CHECK_SIZE, (int)po2, 2);
+        merkle.build(ev_check, D, (uint32_t)D, CHECK_SIZE, nodes_check);
+        mark(9);
+        commit(nodes_check, ms0, CP_CHECK_ROOT);
+        nvtx_pop();
+        // DEEP
+        nvtx_push("hfb200:deep");
+        const uint32_t omega = rou_fwd((int)po2), back_one = finv(omega);
+        dev.launch<TxDeepPointKernel, 32, 1>(1, 1, 32, 0, d_tx, d_tp, po2, finv(to_mont((uint32_t)(N % P))), d_cp + CP_Z);
+        E4* INV = arena.take<E4>(N); E4* Lw = arena.take<E4>(N); E4* INV4 = arena.take<E4>(N); E4* W4 = arena.take<E4>(N);
+        dev.launch<DeepWeightsKernelD, 256, 1>((unsigned)((N + 255) / 256), 1, 256, 0, INV, Lw, INV4, (const TxParams*)d_tp, po2, ntt.rt);
+        dev.launch<PowBitrevKernel, 256, 1>((unsigned)((N + 255) / 256), 1, 256, 0, W4, (const E4*)d_tp->xs, po2);
+        E4* d_evals = arena.take<E4>((size_t)2 * (W + CHECK_SIZE));
+        const uint32_t goff[4] = {0, 2 * cd.w_accum, 2 * (cd.w_accum + cd.w_code), 2 * W};
+        for (int g = 0; g < 3; g++) dot_group(tr[g], cir.group_width(g), cir.group_back1(g), Lw, d_evals + goff[g]);
+        dot_group(check, CHECK_SIZE, 0, W4, d_evals + goff[3]);
+        E4* d_coeff_u = arena.take<E4>(T + CHECK_SIZE);
+        E4* d_regmix = arena.take<E4>(W + CHECK_SIZE);
+        {
+            TxCoeffUArgs a{};
+            a.t = d_tx; a.p = d_tp; a.evals = d_evals;
+            for (int g = 0; g < 4; g++) a.goff[g] = goff[g];
+            for (int g = 0; g < 3; g++) { a.w[g] = cir.group_width(g); a.back1[g] = cir.group_back1(g); }
+            a.n_taps = T; a.back_one = back_one; a.coeff_u = d_coeff_u; a.seal_dst = d_seal + off; a.regmix = d_regmix; a.cp = d_cp;
+            dev.launch<TxCoeffUKernel, 32, 1>(1, 1, 32, (32 + 32 * 16) * 4, a);
+            off += (size_t)4 * (T + CHECK_SIZE);
+        }
+        uint32_t* S0 = arena.take<uint32_t>(4 * N);
+        uint32_t* S1 = arena.take<uint32_t>(4 * N);
+        uint32_t* fin = arena.take<uint32_t>(4 * N);
+        dev.launch<CheckMixKernel, 256, 1>((unsigned)((N + 255) / 256), 1, 256, 0, (const uint32_t*)check, (const E4*)(d_regmix + W), S0, po2, ntt.rt);
+        ntt.expand_evaluate(S0, N, S1, N, 4, (int)po2, 0);
+        {
+            DeepMixArgs da{};
+            da.U0 = da.U1a = da.U1b = da.Vc = e4_zero();
+            da.uvec = d_tp->uvec;
+            for (int g = 0; g < 3; g++) { da.tr[g] = tr[g]; da.w[g] = cir.group_width(g); da.n_back1[g] = cir.group_back1(g); }
+            da.mixpow = d_regmix; da.S = S1; da.INV = INV; da.INV4 = INV4; da.out = fin; da.omega = omega; da.po2 = po2; da.rt = ntt.rt;
+            dev.launch<DeepMixKernel, 256, 1>((unsigned)((N + 255) / 256), 1, 256, 0, da);
+        }
+        ntt.interpolate(fin, N, fin, N, 4, (int)po2, true);
+        mark(10);
+        nvtx_pop();
+        // FRI
+        nvtx_push("hfb200:fri");
+        std::vector<TxTreeInfo> trees;
+        trees.push_back(TxTreeInfo{ev[0], nodes[0], D, (uint32_t)D, cd.w_accum, ms0.top_size, 0});
+        trees.push_back(TxTreeInfo{ev[1], nodes[1], D, (uint32_t)D, cd.w_code, ms0.top_size, 0});
+        trees.push_back(TxTreeInfo{ev[2], nodes[2], D, (uint32_t)D, cd.w_data, ms0.top_size, 0});
+        trees.push_back(TxTreeInfo{ev_check, nodes_check, D, (uint32_t)D, CHECK_SIZE, ms0.top_size, 0});
+        uint32_t* coeffs = fin;
+        size_t n = N;
+        uint32_t round = 0;
+        uint32_t query_words = W + CHECK_SIZE + 4 * ms0.path_words();
+        while (n > FRI_MIN_DEGREE) {
+            if (round >= TX_MAX_FRI_ROUNDS) throw Err("internal: more FRI rounds than TxParams holds");
+            const size_t dom = n * INV_RATE, rows = dom / FRI_FOLD;
+            uint32_t* evr = arena.take<uint32_t>(4 * dom);
+            uint32_t* ndr = arena.take<uint32_t>(2 * rows * 8);
+            ntt.expand_evaluate(coeffs, n, evr, dom, 4, ilog2(n), 2);
+            merkle.build(evr, rows, (uint32_t)rows, FRI_FOLD * 4, ndr);
+            const MerkleShape mr((uint32_t)rows);
+            dev.launch<TxFriCommitKernel, 32, 1>(1, 1, 32, 0, d_tx, d_tp, (const uint32_t*)ndr, mr.top_size, d_seal + off, round, d_cp);
+            off += (size_t)8 * mr.top_size;
+            uint32_t* out = arena.take<uint32_t>(4 * n / FRI_FOLD);
+            dev.launch<FriFoldKernelD, 256, 1>((unsigned)((n / 16 + 255) / 256), 1, 256, 0, (const uint32_t*)coeffs, out, (uint32_t)n, (const E4*)d_tp->fri_mixpow[round]);
+            trees.push_back(TxTreeInfo{evr, ndr, rows, (uint32_t)rows, FRI_FOLD * 4, mr.top_size, 0});
+            query_words += FRI_FOLD * 4 + mr.path_words();
+            coeffs = out;
+            n /= FRI_FOLD;
+            round++;
+        }
+        uint32_t* nat = arena.take<uint32_t>(4 * n);
+        dev.launch<BitRevKernel, 256, 1>((unsigned)((4 * n + 255) / 256), 1, 256, 0, (const uint32_t*)coeffs, nat, 4u, (uint32_t)ilog2(n));
+        {
+            TxTreeInfo* d_trees = arena.take<TxTreeInfo>(trees.size());
+            h2d_small(d_trees, trees.data(), trees.size() * sizeof(TxTreeInfo));
+            const size_t n_desc = (size_t)QUERIES * trees.size();
+            OpenDesc* d_descs = arena.take<OpenDesc>(n_desc);
+            TxQueriesArgs a{};
+            a.t = d_tx; a.p = d_tp; a.final_nat = nat; a.final_words = (uint32_t)(4 * n); a.seal_final = d_seal + off;
+            a.trees = d_trees; a.n_main = 4; a.n_rounds = round; a.domain_bits = (uint32_t)ilog2(D); a.descs = d_descs; a.query_words = query_words; a.cp = d_cp;
+            dev.launch<TxQueriesKernel, 32, 1>(1, 1, 32, 32 * 4, a);
+            off += 4 * n;
+            dev.launch<OpenKernel, 128, 1>((unsigned)n_desc, 1, 128, 0, (const OpenDesc*)d_descs, d_seal + off);
+            off += (size_t)QUERIES * query_words;
+        }
+        if (off != words) throw Err("internal: seal layout mismatch");
+        mark(11);
+        seal_out.resize(words);
+        std::vector<uint32_t> cp(CP_ACCUM_MIX + n_mix);
+        dev.d2h(seal_out.data(), d_seal, words * 4);
+        dev.d2h(cp.data(), d_cp, cp.size() * 4);
+        std::vector<uint32_t> fc;
+        if (debug_checkpoints) { fc.resize(4 * N); dev.d2h(fc.data(), fin, fc.size() * 4); }
+        sync();  // the only synchronisation of the segment
+        nvtx_pop();
+        // checkpoints, under the names of the host-transcript path
+        cp_add("globals_hash", gh.w, 8);
+        cp_add("code_root", &cp[CP_CODE_ROOT], 8); cp_add("data_root", &cp[CP_DATA_ROOT], 8);
+        cp_add("accum_mix", &cp[CP_ACCUM_MIX], n_mix);
+        cp_add("accum_root", &cp[CP_ACCUM_ROOT], 8); cp_add("poly_mix", &cp[CP_POLY_MIX], 4); cp_add("check_root", &cp[CP_CHECK_ROOT], 8);
+        cp_add("z", &cp[CP_Z], 4); cp_add("hash_u", &cp[CP_HASH_U], 8); cp_add("deep_mix", &cp[CP_DEEP_MIX], 4);
+        if (debug_checkpoints) { const Digest8 d = host_hash_elems(fc.data(), fc.size()); cp_add("final_poly_hash", d.w, 8); }
+        for (uint32_t r = 0; r < round; r++) { cp_add("fri_root_" + std::to_string(r), &cp[CP_FRI_ROOT0 + 8 * r], 8); cp_add("fri_mix_" + std::to_string(r), &cp[CP_FRI_MIX0 + 4 * r], 4); }
+        cp_add("fri_final_hash", &cp[CP_FRI_FINAL_HASH], 8);
+        cp_add("query_positions", &cp[CP_POSITIONS], QUERIES);
+        mix.assign(cp.begin() + CP_ACCUM_MIX, cp.begin() + CP_ACCUM_MIX + n_mix);
+        stage_ms[0] = between(0, 1);
+        stage_ms[1] = between(1, 2) + between(3, 4) + between(6, 7);
+        stage_ms[2] = between(2, 3) + between(4, 5) + between(7, 8);
+        stage_ms[3] = between(5, 6);
+        stage_ms[4] = between(8, 9); stage_ms[5] = between(9, 10); stage_ms[6] = between(10, 11);
+        stats.ms_h2d = stage_ms[0]; stats.ms_ntt_main = stage_ms[1]; stats.ms_hash_main = stage_ms[2]; stats.ms_accum = stage_ms[3];
+        stats.ms_check = stage_ms[4]; stats.ms_deep = stage_ms[5]; stats.ms_fri = stage_ms[6];
+        stats.ms_device = between(0, 11);
+        stats.ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        stats.launches = dev.launches - launches_at_begin;
+        stats.ntt_main_bytes = 28ull * W * N;
+        stats.host_syncs = host_syncs - host_syncs_at_begin;
+        emit_metrics();
     }
 
     void witgen(uint32_t p, uint64_t trace_seed, uint64_t blind, uint32_t* globals_out) {

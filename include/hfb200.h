@@ -90,6 +90,12 @@ void hfb200_free_error(const char* msg);
  * the seed -- never use it for real statements. */
 enum { HFB200_BLIND_OS_ENTROPY = 0, HFB200_BLIND_DETERMINISTIC = 1 };
 const char* hfb200_set_blinding(hfb200_ctx* ctx, int mode);
+/* Where the Fiat-Shamir transcript (upstream: WriteIOP + Poseidon2Rng on the host) of the ONE-SHOT entries runs for the built-in circuit.
+ * 0 (default): on the host, 10 stream synchronisations per segment, each a true dependency.  1: on the device as one-warp kernels,
+ * the seal assembled in device memory, ONE synchronisation per segment (csrc/transcript.cuh); identical seals.  Measured ~1 % slower on
+ * B200 (a segment's transcript is ~170 sequential Poseidon2 permutations, 3.3 us each on a warp against ~1 us on a host core); for hosts
+ * with few cores per GPU.  HFB200_DEVICE_TRANSCRIPT=1 in the environment selects it for contexts that never call this. */
+const char* hfb200_set_transcript(hfb200_ctx* ctx, int on_device);
 const char* hfb200_version(void);
 
 /* Pinned host memory for trace staging (plain pointers are accepted too, just slower over PCIe). */

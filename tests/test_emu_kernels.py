@@ -127,3 +127,27 @@ def test_odd_circuit_widths(pkg, emu_lib, orc, widths, po2):
         seal = c.prove_segment(po2, g, code, data, 3)
         assert len(seal) == len(oseal) and (seal == oseal).all()
         assert cir.verify(seal, ocps["code_root"]) == po2
+
+
+@pytest.mark.parametrize("widths,po2", [((8, 16, 8), 12), ((16, 64, 16), 13), ((21, 40, 12), 12)])
+def test_device_transcript_gives_the_same_seal(pkg, emu_lib, orc, widths, po2):
+    """hfb200_set_transcript(1): the Fiat-Shamir transcript as one-warp kernels (csrc/transcript.cuh), seal assembled on the device,
+    ONE synchronisation per segment -- the same seal and the same checkpoints as the host transcript and the oracle."""
+    cir = orc.Circuit(*widths)
+    code = cir.gen_code(po2); g = cir.gen_globals(11); data = cir.gen_data(po2, code, g, 11, 4)
+    oseal, ocps, _ = cir.prove(po2, g, code, data, 4)
+    with pkg.Context(0, po2, widths, lib=emu_lib) as c:
+        host = c.prove_segment(po2, g, code, data, 4)
+        assert c.last_stats()["host_syncs"] >= 8   # 4 + FRI rounds roots, tap evaluations, final coefficients, openings
+        c.set_transcript(True)
+        dev = c.prove_segment(po2, g, code, data, 4)
+        assert c.last_stats()["host_syncs"] == 1
+        cps = c.checkpoints()
+        for k, v in ocps.items():
+            if k in cps:
+                assert (cps[k] == v).all(), k
+        assert len(dev) == len(oseal) and (dev == oseal).all() and (host == oseal).all()
+        root = c.control_root(po2, code)                      # cached control group + device transcript
+        assert (c.prove_segment(po2, g, None, data, 4) == oseal).all() and (root == ocps["code_root"]).all()
+        c.witgen_synth(po2, 11, 4)
+        assert (c.prove_resident(4) == oseal).all()           # resident entry

@@ -364,3 +364,36 @@ def test_data_defined_circuit_at_rv32im_scale_on_gpu(pkg, gpu_lib, orc, monkeypa
     with pkg.Pool(devices=(0,), contexts_per_device=1, max_po2=po2, circuit=W, lib=gpu_lib, ir=ir) as pool:
         _, _, _, errs = pool.prove([(po2, g, code, data, 1)], 1 << 18, return_errors=True)
         assert errs[0] is not None and "step_accum is the caller's" in errs[0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("widths,po2", [(SMALL, 12), (DEFAULT, 16), ((21, 40, 12), 13)])
+def test_device_transcript_on_gpu(pkg, gpu_lib, orc, widths, po2, monkeypatch):
+    """The opt-in device-side transcript (warp-cooperative Poseidon2 RNG, seal assembled in HBM, one sync per segment): seal and
+    checkpoints equal the oracle's, through the host-buffer entry, the cached control group and the resident entry."""
+    monkeypatch.setenv("HFB200_DEBUG_CHECKPOINTS", "1")
+    cir, g, code, data = make_segment(orc, widths, po2)
+    oseal, ocps, _ = cir.prove(po2, g, code, data, 1)
+    with pkg.Context(0, po2, widths, lib=gpu_lib) as c:
+        c.set_transcript(True)
+        seal = c.prove_segment(po2, g, code, data, 1)
+        assert c.last_stats()["host_syncs"] == 1              # the seal (the debug checkpoint's read-back shares that synchronisation)
+        cps = c.checkpoints()
+        for k, v in ocps.items():
+            assert (cps[k] == v).all(), k
+        assert len(seal) == len(oseal) and (seal == oseal).all()
+        c.control_root(po2, code)
+        assert (c.prove_segment(po2, g, None, data, 1) == oseal).all()
+        c.witgen_synth(po2, TRACE_SEED, 1)
+        assert (c.prove_resident(1) == oseal).all()
+
+
+@pytest.mark.gpu
+def test_device_transcript_headline_pins(pkg, gpu_lib, orc, monkeypatch):
+    monkeypatch.setenv("HFB200_DEBUG_CHECKPOINTS", "1")
+    gold = _load_pins(20)
+    with pkg.Context(0, 20, tuple(gold["widths"]), lib=gpu_lib) as c:
+        c.set_transcript(True)
+        c.witgen_synth(20, gold["trace_seed"], gold["blind_seed"])
+        seal = c.prove_resident(gold["blind_seed"])
+        _check_against_pins(orc, gold, seal, c.checkpoints())
