@@ -32,6 +32,9 @@ static const char* dup_err(const std::string& s) {
 #define API_TRY try {
 #define API_CATCH } catch (const std::exception& e) { return dup_err(e.what()); } catch (...) { return dup_err("hfb200: unknown error"); } return nullptr;
 
+// An error return must not leave copies from (or to) caller memory in flight: drain both streams before reporting it.
+#define API_CATCH_QUIESCE(ctx_) } catch (const std::exception& e) { if (ctx_) (ctx_)->p.quiesce(); return dup_err(e.what()); } catch (...) { if (ctx_) (ctx_)->p.quiesce(); return dup_err("hfb200: unknown error"); } return nullptr;
+
 static const char* emit_seal(hfb200_ctx* ctx, uint32_t* seal_out, size_t seal_cap, size_t* seal_words) {
     if (seal_words) *seal_words = ctx->seal.size();
     if (seal_cap < ctx->seal.size() || !seal_out) return dup_err("seal buffer too small: need " + std::to_string(ctx->seal.size()) + " words");
@@ -142,7 +145,7 @@ const char* hfb200_prove_segment(hfb200_ctx* ctx, uint32_t po2, const uint32_t* 
     if (ctx->p.device_transcript()) ctx->p.prove_device(po2, globals, code, data, blind_seed, ctx->seal);
     else { ctx->p.begin(po2, globals, code, data, blind_seed); ctx->p.finish(nullptr, ctx->seal); }
     if (const char* e = emit_seal(ctx, seal_out, seal_cap, seal_words)) return e;
-    API_CATCH
+    API_CATCH_QUIESCE(ctx)
 }
 
 const char* hfb200_segment_begin(hfb200_ctx* ctx, uint32_t po2, const uint32_t* globals, const uint32_t* code, const uint32_t* data,
@@ -155,14 +158,14 @@ const char* hfb200_segment_begin(hfb200_ctx* ctx, uint32_t po2, const uint32_t* 
         if (mix_cap < ctx->p.mix.size()) throw Err("mix buffer too small");
         std::memcpy(mix_out, ctx->p.mix.data(), ctx->p.mix.size() * 4);
     }
-    API_CATCH
+    API_CATCH_QUIESCE(ctx)
 }
 const char* hfb200_segment_finish(hfb200_ctx* ctx, const uint32_t* accum_or_null, uint32_t* seal_out, size_t seal_cap, size_t* seal_words) {
     API_TRY
     if (!ctx) throw Err("hfb200_segment_finish: NULL ctx");
     ctx->p.finish(accum_or_null, ctx->seal);
     if (const char* e = emit_seal(ctx, seal_out, seal_cap, seal_words)) return e;
-    API_CATCH
+    API_CATCH_QUIESCE(ctx)
 }
 
 const char* hfb200_witgen_synth(hfb200_ctx* ctx, uint32_t po2, uint64_t trace_seed, uint64_t blind_seed, uint32_t* globals_out) {
@@ -180,7 +183,7 @@ const char* hfb200_prove_resident(hfb200_ctx* ctx, uint64_t blind_seed, uint32_t
     if (ctx->p.device_transcript()) ctx->p.prove_device(ctx->p.po2, g, nullptr, nullptr, blind_seed, ctx->seal);
     else { ctx->p.begin(ctx->p.po2, g, nullptr, nullptr, blind_seed); ctx->p.finish(nullptr, ctx->seal); }
     if (const char* e = emit_seal(ctx, seal_out, seal_cap, seal_words)) return e;
-    API_CATCH
+    API_CATCH_QUIESCE(ctx)
 }
 const char* hfb200_read_group(hfb200_ctx* ctx, uint32_t group, uint32_t* out, size_t cap_words) {
     API_TRY
@@ -468,6 +471,7 @@ struct DevBuf {
 
 const char* hfb200_op_interpolate_ntt(hfb200_ctx* ctx, uint32_t* io, size_t count, size_t n, int zk_shift) {
     API_TRY
+    if (!ctx || !io) throw Err("op_interpolate_ntt: NULL argument");
     ctx->p.bind();
     Dev& d = ctx->p.dev;
     const int lg = ilog2(n);
@@ -481,6 +485,7 @@ const char* hfb200_op_interpolate_ntt(hfb200_ctx* ctx, uint32_t* io, size_t coun
 }
 const char* hfb200_op_expand_ntt(hfb200_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, size_t n_in, uint32_t expand_bits) {
     API_TRY
+    if (!ctx || !out || !in) throw Err("op_expand_ntt: NULL argument");
     ctx->p.bind();
     Dev& d = ctx->p.dev;
     const int lg = ilog2(n_in);
@@ -494,6 +499,7 @@ const char* hfb200_op_expand_ntt(hfb200_ctx* ctx, uint32_t* out, const uint32_t*
 }
 const char* hfb200_op_lde(hfb200_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, size_t n_in) {
     API_TRY
+    if (!ctx || !out || !in) throw Err("op_lde: NULL argument");
     ctx->p.bind();
     Dev& d = ctx->p.dev;
     const int lg = ilog2(n_in);
@@ -507,6 +513,7 @@ const char* hfb200_op_lde(hfb200_ctx* ctx, uint32_t* out, const uint32_t* in, si
 }
 const char* hfb200_op_merkle(hfb200_ctx* ctx, const uint32_t* matrix, size_t rows, size_t cols, uint32_t* nodes_out) {
     API_TRY
+    if (!ctx || !matrix || !nodes_out) throw Err("op_merkle: NULL argument");
     ctx->p.bind();
     Dev& d = ctx->p.dev;
     if ((1ull << ilog2(rows)) != rows || rows < 2 || cols == 0) throw Err("op_merkle: rows must be a power of two >= 2");
@@ -520,6 +527,7 @@ const char* hfb200_op_merkle(hfb200_ctx* ctx, const uint32_t* matrix, size_t row
 }
 const char* hfb200_op_poseidon2(hfb200_ctx* ctx, uint32_t* states, size_t n) {
     API_TRY
+    if (!ctx || (!states && n)) throw Err("op_poseidon2: NULL argument");
     ctx->p.bind();
     Dev& d = ctx->p.dev;
     DevBuf b(d, n * 24);
@@ -531,6 +539,7 @@ const char* hfb200_op_poseidon2(hfb200_ctx* ctx, uint32_t* states, size_t n) {
 }
 const char* hfb200_op_fri_fold(hfb200_ctx* ctx, uint32_t* out, const uint32_t* in, size_t n, const uint32_t* mix4) {
     API_TRY
+    if (!ctx || !out || !in || !mix4) throw Err("op_fri_fold: NULL argument");
     ctx->p.bind();
     Dev& d = ctx->p.dev;
     if (n < 16 || (n & 15)) throw Err("op_fri_fold: n must be a multiple of 16");
@@ -548,6 +557,7 @@ const char* hfb200_op_fri_fold(hfb200_ctx* ctx, uint32_t* out, const uint32_t* i
 
 const char* hfb200_bench_lde(hfb200_ctx* ctx, uint32_t po2, uint32_t count, uint32_t iters, float* ms_avg) {
     API_TRY
+    if (!ctx || !ms_avg) throw Err("bench_lde: NULL argument");
     Prover& p = ctx->p;
     p.bind();
     p.layout(po2);
@@ -565,6 +575,7 @@ const char* hfb200_bench_lde(hfb200_ctx* ctx, uint32_t po2, uint32_t count, uint
 }
 const char* hfb200_bench_merkle(hfb200_ctx* ctx, uint32_t po2, uint32_t count, uint32_t iters, float* ms_avg) {
     API_TRY
+    if (!ctx || !ms_avg) throw Err("bench_merkle: NULL argument");
     Prover& p = ctx->p;
     p.bind();
     p.layout(po2);

@@ -180,6 +180,16 @@ struct Prover {
         }
     }
     void sync() { dev.sync(); host_syncs++; }
+    // error path of an API entry: wait for everything queued on both streams (best effort, never throws) so that no copy from
+    // or to caller memory is still in flight when the error is returned; the half-proved segment is abandoned
+    void quiesce() noexcept {
+#ifndef HFB200_EMU
+        cudaSetDevice(device_id);
+        if (copy_stream) cudaStreamSynchronize(copy_stream);
+        if (dev.stream) cudaStreamSynchronize(dev.stream);
+#endif
+        begun = false;
+    }
     void destroy() {
         dev.free(arena.base);
 #ifndef HFB200_EMU

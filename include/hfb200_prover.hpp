@@ -65,6 +65,8 @@ struct Segment {
     const uint32_t* code = nullptr;
     const uint32_t* data = nullptr;
     uint64_t blind_seed = 0;
+    // optional: words behind `code` / `data`; when non-zero, prove() checks them against (circuit, po2) before any pointer reaches the library
+    size_t code_words = 0, data_words = 0;
 };
 struct Session {
     std::vector<Segment> segments;
@@ -276,8 +278,12 @@ class Prover {
     // prover.prove(env, elf) -> ProveInfo
     // n_total_segments: segments of the whole session when this call proves only a share of it (multi-process operation); 0 = all
     ProveInfo prove(const Session& session, size_t seal_cap_words = (size_t)1 << 18, size_t n_total_segments = 0) {
-        for (const Segment& s : session.segments)
+        for (const Segment& s : session.segments) {
             if (s.po2 > opts_.max_segment_po2) throw Error("segment po2 " + std::to_string(s.po2) + " exceeds max_segment_po2 " + std::to_string(opts_.max_segment_po2));
+            if (!s.globals || !s.data || (!s.code && !opts_.reuse_control)) throw Error("segment " + std::to_string(s.index) + ": NULL trace pointer");
+            if ((s.code_words && s.code_words != ((size_t)opts_.circuit.w_code << s.po2)) || (s.data_words && s.data_words != ((size_t)opts_.circuit.w_data << s.po2)))
+                throw Error("segment " + std::to_string(s.index) + ": trace shape does not match (circuit, po2)");
+        }
         const size_t n = session.segments.size();
         std::vector<std::vector<uint32_t>> seals(n, std::vector<uint32_t>(seal_cap_words));
         std::vector<hfb200_segment_job> jobs(n);

@@ -51,6 +51,7 @@ int main(int argc, char** argv) {
         for (size_t i = 0; i < po2s.size(); i++) {
             Segment s;
             s.index = (uint32_t)i; s.po2 = po2s[i]; s.globals = globals[i].data(); s.code = code[i].data(); s.data = data[i].data(); s.blind_seed = 9 + i;
+            s.code_words = code[i].size(); s.data_words = data[i].size();
             session.segments.push_back(s);
         }
         ProverOpts opts;
@@ -97,6 +98,7 @@ int main(int argc, char** argv) {
         { ProverOpts o = opts; o.receipt_kind = "groth16"; EXPECT_THROW(Prover p(o), "recursion"); }
         { ProverOpts o = opts; o.max_segment_po2 = 12; Prover p(o); if (max_po2 > 12) EXPECT_THROW(p.prove(session), "exceeds max_segment_po2"); }
         EXPECT_THROW(Receipt::from_json("{\"inner\":\"Fake\"}"), "missing");
+        { Session bad_shape = session; bad_shape.segments[0].data_words -= 1; EXPECT_THROW(prover->prove(bad_shape), "trace shape"); }
 
         // opt-in control reuse (segments of equal po2 share their control columns): identical seals
         std::set<uint32_t> distinct(po2s.begin(), po2s.end());

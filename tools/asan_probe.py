@@ -1,5 +1,5 @@
 import sys
-import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import os; os.environ.setdefault("HFB200_DETERMINISTIC_BLINDING", "1"); sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, hfb200_loader
 pkg = hfb200_loader.load()
 lib = pkg.load_library("/tmp/libhfb200_emu_asan.so")
@@ -36,3 +36,35 @@ for widths, po2 in (((16, 192, 48), 12), ((21, 72, 20), 12)):
             except pkg.Hfb200Error:
                 pass
 print("asan probe 2 ok")
+# round 2: device transcript, pool fault handling + control generations, claims, chunked data-defined circuits
+os.environ["HFB200_IR_CHUNK"] = "200"
+from oracle import synth_ir   # table builder only
+with pkg.Context(0, 13, (16, 64, 16), lib=lib, deterministic=True) as ctx:
+    g = ctx.witgen_synth(13, 5, 2)
+    code, data = ctx.read_group(1), ctx.read_group(2)
+    host = ctx.prove_segment(13, g, code, data, 2)
+    ctx.set_transcript(True)
+    assert (ctx.prove_segment(13, g, code, data, 2) == host).all() and (ctx.prove_resident(2) == host).all()
+with pkg.Pool(devices=(0, 0), contexts_per_device=2, max_po2=13, circuit=(16, 64, 16), lib=lib, deterministic=True) as pool:
+    pool.inject_fault(0, 0, 0)
+    pool.load_control(13, code)
+    seals, _, _ = pool.prove([(13, g, code, data, 2), (13, g, None, data, 2), (13, g, code, data, 2)], 1 << 17)
+    assert all((s == host).all() for s in seals)
+    keep = code.copy()
+    pool.load_control(13, keep)
+    seals, _, _ = pool.prove([(13, g, None, data, 2)], 1 << 17)
+    assert (seals[0] == host).all()
+ir = synth_ir.build((16, 64, 16), 1, nest=True)
+with pkg.Context(0, 12, (16, 64, 16), lib=lib, ir=ir, deterministic=True) as ctx:
+    rng2 = np.random.default_rng(2)
+    code = rng2.integers(0, pkg.P, size=(16, 4096), dtype=np.uint32); data = rng2.integers(0, pkg.P, size=(64, 4096), dtype=np.uint32)
+    accum = rng2.integers(0, pkg.P, size=(16, 4096), dtype=np.uint32)
+    ctx.segment_begin(12, g, code, data, 1); ctx.segment_finish(accum)
+big = synth_ir.build_scaled(n_groups=40)
+with pkg.Context(0, 12, big["widths"], lib=lib, ir=big, deterministic=True) as ctx:
+    W = big["widths"]
+    code = rng2.integers(0, pkg.P, size=(W[0], 4096), dtype=np.uint32); data = rng2.integers(0, pkg.P, size=(W[1], 4096), dtype=np.uint32)
+    accum = rng2.integers(0, pkg.P, size=(W[2], 4096), dtype=np.uint32)
+    ctx.segment_begin(12, g, code, data, 1); ctx.segment_finish(accum)
+d = pkg.digest_bytes(b"journal", lib=lib); pkg.digest_pair(d, d, lib=lib); pkg.claim_next_state(d, 3, 20, lib=lib)
+print("asan probe 3 ok")
