@@ -16,7 +16,7 @@ P = 2013265921
 
 # Every symbol include/hfb200.h declares (tests check that the built library exports all of them).
 EXPORTS = [
-    "hfb200_init", "hfb200_init_ir", "hfb200_ir_source", "hfb200_ir_jit_active", "hfb200_verify_segment", "hfb200_control_root", "hfb200_destroy", "hfb200_free_error", "hfb200_version", "hfb200_host_alloc", "hfb200_host_free",
+    "hfb200_init", "hfb200_init_ir", "hfb200_ir_source", "hfb200_ir_jit_active", "hfb200_verify_segment", "hfb200_verify_segments", "hfb200_control_root", "hfb200_destroy", "hfb200_free_error", "hfb200_version", "hfb200_host_alloc", "hfb200_host_free",
     "hfb200_prove_segment", "hfb200_segment_begin", "hfb200_segment_finish", "hfb200_witgen_synth",
     "hfb200_prove_resident", "hfb200_read_group", "hfb200_seal_words", "hfb200_checkpoint", "hfb200_last_stats",
     "hfb200_total_launches", "hfb200_op_interpolate_ntt", "hfb200_op_expand_ntt", "hfb200_op_lde", "hfb200_op_merkle",
@@ -142,6 +142,7 @@ def load_library(path=None):
         "hfb200_claim_encode": (err, [C.POINTER(Claim), vp]),
         "hfb200_claim_decode": (err, [vp, sz, C.POINTER(Claim)]),
         "hfb200_claim_next_state": (err, [vp, u32, u32, vp]),
+        "hfb200_verify_segments": (err, [C.POINTER(CircuitDesc), C.POINTER(CircuitIR), C.POINTER(vp), C.POINTER(sz), sz, vp, vp, C.c_uint, C.POINTER(sz)]),
         "hfb200_verify_claims": (err, [C.POINTER(vp), C.POINTER(sz), sz, vp, C.c_char_p, sz]),
     }
     for name, (res, args) in sig.items():
@@ -463,6 +464,31 @@ def claim_decode(seal, lib=None):
     c = Claim()
     _raise_err(lib, lib.hfb200_claim_decode(_ptr(seal), seal.size, C.byref(c)))
     return c
+
+
+def verify_segments(seals, code_roots, circuit=(16, 192, 48), ir=None, threads=0, lib=None):
+    """`hfb200_verify_segments`: the segment seals of a composite receipt checked on `threads` host threads (0 = all hardware
+    threads).  `code_roots`: one 8-word control id per seal.  Returns the po2 of every seal; raises Hfb200Error naming the
+    first rejected seal."""
+    lib = lib or load_library()
+    seals = [_u32(s) for s in seals]
+    roots = np.ascontiguousarray(np.stack([_u32(r) for r in code_roots]) if len(code_roots) else np.zeros((0, 8), np.uint32), dtype=np.uint32)
+    n = len(seals)
+    if roots.shape != (n, 8):
+        raise Hfb200Error("verify_segments: one 8-word control id per seal")
+    ptrs = (C.c_void_p * max(n, 1))(*[s.ctypes.data for s in seals])
+    lens = (C.c_size_t * max(n, 1))(*[s.size for s in seals])
+    po2 = np.zeros(max(n, 1), dtype=np.uint32)
+    bad = C.c_size_t(n)
+    if ir is not None:
+        taps, steps = _u32(ir["taps"]), _u32(ir["steps"])
+        d = CircuitIR(circuit[0], circuit[1], circuit[2], int(ir["n_mix"]), taps.ctypes.data, taps.size // 3, steps.ctypes.data, steps.size // 4, int(ir["ret"]))
+        e = lib.hfb200_verify_segments(None, C.byref(d), ptrs, lens, n, _ptr(roots) if n else None, _ptr(po2), threads, C.byref(bad))
+    else:
+        d = CircuitDesc(circuit[0], circuit[1], circuit[2], 0)
+        e = lib.hfb200_verify_segments(C.byref(d), None, ptrs, lens, n, _ptr(roots) if n else None, _ptr(po2), threads, C.byref(bad))
+    _raise_err(lib, e)
+    return [int(x) for x in po2[:n]]
 
 
 def verify_claims(seals, image_id, journal_bytes, lib=None):

@@ -603,6 +603,43 @@ const char* hfb200_verify_segment(const hfb200_circuit_desc* c, const hfb200_cir
     verify_segment(vc, seal, seal_words, code_root, po2_out);
     API_CATCH
 }
+// n seals at once on up to `threads` host threads (0 = one per hardware thread): what `receipt.verify` does over the segment
+// receipts of a composite receipt; the seals are independent, so this is plain fan-out.  The FIRST failing seal (lowest index)
+// is reported, prefixed with its index; `first_bad` receives that index (or n when all verify).
+const char* hfb200_verify_segments(const hfb200_circuit_desc* c, const hfb200_circuit_ir* ir, const uint32_t* const* seals, const size_t* seal_words,
+                                   size_t n, const uint32_t* code_roots, uint32_t* po2_out, unsigned threads, size_t* first_bad) {
+    API_TRY
+    if ((c == nullptr) == (ir == nullptr)) throw Err("hfb200_verify_segments: pass exactly one of circuit / ir");
+    if (n && (!seals || !seal_words || !code_roots)) throw Err("hfb200_verify_segments: NULL argument");
+    if (first_bad) *first_bad = n;
+    VCircuit vc;
+    if (c) vc.init_builtin(c->w_code, c->w_data, c->w_accum);
+    else vc.init_ir(ir->w_code, ir->w_data, ir->w_accum, ir->n_mix, reinterpret_cast<const IrTap*>(ir->taps), ir->n_taps,
+                    reinterpret_cast<const IrStep*>(ir->steps), ir->n_steps, ir->ret);
+    p2_host_consts();
+    unsigned nt = threads ? threads : std::thread::hardware_concurrency();
+    if (nt == 0) nt = 1;
+    if (nt > n) nt = (unsigned)n;
+    std::vector<std::string> errs(n);
+    std::vector<char> bad(n, 0);
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+        for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) {
+            try {
+                if (!seals[i]) throw Err("NULL seal");
+                uint32_t po2 = 0;
+                verify_segment(vc, seals[i], seal_words[i], code_roots + 8 * i, &po2);
+                if (po2_out) po2_out[i] = po2;
+            } catch (const std::exception& e) { errs[i] = e.what(); bad[i] = 1; } catch (...) { errs[i] = "unknown error"; bad[i] = 1; }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nt; t++) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    for (size_t i = 0; i < n; i++) if (bad[i]) { if (first_bad) *first_bad = i; throw Err("segment " + std::to_string(i) + ": " + errs[i]); }
+    API_CATCH
+}
 // ---- receipt claims (host only) ------------------------------------------------------------------------------------------
 // Upstream's `Receipt::verify(image_id)` (/root/reference/host/src/main.rs:622-624, /root/reference/verifier/src/main.rs:124-126)
 // does more than check seals: it decodes each segment's ReceiptClaim from the seal's globals, chains pre/post state digests from

@@ -117,15 +117,17 @@ class Receipt:
             if s.claim is not None and s.claim != claim_decode(s.seal, lib=lib).to_obj():
                 raise Hfb200Error("verify: segment %d: the claim in the receipt differs from the one its seal commits to" % i)
 
-    def verify_seals(self, control_ids, circuit=(16, 192, 48), ir=None, lib=None) -> None:
+    def verify_seals(self, control_ids, circuit=(16, 192, 48), ir=None, lib=None, threads=0) -> None:
         """Step 1 of verify() alone: seals against control ids and index order.  NOT a substitute for verify(): it says
-        nothing about the journal or the image id."""
-        from .binding import verify_segment, Hfb200Error
+        nothing about the journal or the image id.  The seals are independent and are checked on `threads` host threads
+        (`hfb200_verify_segments`; 0 = all hardware threads)."""
+        from .binding import verify_segments, Hfb200Error
         if isinstance(self.inner, str):
             raise Hfb200Error("verify: %s receipt carries no seal (dev-mode receipts are refused)" % self.inner)
         segs = self.inner.segments
         if not segs:
             raise Hfb200Error("verify: composite receipt without segments")
+        roots = []
         for want, s in enumerate(segs):
             if s.index != want:
                 raise Hfb200Error("verify: segment index %d at position %d" % (s.index, want))
@@ -136,7 +138,5 @@ class Receipt:
             po2 = int(s.seal[32])  # seal layout: 32 globals, po2, ...
             if po2 not in control_ids:
                 raise Hfb200Error("verify: segment %d: no control id for po2 %d" % (want, po2))
-            try:
-                verify_segment(s.seal, control_ids[po2], circuit, ir=ir, lib=lib)
-            except Hfb200Error as e:
-                raise Hfb200Error("segment %d: %s" % (want, e)) from None
+            roots.append(control_ids[po2])
+        verify_segments([s.seal for s in segs], roots, circuit, ir=ir, threads=threads, lib=lib)

@@ -1,7 +1,7 @@
 //! Raw bindings of `include/hfb200.h`.  Error convention is the one of upstream's sys crates
 //! (`risc0_sys::ffi_wrap`): NULL = success, otherwise a malloc'd C string released with `hfb200_free_error`.
 #![allow(non_camel_case_types)]
-use std::os::raw::{c_char, c_int};
+use std::os::raw::{c_char, c_int, c_uint};
 
 #[repr(C)]
 pub struct hfb200_ctx {
@@ -135,6 +135,12 @@ extern "C" {
     pub fn hfb200_verify_segment(
         circuit: *const hfb200_circuit_desc, ir: *const hfb200_circuit_ir, seal: *const u32, seal_words: usize,
         code_root: *const u32, po2_out: *mut u32,
+    ) -> *const c_char;
+    /// The same over the `n` segment seals of a composite receipt on up to `threads` host threads (0 = all); reports the first
+    /// failing seal.  `code_roots`: n x 8 words, `po2_out`: n words or null, `first_bad`: optional.
+    pub fn hfb200_verify_segments(
+        circuit: *const hfb200_circuit_desc, ir: *const hfb200_circuit_ir, seals: *const *const u32, seal_words: *const usize, n: usize,
+        code_roots: *const u32, po2_out: *mut u32, threads: c_uint, first_bad: *mut usize,
     ) -> *const c_char;
     /// Control id of (circuit, po2): Merkle root of the committed control columns, computed on the GPU.
     pub fn hfb200_control_root(ctx: *mut hfb200_ctx, po2: u32, code: *const u32, root_out: *mut u32) -> *const c_char;

@@ -144,6 +144,13 @@ const char* hfb200_checkpoint(hfb200_ctx* ctx, const char* name, uint32_t* out, 
  * Returns NULL when the seal is valid, else the reason. */
 const char* hfb200_verify_segment(const hfb200_circuit_desc* circuit, const hfb200_circuit_ir* ir, const uint32_t* seal, size_t seal_words,
                                   const uint32_t* code_root /*[8]*/, uint32_t* po2_out);
+/* The same over the n segment seals of a composite receipt, fanned out over up to `threads` host threads (0 = one per hardware
+ * thread; the seals are independent).  `code_roots` = n x 8 words (the control id of each seal's po2), `po2_out` (optional) = n
+ * words.  Returns NULL when every seal is valid; otherwise the reason of the FIRST failing seal (lowest index), prefixed
+ * "segment <i>: ", and `*first_bad` (optional) = i (n when all verify). */
+const char* hfb200_verify_segments(const hfb200_circuit_desc* circuit, const hfb200_circuit_ir* ir, const uint32_t* const* seals,
+                                   const size_t* seal_words, size_t n, const uint32_t* code_roots /*[n][8]*/, uint32_t* po2_out /*[n] or NULL*/,
+                                   unsigned threads, size_t* first_bad);
 /* ---- receipt claims: the rest of `receipt.verify(image_id)` (host only; no device, no context) -------------------------
  * Upstream's Receipt::verify also decodes each segment's ReceiptClaim from the seal's globals, chains pre/post state digests
  * from the image id and ties the journal digest to the last claim's output (/root/reference/verifier/src/main.rs:124-126 trusts

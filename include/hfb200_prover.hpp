@@ -233,9 +233,12 @@ struct Receipt {
         ffi_wrap(hfb200_verify_claims(ptrs.data(), lens.data(), ptrs.size(), image_id.data(), journal.bytes.data(), journal.bytes.size()));
     }
     // step (1) alone; NOT a substitute for verify(): it says nothing about the journal or the image id
-    void verify_seals(const std::map<uint32_t, Digest>& control_ids, const hfb200_circuit_desc& circuit = hfb200_circuit_desc{16, 192, 48, 0}) const {
+    void verify_seals(const std::map<uint32_t, Digest>& control_ids, const hfb200_circuit_desc& circuit = hfb200_circuit_desc{16, 192, 48, 0}, unsigned threads = 0) const {
         if (fake) throw Error("verify: Fake receipt carries no seal (dev-mode receipts are refused)");
         if (segments.empty()) throw Error("verify: composite receipt without segments");
+        std::vector<const uint32_t*> ptrs;
+        std::vector<size_t> lens;
+        std::vector<uint32_t> roots;
         for (size_t want = 0; want < segments.size(); want++) {
             const SegmentReceipt& s = segments[want];
             if (s.index != want) throw Error("verify: segment index " + std::to_string(s.index) + " at position " + std::to_string(want));
@@ -244,10 +247,11 @@ struct Receipt {
             const uint32_t po2 = s.seal[32];  // seal layout: 32 globals, po2, ...
             const auto it = control_ids.find(po2);
             if (it == control_ids.end()) throw Error("verify: segment " + std::to_string(want) + ": no control id for po2 " + std::to_string(po2));
-            uint32_t got = 0;
-            try { ffi_wrap(hfb200_verify_segment(&circuit, nullptr, s.seal.data(), s.seal.size(), it->second.data(), &got)); }
-            catch (const Error& e) { throw Error("segment " + std::to_string(want) + ": " + e.what()); }
+            ptrs.push_back(s.seal.data()); lens.push_back(s.seal.size());
+            roots.insert(roots.end(), it->second.begin(), it->second.end());
         }
+        // the seals are independent: one library call fans them out over the host threads (0 = all of them)
+        ffi_wrap(hfb200_verify_segments(&circuit, nullptr, ptrs.data(), lens.data(), ptrs.size(), roots.data(), nullptr, threads, nullptr));
     }
 };
 

@@ -175,3 +175,25 @@ def test_gpu_seal_verifies_and_control_root(pkg, orc):
     bad = seal.copy(); bad[len(bad) // 2] ^= 1
     with pytest.raises(pkg.Hfb200Error):
         pkg.verify_segment(bad, root, widths)
+
+
+def test_batch_verifier_fans_out_and_names_the_first_bad_seal(pkg, gpu_lib, orc):
+    """hfb200_verify_segments: n seals on several host threads give the same verdicts as n single calls; the FIRST rejected seal
+    (lowest index) is the one reported, whatever thread found it."""
+    seals, roots = [], []
+    for i, po2 in enumerate((12, 13, 12, 12, 13, 12)):
+        cir, g, code, data = make_segment(orc, SMALL, po2, trace_seed=100 + i)
+        seal, cps, _ = cir.prove(po2, g, code, data, 1)
+        seals.append(np.array(seal, np.uint32)); roots.append(np.array(cps["code_root"], np.uint32))
+    for threads in (0, 1, 3, 16):
+        assert pkg.verify_segments(seals, roots, SMALL, threads=threads, lib=gpu_lib) == [12, 13, 12, 12, 13, 12]
+    assert pkg.verify_segments([], [], SMALL, lib=gpu_lib) == []
+    bad = [s.copy() for s in seals]
+    bad[4][200] ^= 1; bad[2][150] ^= 1
+    for threads in (1, 4):
+        with pytest.raises(pkg.Hfb200Error, match="segment 2"):
+            pkg.verify_segments(bad, roots, SMALL, threads=threads, lib=gpu_lib)
+    with pytest.raises(pkg.Hfb200Error, match="segment 1"):                       # a seal checked against another po2's control id
+        pkg.verify_segments(seals, [roots[0]] * 6, SMALL, lib=gpu_lib)
+    with pytest.raises(pkg.Hfb200Error, match="one 8-word control id per seal"):
+        pkg.verify_segments(seals, roots[:3], SMALL, lib=gpu_lib)
