@@ -24,7 +24,7 @@ EXPORTS = [
     "hfb200_mark", "hfb200_mark_elapsed",
     "hfb200_pool_create", "hfb200_pool_create_ir", "hfb200_pool_load_control", "hfb200_pool_prove", "hfb200_pool_destroy",
     "hfb200_set_blinding", "hfb200_pool_set_blinding", "hfb200_pool_stats", "hfb200_pool_inject_fault",
-    "hfb200_set_transcript", "hfb200_digest_bytes", "hfb200_digest_pair", "hfb200_claim_encode", "hfb200_claim_decode", "hfb200_claim_next_state", "hfb200_verify_claims",
+    "hfb200_set_transcript", "hfb200_graph_launches", "hfb200_digest_bytes", "hfb200_digest_pair", "hfb200_claim_encode", "hfb200_claim_decode", "hfb200_claim_next_state", "hfb200_verify_claims",
 ]
 
 BLIND_OS_ENTROPY, BLIND_DETERMINISTIC = 0, 1
@@ -137,6 +137,7 @@ def load_library(path=None):
         "hfb200_pool_stats": (err, [vp, C.POINTER(PoolStats)]),
         "hfb200_pool_inject_fault": (err, [vp, sz, u64, C.c_int]),
         "hfb200_set_transcript": (err, [vp, C.c_int]),
+        "hfb200_graph_launches": (u64, [vp]),
         "hfb200_digest_bytes": (err, [C.c_char_p, sz, vp]),
         "hfb200_digest_pair": (err, [vp, vp, vp]),
         "hfb200_claim_encode": (err, [C.POINTER(Claim), vp]),
@@ -192,9 +193,13 @@ class Context:
     def set_blinding(self, mode):
         self._check(self.lib.hfb200_set_blinding(self._h, int(mode)))
 
-    def set_transcript(self, on_device):
-        """Fiat-Shamir transcript of the one-shot entries on the device (one sync per segment) or on the host (default)."""
-        self._check(self.lib.hfb200_set_transcript(self._h, int(bool(on_device))))
+    def set_transcript(self, mode):
+        """Fiat-Shamir transcript of the one-shot entries: 0 / False = host (default), 1 / True = device (one sync per segment),
+        2 = device + CUDA-graph replay (one cudaGraphLaunch per segment from the third segment of a shape on)."""
+        self._check(self.lib.hfb200_set_transcript(self._h, int(mode)))
+
+    def graph_launches(self):
+        return self.lib.hfb200_graph_launches(self._h)
 
     def _check(self, e):
         if e:

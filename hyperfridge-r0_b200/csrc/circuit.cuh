@@ -109,7 +109,10 @@ static constexpr uint32_t ACC_ITEMS = 256, ACC_PER = 8, ACC_RPB = ACC_ITEMS * AC
 // mode 1: read the exclusive block offset from partial[...] and write the running products (+ blinding rows)
 struct AccumKernel {
     static constexpr bool kBarrier = true;
-    HD static void run(const KCtx& cx, uint32_t* sm, uint32_t* accum, const uint32_t* data, const uint32_t* mix, E4* partial, CircuitDev cd, uint32_t po2, BlindKey blind, int mode) {
+    HD static void run(const KCtx& cx, uint32_t* sm, uint32_t* accum, const uint32_t* data, const uint32_t* mix, E4* partial, CircuitDev cd, uint32_t po2, BlindKey blind, int mode,
+                       const BlindKey* blind_dev = nullptr) {
+        // blind_dev != NULL: the key lives in device memory (CUDA-graph replay: a by-value key would be frozen into the graph)
+        if (blind_dev) blind = *blind_dev;
         const uint64_t n = 1ull << po2, act = n - ZK_CYCLES;
         const uint32_t chain = cx.by, blk = cx.bx, nblk = cx.gx;
         const uint32_t* src = data + (uint64_t)cd.chain_src[chain] * n;
@@ -168,6 +171,7 @@ struct EvalCheckArgs {
     const E4* mixpow;                              // poly_mix^j, j < n_constraints (device)
     const uint32_t* mix;                           // accum mix elems (device) [4*n_chains]
     uint32_t global0;
+    const uint32_t* global0_dev;                   // non-NULL: globals[0] is read from device memory instead (CUDA-graph replay)
     uint32_t yinv[4];                              // 1/((3 w_4N^i)^N - 1) depends on i mod 4 only
     uint32_t po2;
     uint32_t rows_per_block;
@@ -221,7 +225,7 @@ struct EvalCheckKernel {
                 for (int k = 0; k < 4; k++, j++) e4a_mac(lt, mp[j], fsub(acc.c[k], pr.c[k]));
             }
             E4A lf = e4a_zero();
-            e4a_mac(lf, mp[j], fmul(first, fsub(p.ev_data[i], p.global0)));
+            e4a_mac(lf, mp[j], fmul(first, fsub(p.ev_data[i], p.global0_dev ? *p.global0_dev : p.global0)));
             const E4 tot = e4_add(e4_scale(e4a_redc(lt), active), e4a_redc(lf));
             const uint32_t yi = p.yinv[i & 3];
             for (int k = 0; k < 4; k++) p.check[(uint64_t)k * domain + i] = fmul(tot.c[k], yi);

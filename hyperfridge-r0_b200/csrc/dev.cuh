@@ -112,9 +112,13 @@ struct Dev {
     uint64_t launches = 0;
     int sm_count = 148;
     int device = 0;  // CUDA device ordinal of the owning context
+    // CUDA-graph replay (prover.cuh, transcript mode 2): the host walks the same enqueue code again so that pinned staging areas
+    // receive this segment's parameters, but every launch and copy is already a node of the instantiated graph and is skipped here
+    bool replay = false;
     template <typename Body, int MAXT = 256, int MINB = 1, typename... A>
     void launch(unsigned gx, unsigned gy, int block, size_t smem, A... a) {
         if (gx == 0 || gy == 0) return;
+        if (replay) { launches++; return; }
         auto k = kernel_entry<Body, MAXT, MINB, A...>;
         if (smem > 48 * 1024) {
             // The opt-in limit is a property of (kernel, device), shared by every context and host thread that uses
@@ -137,10 +141,10 @@ struct Dev {
     }
     void* alloc(size_t bytes) { void* p; CUDA_CHECK(cudaMalloc(&p, bytes)); return p; }
     void free(void* p) { if (p) cudaFree(p); }
-    void h2d(void* d, const void* h, size_t bytes) { CUDA_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream)); }
-    void d2h(void* h, const void* d, size_t bytes) { CUDA_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, stream)); }
-    void d2d(void* d, const void* s, size_t bytes) { CUDA_CHECK(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, stream)); }
-    void zero(void* d, size_t bytes) { CUDA_CHECK(cudaMemsetAsync(d, 0, bytes, stream)); }
+    void h2d(void* d, const void* h, size_t bytes) { if (!replay) CUDA_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream)); }
+    void d2h(void* h, const void* d, size_t bytes) { if (!replay) CUDA_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, stream)); }
+    void d2d(void* d, const void* s, size_t bytes) { if (!replay) CUDA_CHECK(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, stream)); }
+    void zero(void* d, size_t bytes) { if (!replay) CUDA_CHECK(cudaMemsetAsync(d, 0, bytes, stream)); }
     void sync() { CUDA_CHECK(cudaStreamSynchronize(stream)); }
 };
 
@@ -161,6 +165,7 @@ struct Dev {
     void* stream = nullptr;
     uint64_t launches = 0;
     int sm_count = 148;
+    bool replay = false;  // never set in the emulator (no CUDA graphs)
     template <typename Body, int MAXT = 256, int MINB = 1, typename... A>
     void launch(unsigned gx, unsigned gy, int block, size_t smem, A... a) {
         if (gx == 0 || gy == 0) return;

@@ -115,9 +115,12 @@ const char* hfb200_set_transcript(hfb200_ctx* ctx, int on_device) {
     API_TRY
     if (!ctx) throw Err("hfb200_set_transcript: NULL ctx");
     if (ctx->p.begun) throw Err("hfb200_set_transcript: a segment is in flight");
-    ctx->p.transcript_mode = on_device ? 1 : 0;
+    if (on_device < 0 || on_device > 2) throw Err("hfb200_set_transcript: mode must be 0 (host), 1 (device) or 2 (device + CUDA-graph replay)");
+    ctx->p.transcript_mode = on_device;
     API_CATCH
 }
+
+uint64_t hfb200_graph_launches(const hfb200_ctx* ctx) { return ctx ? ctx->p.graph_launches : 0; }
 
 const char* hfb200_host_alloc(size_t bytes, void** out) {
     API_TRY

@@ -152,6 +152,7 @@ static inline bool tma_make_map(CUtensorMap* m, const uint32_t* base, uint64_t c
 static inline bool strided_tma(Dev* dev, const RootTables& rt, const uint32_t* in, uint64_t in_stride, uint32_t* out, uint64_t out_stride, uint32_t ncols, int a, int b, bool inv) {
     static const bool enabled = [] { const char* e = std::getenv("HFB200_NTT_TMA"); return !e || std::atoi(e) != 0; }();
     if (!enabled || b != TMA_ROWS_LOG || a < TMA_SEG_LOG || ncols == 0) return false;
+    if (dev->replay) { dev->launches++; return true; }  // CUDA-graph replay: this launch is a node of the instantiated graph
     alignas(64) CUtensorMap mi, mo;
     if (!tma_make_map(&mi, in, in_stride, ncols, a) || !tma_make_map(&mo, out, out_stride, ncols, a)) return false;
     StrTmaArgs p{};

@@ -175,6 +175,7 @@ struct Prover {
             dev.h2d(d, stage_h + stage_off, bytes);
             stage_off += need;
         } else {
+            if (marks_off) throw Err("internal: parameter staging area exhausted while a CUDA graph is captured or replayed");
             dev.h2d(d, h, bytes);
             sync();
         }
@@ -193,10 +194,14 @@ struct Prover {
     void destroy() {
         dev.free(arena.base);
 #ifndef HFB200_EMU
+        drop_graphs();
         if (stage_h) cudaFreeHost(stage_h);
+        if (out_h) cudaFreeHost(out_h);
 #else
         std::free(stage_h);
+        std::free(out_h);
 #endif
+        out_h = nullptr; out_cap = 0;
         stage_h = nullptr;
         jit.destroy();
         gen.destroy(&dev);
@@ -225,8 +230,10 @@ struct Prover {
         CUDA_CHECK(cudaSetDevice(device_id));
 #endif
     }
+    bool marks_off = false;  // graph capture / replay: stage events cannot be recorded inside the graph
     void mark(int i) {
 #ifndef HFB200_EMU
+        if (marks_off) return;
         CUDA_CHECK(cudaEventRecord(evs[i], dev.stream));
 #else
         (void)i;
@@ -234,6 +241,7 @@ struct Prover {
     }
     float between(int i, int j) {
 #ifndef HFB200_EMU
+        if (marks_off) return 0.f;
         float m = 0; CUDA_CHECK(cudaEventElapsedTime(&m, evs[i], evs[j])); return m;
 #else
         (void)i; (void)j; return 0.f;
@@ -419,14 +427,16 @@ struct Prover {
         begun = true;
     }
 
-    void step_accum() {
+    // key_dev != NULL: the blinding key is read from device memory (graph replay); the by-value copy is then a placeholder
+    void step_accum(const BlindKey* key_dev = nullptr) {
         const size_t N = (size_t)1 << po2;
         const uint32_t nblk = (uint32_t)((N + ACC_RPB - 1) / ACC_RPB);
         E4* partial = arena.take<E4>((size_t)cir.cd.n_chains * nblk);
         const size_t sm1 = 2 * ACC_ITEMS * sizeof(E4);
-        dev.launch<AccumKernel, 256, 1>(nblk, cir.cd.n_chains, 256, sm1, tr[GROUP_ACCUM], (const uint32_t*)tr[GROUP_DATA], (const uint32_t*)d_mix, partial, cir.cd, po2, blind_key, 0);
+        const BlindKey by_value = key_dev ? BlindKey{} : blind_key;
+        dev.launch<AccumKernel, 256, 1>(nblk, cir.cd.n_chains, 256, sm1, tr[GROUP_ACCUM], (const uint32_t*)tr[GROUP_DATA], (const uint32_t*)d_mix, partial, cir.cd, po2, by_value, 0, key_dev);
         dev.launch<AccumOffsetsKernel, 256, 1>(1, cir.cd.n_chains, 256, 2 * (size_t)nblk * sizeof(E4), partial, nblk);
-        dev.launch<AccumKernel, 256, 1>(nblk, cir.cd.n_chains, 256, sm1, tr[GROUP_ACCUM], (const uint32_t*)tr[GROUP_DATA], (const uint32_t*)d_mix, partial, cir.cd, po2, blind_key, 1);
+        dev.launch<AccumKernel, 256, 1>(nblk, cir.cd.n_chains, 256, sm1, tr[GROUP_ACCUM], (const uint32_t*)tr[GROUP_DATA], (const uint32_t*)d_mix, partial, cir.cd, po2, by_value, 1, key_dev);
     }
 
     static uint32_t rou_fwd(int k) { uint32_t g = to_mont(137); for (int i = k; i < 27; i++) g = fmul(g, g); return g; }
@@ -794,11 +804,41 @@ struct Prover {
     // 5.54 ms for one po2 = 16 segment): a segment's transcript is ~170 SEQUENTIAL Poseidon2 permutations (92 for hash_u, 64 for the
     // final coefficients, 13 for the query draws), a warp-cooperative permutation takes ~3.3 us on the GPU against ~1 us on a host
     // core, and the stream synchronisations it removes cost less than that.  It pays where host threads are the scarce resource.
-    int transcript_mode = -1;  // -1: environment, 0: host, 1: device
-    bool device_transcript() const {
-        static const bool env_on = [] { const char* e = std::getenv("HFB200_DEVICE_TRANSCRIPT"); return e && std::atoi(e) != 0; }();
-        return (transcript_mode < 0 ? env_on : transcript_mode == 1) && !gen.active;
+    // Mode 2 adds CUDA-GRAPH REPLAY on top: a device-transcript segment is a fixed, stream-ordered sequence of ~170 launches and a
+    // handful of small copies whose arguments depend on (circuit, po2) only -- every per-segment value (globals, RNG header,
+    // blinding key, tree descriptors) reaches the kernels through pinned staging memory or device memory, never by value.  The
+    // first segment of a (po2, control-reuse) shape runs plainly (module loading, attribute set-up), the second is captured
+    // (cudaStreamBeginCapture .. EndCapture, instantiated once), every later one refills the staging area and issues ONE
+    // cudaGraphLaunch.  Trace uploads from caller memory stay outside the graph (their source pointers change per call).
+    int transcript_mode = -1;  // -1: environment, 0: host, 1: device, 2: device + CUDA-graph replay
+    static int env_transcript() { static const int v = [] { const char* e = std::getenv("HFB200_DEVICE_TRANSCRIPT"); return e ? std::atoi(e) : 0; }(); return v; }
+    int transcript_setting() const { return transcript_mode < 0 ? env_transcript() : transcript_mode; }
+    bool device_transcript() const { return transcript_setting() >= 1 && !gen.active; }
+    bool graph_replay() const { return transcript_setting() >= 2 && !gen.active && !debug_checkpoints; }
+    uint64_t graph_launches = 0;  // segments issued as one cudaGraphLaunch
+    uint8_t* out_h = nullptr;     // pinned landing area of the seal and the checkpoint words (device-transcript path)
+    size_t out_cap = 0;
+    void ensure_out(size_t bytes) {
+        if (bytes <= out_cap) return;
+#ifndef HFB200_EMU
+        if (out_h) cudaFreeHost(out_h);
+        out_h = nullptr; out_cap = 0;
+        CUDA_CHECK(cudaHostAlloc((void**)&out_h, bytes, cudaHostAllocDefault));
+#else
+        std::free(out_h);
+        out_h = (uint8_t*)std::malloc(bytes);
+        if (!out_h) throw Err("emu: out of memory");
+#endif
+        out_cap = bytes;
     }
+#ifndef HFB200_EMU
+    struct GraphEntry { int state = 0; cudaGraphExec_t exec = nullptr; };  // 0: never run, 1: warmed up, 2: instantiated
+    std::map<uint64_t, GraphEntry> graphs;                                // key = po2 * 2 + use_control
+    void drop_graphs() {
+        for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+        graphs.clear();
+    }
+#endif
     void prove_device(uint32_t p, const uint32_t* globals_h, const uint32_t* code_h, const uint32_t* data_h, uint64_t blind, std::vector<uint32_t>& seal_out) {
         const Staged sg = stage_inputs(p, globals_h, code_h, data_h, blind);
         begun = false;
@@ -806,13 +846,25 @@ struct Prover {
         const CircuitDev& cd = cir.cd;
         const uint32_t W = cir.n_regs(), T = cir.n_taps, n_mix = cir.n_mix();
         const size_t words = seal_words(po2);
+        if (n_mix > 4096) throw Err("internal: accum mix larger than the checkpoint buffer");
+        const size_t cp_words = CP_ACCUM_MIX + n_mix;
+        ensure_out((words + cp_words) * 4);
+        uint32_t* seal_pin = reinterpret_cast<uint32_t*>(out_h);
+        uint32_t* cp_pin = seal_pin + words;
+        const Digest8 gh = host_hash_elems(globals, N_GLOBAL);
+        bool chunked = sg.chunked;
+        uint32_t round = 0;
+        uint32_t* fin = nullptr;
+        // Everything that is queued on the stream for this segment.  Runs once per call: plainly, under stream capture, or -- graph
+        // replay -- with launches and copies suppressed (dev.replay) so that only the pinned staging area is refilled.
+        auto enqueue = [&]() {
         uint32_t* d_seal = arena.take<uint32_t>(words);
         uint32_t* d_cp = arena.take<uint32_t>(CP_WORDS);
         TxState* d_tx = arena.take<TxState>(1);
         TxParams* d_tp = arena.take<TxParams>(1);
-        if (n_mix > 4096) throw Err("internal: accum mix larger than the checkpoint buffer");
+        BlindKey* d_key = arena.take<BlindKey>(1);
+        h2d_small(d_key, &blind_key, sizeof blind_key);
         // header: the globals are the caller's, so their hash and the RNG state after mixing it are computed here and uploaded
-        const Digest8 gh = host_hash_elems(globals, N_GLOBAL);
         {
             HostRng r0; r0.mix(gh.w);
             TxState h{};
@@ -842,7 +894,7 @@ struct Prover {
         // DATA
         {
             StageRange r("hfb200:commit_data");
-            lde_data(sg.chunked);
+            lde_data(chunked);
             mark(4);
             merkle.build(ev[GROUP_DATA], D, (uint32_t)D, cd.w_data, nodes[GROUP_DATA]);
             mark(5);
@@ -852,7 +904,7 @@ struct Prover {
         // ACCUM
         {
             StageRange r("hfb200:commit_accum");
-            step_accum();
+            step_accum(d_key);
             mark(6);
             ntt.lde(tr[GROUP_ACCUM], N, ev[GROUP_ACCUM], D, scratch, cd.w_accum, (int)po2);
             mark(7);
@@ -874,7 +926,7 @@ struct Prover {
             dev.launch<TxPolyMixKernel, 32, 1>(1, 1, 32, 0, d_tx, d_tp, d_mp, nc, d_cp + CP_POLY_MIX);
             EvalCheckArgs a{};
             a.ev_accum = ev[GROUP_ACCUM]; a.ev_code = ev[GROUP_CODE]; a.ev_data = ev[GROUP_DATA];
-            a.check = check; a.mixpow = d_mp; a.mix = d_mix; a.global0 = globals[0];
+            a.check = check; a.mixpow = d_mp; a.mix = d_mix; a.global0 = 0; a.global0_dev = d_seal;  // seal word 0 = globals[0]
             for (int s_ = 0; s_ < 4; s_++) a.yinv[s_] = yinv4[s_];
             a.po2 = po2; a.cd = cd;
             a.rows_per_block = 128;
@@ -910,7 +962,7 @@ struct Prover {
         }
         uint32_t* S0 = arena.take<uint32_t>(4 * N);
         uint32_t* S1 = arena.take<uint32_t>(4 * N);
-        uint32_t* fin = arena.take<uint32_t>(4 * N);
+        fin = arena.take<uint32_t>(4 * N);
         dev.launch<CheckMixKernel, 256, 1>((unsigned)((N + 255) / 256), 1, 256, 0, (const uint32_t*)check, (const E4*)(d_regmix + W), S0, po2, ntt.rt);
         ntt.expand_evaluate(S0, N, S1, N, 4, (int)po2, 0);
         {
@@ -933,7 +985,7 @@ struct Prover {
         trees.push_back(TxTreeInfo{ev_check, nodes_check, D, (uint32_t)D, CHECK_SIZE, ms0.top_size, 0});
         uint32_t* coeffs = fin;
         size_t n = N;
-        uint32_t round = 0;
+        round = 0;
         uint32_t query_words = W + CHECK_SIZE + 4 * ms0.path_words();
         while (n > FRI_MIN_DEGREE) {
             if (round >= TX_MAX_FRI_ROUNDS) throw Err("internal: more FRI rounds than TxParams holds");
@@ -970,14 +1022,52 @@ struct Prover {
         }
         if (off != words) throw Err("internal: seal layout mismatch");
         mark(11);
-        seal_out.resize(words);
-        std::vector<uint32_t> cp(CP_ACCUM_MIX + n_mix);
-        dev.d2h(seal_out.data(), d_seal, words * 4);
-        dev.d2h(cp.data(), d_cp, cp.size() * 4);
+        dev.d2h(seal_pin, d_seal, words * 4);
+        dev.d2h(cp_pin, d_cp, cp_words * 4);
+        nvtx_pop();
+        };  // enqueue
+
+        bool as_graph = false;
+#ifndef HFB200_EMU
+        if (graph_replay()) {
+            GraphEntry& ge = graphs[(uint64_t)po2 * 2 + (sg.use_control ? 1 : 0)];
+            if (ge.state == 0) ge.state = 1;  // first segment of this shape: plain run below (module loading, attribute set-up)
+            else {
+                as_graph = true;
+                // trace uploads stay outside the graph: the graph's first node follows the last slice in stream order
+                if (chunked) { CUDA_CHECK(cudaStreamWaitEvent(dev.stream, chunk_ev[H2D_CHUNKS - 1], 0)); chunked = false; }
+                marks_off = true;
+                try {
+                    if (ge.state == 1) {
+                        CUDA_CHECK(cudaStreamBeginCapture(dev.stream, cudaStreamCaptureModeThreadLocal));
+                        cudaGraph_t g = nullptr;
+                        try { enqueue(); }
+                        catch (...) { cudaStreamEndCapture(dev.stream, &g); if (g) cudaGraphDestroy(g); throw; }
+                        CUDA_CHECK(cudaStreamEndCapture(dev.stream, &g));
+                        const cudaError_t e = cudaGraphInstantiate(&ge.exec, g, 0);
+                        cudaGraphDestroy(g);
+                        CUDA_CHECK(e);
+                        ge.state = 2;
+                    } else {
+                        dev.replay = true;
+                        try { enqueue(); } catch (...) { dev.replay = false; throw; }
+                        dev.replay = false;
+                    }
+                } catch (...) { marks_off = false; throw; }
+                marks_off = false;
+                mark(1);
+                CUDA_CHECK(cudaGraphLaunch(ge.exec, dev.stream));
+                mark(11);
+                graph_launches++;
+            }
+        }
+#endif
+        if (!as_graph) enqueue();
         std::vector<uint32_t> fc;
         if (debug_checkpoints) { fc.resize(4 * N); dev.d2h(fc.data(), fin, fc.size() * 4); }
         sync();  // the only synchronisation of the segment
-        nvtx_pop();
+        seal_out.assign(seal_pin, seal_pin + words);
+        std::vector<uint32_t> cp(cp_pin, cp_pin + cp_words);
         // checkpoints, under the names of the host-transcript path
         cp_add("globals_hash", gh.w, 8);
         cp_add("code_root", &cp[CP_CODE_ROOT], 8); cp_add("data_root", &cp[CP_DATA_ROOT], 8);
@@ -990,10 +1080,12 @@ struct Prover {
         cp_add("query_positions", &cp[CP_POSITIONS], QUERIES);
         mix.assign(cp.begin() + CP_ACCUM_MIX, cp.begin() + CP_ACCUM_MIX + n_mix);
         stage_ms[0] = between(0, 1);
-        stage_ms[1] = between(1, 2) + between(3, 4) + between(6, 7);
-        stage_ms[2] = between(2, 3) + between(4, 5) + between(7, 8);
-        stage_ms[3] = between(5, 6);
-        stage_ms[4] = between(8, 9); stage_ms[5] = between(9, 10); stage_ms[6] = between(10, 11);
+        if (!as_graph) {  // a replayed graph has no stage events inside it: only the upload and the whole-segment time are known
+            stage_ms[1] = between(1, 2) + between(3, 4) + between(6, 7);
+            stage_ms[2] = between(2, 3) + between(4, 5) + between(7, 8);
+            stage_ms[3] = between(5, 6);
+            stage_ms[4] = between(8, 9); stage_ms[5] = between(9, 10); stage_ms[6] = between(10, 11);
+        }
         stats.ms_h2d = stage_ms[0]; stats.ms_ntt_main = stage_ms[1]; stats.ms_hash_main = stage_ms[2]; stats.ms_accum = stage_ms[3];
         stats.ms_check = stage_ms[4]; stats.ms_deep = stage_ms[5]; stats.ms_fri = stage_ms[6];
         stats.ms_device = between(0, 11);

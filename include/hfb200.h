@@ -94,8 +94,14 @@ const char* hfb200_set_blinding(hfb200_ctx* ctx, int mode);
  * 0 (default): on the host, 10 stream synchronisations per segment, each a true dependency.  1: on the device as one-warp kernels,
  * the seal assembled in device memory, ONE synchronisation per segment (csrc/transcript.cuh); identical seals.  Measured ~1 % slower on
  * B200 (a segment's transcript is ~170 sequential Poseidon2 permutations, 3.3 us each on a warp against ~1 us on a host core); for hosts
- * with few cores per GPU.  HFB200_DEVICE_TRANSCRIPT=1 in the environment selects it for contexts that never call this. */
-const char* hfb200_set_transcript(hfb200_ctx* ctx, int on_device);
+ * with few cores per GPU.  2: mode 1 replayed as a CUDA GRAPH: the first segment of a (po2, control-reuse) shape runs plainly, the
+ * second is captured and instantiated, every later one refills the pinned parameter staging area and issues one cudaGraphLaunch
+ * (trace uploads from caller memory stay outside the graph); identical seals; per-stage times are not available for replayed
+ * segments (hfb200_last_stats reports ms_device only).  HFB200_DEVICE_TRANSCRIPT=1|2 in the environment selects a mode for
+ * contexts that never call this. */
+const char* hfb200_set_transcript(hfb200_ctx* ctx, int mode);
+/* Segments of this context that were issued as one cudaGraphLaunch (transcript mode 2). */
+uint64_t hfb200_graph_launches(const hfb200_ctx* ctx);
 const char* hfb200_version(void);
 
 /* Pinned host memory for trace staging (plain pointers are accepted too, just slower over PCIe). */

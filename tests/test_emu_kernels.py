@@ -151,3 +151,9 @@ def test_device_transcript_gives_the_same_seal(pkg, emu_lib, orc, widths, po2):
         assert (c.prove_segment(po2, g, None, data, 4) == oseal).all() and (root == ocps["code_root"]).all()
         c.witgen_synth(po2, 11, 4)
         assert (c.prove_resident(4) == oseal).all()           # resident entry
+        c.set_transcript(2)                                   # graph-replay mode: the device-resident key / globals[0] path (the emulator has no graphs)
+        for _ in range(3):
+            assert (c.prove_segment(po2, g, code, data, 4) == oseal).all()
+        assert c.graph_launches() == 0
+        with pytest.raises(pkg.Hfb200Error, match="mode must be"):
+            c.set_transcript(3)

@@ -397,3 +397,38 @@ def test_device_transcript_headline_pins(pkg, gpu_lib, orc, monkeypatch):
         c.witgen_synth(20, gold["trace_seed"], gold["blind_seed"])
         seal = c.prove_resident(gold["blind_seed"])
         _check_against_pins(orc, gold, seal, c.checkpoints())
+
+
+@pytest.mark.gpu
+def test_cuda_graph_replay_on_gpu(pkg, gpu_lib, orc):
+    """Transcript mode 2: the device-transcript segment captured once as a CUDA graph and replayed.  Every per-segment value
+    (globals, blinding key, trace, control reuse) must reach the replayed kernels: segments with DIFFERENT traces, globals and
+    blind seeds proved through one instantiated graph equal the oracle's seals word for word, for host buffers, the cached
+    control group (a second graph) and the resident entry, across a po2 switch and back."""
+    widths = (16, 64, 16)
+    cir = orc.Circuit(*widths)
+    def inputs(po2, trace_seed, blind):
+        _, g, code, data = make_segment(orc, widths, po2, trace_seed=trace_seed, blind_seed=blind)
+        return g, code, data, cir.prove(po2, g, code, data, blind)[0]
+    with pkg.Context(0, 13, widths, lib=gpu_lib, deterministic=True) as c:
+        c.set_transcript(2)
+        for i, (po2, ts, blind) in enumerate([(13, 11, 1), (13, 12, 2), (13, 13, 3), (13, 14, 4), (12, 21, 5), (12, 22, 6), (12, 23, 7), (13, 15, 8)]):
+            g, code, data, oseal = inputs(po2, ts, blind)
+            seal = c.prove_segment(po2, g, code, data, blind)
+            assert len(seal) == len(oseal) and (seal == oseal).all(), (i, po2)
+            assert c.last_stats()["host_syncs"] == 1
+        n_host = c.graph_launches()
+        assert n_host >= 5                                  # per shape: one plain run, one capture (already a graph launch), then replays
+        g, code, data, oseal = inputs(13, 31, 9)
+        c.control_root(13, code)
+        for blind in (9, 10, 11):                           # cached control group: its own graph
+            _, _, _, oseal = inputs(13, 31, blind)
+            _, g2, code2, data2 = make_segment(orc, widths, 13, trace_seed=31, blind_seed=blind)
+            assert (c.prove_segment(13, g2, None, data2, blind) == oseal).all()
+        assert c.graph_launches() >= n_host + 2
+        c.witgen_synth(13, TRACE_SEED, 1)                   # resident entry: the data columns carry blind seed 1, the accum noise the call's seed
+        _, g3, code3, data3 = make_segment(orc, widths, 13)
+        for blind in (1, 1):
+            assert (c.prove_resident(blind) == cir.prove(13, g3, code3, data3, blind)[0]).all()
+        c.set_transcript(0)                                 # back to the host transcript: same seal
+        assert (c.prove_resident(1) == cir.prove(13, g3, code3, data3, 1)[0]).all()
