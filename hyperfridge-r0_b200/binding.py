@@ -57,7 +57,20 @@ class Stats(C.Structure):
 
 class CircuitIR(C.Structure):
     _fields_ = [("w_code", C.c_uint32), ("w_data", C.c_uint32), ("w_accum", C.c_uint32), ("n_mix", C.c_uint32),
-                ("taps", C.c_void_p), ("n_taps", C.c_size_t), ("steps", C.c_void_p), ("n_steps", C.c_size_t), ("ret", C.c_uint32)]
+                ("taps", C.c_void_p), ("n_taps", C.c_size_t), ("steps", C.c_void_p), ("n_steps", C.c_size_t), ("ret", C.c_uint32),
+                ("info", C.c_uint8 * 16)]  # CIRCUIT_INFO; zeros = upstream's "RV32IM:v2_______"
+
+
+def _mk_ir(ir, *fields):
+    """hfb200_circuit_ir from positional fields + the circuit's 16-byte CIRCUIT_INFO (ir["info"]; absent / None = zeros = the
+    library default for data-defined circuits, upstream's b"RV32IM:v2_______")."""
+    d = CircuitIR(*fields)
+    info = ir.get("info") if hasattr(ir, "get") else None
+    if info is not None:
+        if len(info) != 16:
+            raise Hfb200Error("circuit info must be 16 bytes")
+        C.memmove(d.info, bytes(info), 16)
+    return d
 
 
 class SegmentJob(C.Structure):
@@ -181,7 +194,7 @@ class Context:
         self._po2 = max_po2
         if ir is not None:
             taps, steps = _u32(ir["taps"]), _u32(ir["steps"])
-            desc = CircuitIR(self.circuit[0], self.circuit[1], self.circuit[2], int(ir["n_mix"]), taps.ctypes.data, taps.size // 3,
+            desc = _mk_ir(ir, self.circuit[0], self.circuit[1], self.circuit[2], int(ir["n_mix"]), taps.ctypes.data, taps.size // 3,
                              steps.ctypes.data, steps.size // 4, int(ir["ret"]))
             self._check(self.lib.hfb200_init_ir(device, max_po2, C.byref(desc), C.byref(h)))
         else:
@@ -410,7 +423,7 @@ def verify_segment(seal, code_root, circuit=(16, 192, 48), ir=None, lib=None):
     po2 = C.c_uint32()
     if ir is not None:
         taps, steps = _u32(ir["taps"]), _u32(ir["steps"])
-        d = CircuitIR(circuit[0], circuit[1], circuit[2], int(ir["n_mix"]), taps.ctypes.data, taps.size // 3, steps.ctypes.data, steps.size // 4, int(ir["ret"]))
+        d = _mk_ir(ir, circuit[0], circuit[1], circuit[2], int(ir["n_mix"]), taps.ctypes.data, taps.size // 3, steps.ctypes.data, steps.size // 4, int(ir["ret"]))
         e = lib.hfb200_verify_segment(None, C.byref(d), _ptr(seal), seal.size, _ptr(code_root), C.byref(po2))
     else:
         d = CircuitDesc(circuit[0], circuit[1], circuit[2], 0)
@@ -487,7 +500,7 @@ def verify_segments(seals, code_roots, circuit=(16, 192, 48), ir=None, threads=0
     bad = C.c_size_t(n)
     if ir is not None:
         taps, steps = _u32(ir["taps"]), _u32(ir["steps"])
-        d = CircuitIR(circuit[0], circuit[1], circuit[2], int(ir["n_mix"]), taps.ctypes.data, taps.size // 3, steps.ctypes.data, steps.size // 4, int(ir["ret"]))
+        d = _mk_ir(ir, circuit[0], circuit[1], circuit[2], int(ir["n_mix"]), taps.ctypes.data, taps.size // 3, steps.ctypes.data, steps.size // 4, int(ir["ret"]))
         e = lib.hfb200_verify_segments(None, C.byref(d), ptrs, lens, n, _ptr(roots) if n else None, _ptr(po2), threads, C.byref(bad))
     else:
         d = CircuitDesc(circuit[0], circuit[1], circuit[2], 0)
@@ -514,7 +527,7 @@ def ir_source(ir, circuit, lib=None):
     """CUDA source that hfb200_init_ir compiles for the eval_check of a data-defined circuit (needs no device)."""
     lib = lib or load_library()
     taps, steps = _u32(ir["taps"]), _u32(ir["steps"])
-    desc = CircuitIR(circuit[0], circuit[1], circuit[2], int(ir["n_mix"]), taps.ctypes.data, taps.size // 3, steps.ctypes.data, steps.size // 4, int(ir["ret"]))
+    desc = _mk_ir(ir, circuit[0], circuit[1], circuit[2], int(ir["n_mix"]), taps.ctypes.data, taps.size // 3, steps.ctypes.data, steps.size // 4, int(ir["ret"]))
     need = C.c_size_t()
     e = lib.hfb200_ir_source(C.byref(desc), None, 0, C.byref(need))
     if e:
@@ -538,7 +551,7 @@ class Pool:
         self._h = None
         if ir is not None:
             taps, steps = _u32(ir["taps"]), _u32(ir["steps"])
-            desc = CircuitIR(self.circuit[0], self.circuit[1], self.circuit[2], int(ir["n_mix"]), taps.ctypes.data, taps.size // 3,
+            desc = _mk_ir(ir, self.circuit[0], self.circuit[1], self.circuit[2], int(ir["n_mix"]), taps.ctypes.data, taps.size // 3,
                              steps.ctypes.data, steps.size // 4, int(ir["ret"]))
             e = self.lib.hfb200_pool_create_ir(devs, len(devices), contexts_per_device, max_po2, C.byref(desc), C.byref(h))
         else:

@@ -72,7 +72,7 @@ const char* hfb200_init_ir(int device, uint32_t max_po2, const hfb200_circuit_ir
     hfb200_ctx* ctx = new hfb200_ctx();
     try {
         ctx->p.init(device, max_po2, c->w_code, c->w_data, c->w_accum, reinterpret_cast<const IrTap*>(c->taps), c->n_taps,
-                    reinterpret_cast<const IrStep*>(c->steps), c->n_steps, c->ret, c->n_mix);
+                    reinterpret_cast<const IrStep*>(c->steps), c->n_steps, c->ret, c->n_mix, c->info);
     } catch (...) { delete ctx; throw; }
     *out = ctx;
     API_CATCH
@@ -245,7 +245,7 @@ struct hfb200_pool {
     uint32_t max_po2 = 0;
     hfb200_circuit_desc desc{};
     bool is_ir = false;
-    std::vector<IrTap> ir_taps; std::vector<IrStep> ir_steps; uint32_t ir_ret = 0, ir_n_mix = 0;
+    std::vector<IrTap> ir_taps; std::vector<IrStep> ir_steps; uint32_t ir_ret = 0, ir_n_mix = 0; uint8_t ir_info[16] = {0};
     int blind_mode = BLIND_OS_ENTROPY;
     // test hook (hfb200_pool_inject_fault): worker `w` reports a CUDA error instead of proving its n-th job from now
     std::mutex inject_mu;
@@ -255,7 +255,7 @@ struct hfb200_pool {
     hfb200_ctx* make_ctx(int device) const {
         hfb200_ctx* ctx = new hfb200_ctx();
         try {
-            if (is_ir) ctx->p.init(device, max_po2, desc.w_code, desc.w_data, desc.w_accum, ir_taps.data(), ir_taps.size(), ir_steps.data(), ir_steps.size(), ir_ret, ir_n_mix);
+            if (is_ir) ctx->p.init(device, max_po2, desc.w_code, desc.w_data, desc.w_accum, ir_taps.data(), ir_taps.size(), ir_steps.data(), ir_steps.size(), ir_ret, ir_n_mix, ir_info);
             else ctx->p.init(device, max_po2, desc.w_code, desc.w_data, desc.w_accum);
             ctx->p.blind_mode = blind_mode;
         } catch (...) { try { ctx->p.destroy(); } catch (...) {} delete ctx; throw; }
@@ -312,7 +312,7 @@ const char* hfb200_pool_create_ir(const int* devices, int n_devices, int context
     const IrStep* st = reinterpret_cast<const IrStep*>(c->steps);
     pool->ir_taps.assign(t, t + c->n_taps);
     pool->ir_steps.assign(st, st + c->n_steps);
-    pool->ir_ret = c->ret; pool->ir_n_mix = c->n_mix;
+    pool->ir_ret = c->ret; pool->ir_n_mix = c->n_mix; std::memcpy(pool->ir_info, c->info, 16);
     pool_fill(pool.get(), devices, n_devices, contexts_per_device);
     *out = pool.release();
     API_CATCH
@@ -602,7 +602,7 @@ const char* hfb200_verify_segment(const hfb200_circuit_desc* c, const hfb200_cir
     VCircuit vc;
     if (c) vc.init_builtin(c->w_code, c->w_data, c->w_accum);
     else vc.init_ir(ir->w_code, ir->w_data, ir->w_accum, ir->n_mix, reinterpret_cast<const IrTap*>(ir->taps), ir->n_taps,
-                    reinterpret_cast<const IrStep*>(ir->steps), ir->n_steps, ir->ret);
+                    reinterpret_cast<const IrStep*>(ir->steps), ir->n_steps, ir->ret, ir->info);
     verify_segment(vc, seal, seal_words, code_root, po2_out);
     API_CATCH
 }
@@ -618,7 +618,7 @@ const char* hfb200_verify_segments(const hfb200_circuit_desc* c, const hfb200_ci
     VCircuit vc;
     if (c) vc.init_builtin(c->w_code, c->w_data, c->w_accum);
     else vc.init_ir(ir->w_code, ir->w_data, ir->w_accum, ir->n_mix, reinterpret_cast<const IrTap*>(ir->taps), ir->n_taps,
-                    reinterpret_cast<const IrStep*>(ir->steps), ir->n_steps, ir->ret);
+                    reinterpret_cast<const IrStep*>(ir->steps), ir->n_steps, ir->ret, ir->info);
     p2_host_consts();
     unsigned nt = threads ? threads : std::thread::hardware_concurrency();
     if (nt == 0) nt = 1;

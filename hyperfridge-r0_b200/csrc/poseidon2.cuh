@@ -421,7 +421,14 @@ static inline Digest8 host_hash_elems(const uint32_t* in, size_t n) {
 struct HostRng {
     uint32_t cells[24] = {0};
     int pool_used = 0;
-    void mix(const uint32_t* d8) { p2_host_consts(); for (int i = 0; i < 8; i++) cells[i] = fadd(cells[i], d8[i]); p2_mix(cells); pool_used = 0; }
+    // Poseidon2Rng::mix: a permutation first when elements were drawn since the last mix (upstream: "if switching from squeezing,
+    // do a poseidon2 mix"), then add the 8 digest words into the rate and permute
+    void mix(const uint32_t* d8) {
+        p2_host_consts();
+        if (pool_used != 0) { p2_mix(cells); pool_used = 0; }
+        for (int i = 0; i < 8; i++) cells[i] = fadd(cells[i], d8[i]);
+        p2_mix(cells);
+    }
     uint32_t random_elem() { if (pool_used == 16) { p2_mix(cells); pool_used = 0; } return cells[pool_used++]; }
     E4 random_ext() { uint32_t a = random_elem(), b = random_elem(), c = random_elem(), d = random_elem(); return e4(a, b, c, d); }
     uint32_t random_bits(unsigned bits) {
@@ -430,5 +437,37 @@ struct HostRng {
         return v & (uint32_t)((1ull << bits) - 1);
     }
 };
+
+// ---- transcript header ------------------------------------------------------------------------------------------------
+// risc0-circuit-rv32im `SegmentProver::prove` / risc0-zkp `verify`: "At the start of the protocol, seed the Fiat-Shamir
+// transcript with context information about the proof system and circuit":
+//   commit(H(PROOF_SYSTEM_INFO.encode())); commit(H(CIRCUIT_INFO.encode()));         (`ProtocolInfo`: 16 bytes, one element per byte)
+//   header = globals ++ [po2 as a raw word]; commit(H(header)); write header
+// Returns the header digest.  Host code, shared by the prover (both transcript modes) and the verifier.
+static constexpr char PROOF_SYSTEM_INFO[17] = "RISC0_STARK:v1__";      // risc0-zkp PROOF_SYSTEM_INFO
+static constexpr char BUILTIN_CIRCUIT_INFO[17] = "SYNTH_RV32IM:v1_";   // the declared stand-in circuit names itself
+static constexpr char DEFAULT_IR_CIRCUIT_INFO[17] = "RV32IM:v2_______"; // data-defined circuits: upstream's rv32im-v2 string unless given
+// dst[17] <- the circuit's info string: built-in circuit, data-defined with its own 16 bytes, or data-defined default
+static inline void set_circuit_info(char* dst, bool data_defined, const uint8_t* info16) {
+    bool given = false;
+    if (info16) for (int i = 0; i < 16; i++) given = given || info16[i] != 0;
+    if (!data_defined) std::memcpy(dst, BUILTIN_CIRCUIT_INFO, 17);
+    else if (given) { std::memcpy(dst, info16, 16); dst[16] = 0; }
+    else std::memcpy(dst, DEFAULT_IR_CIRCUIT_INFO, 17);
+}
+static inline Digest8 protocol_info_digest(const char* info16) {
+    uint32_t e[16];
+    for (int i = 0; i < 16; i++) e[i] = to_mont((uint32_t)(uint8_t)info16[i]);
+    return host_hash_elems(e, 16);
+}
+static inline Digest8 transcript_header(HostRng& rng, const char* circuit_info16, const uint32_t* globals, size_t n_globals, uint32_t po2) {
+    rng.mix(protocol_info_digest(PROOF_SYSTEM_INFO).w);
+    rng.mix(protocol_info_digest(circuit_info16).w);
+    std::vector<uint32_t> header(globals, globals + n_globals);
+    header.push_back(po2);
+    const Digest8 d = host_hash_elems(header.data(), header.size());
+    rng.mix(d.w);
+    return d;
+}
 
 }  // namespace hf

@@ -68,6 +68,7 @@ struct Prover {
     GenericCircuitHost gen;  // active for data-defined circuits (hfb200_init_ir)
     JitEvalCheck jit;        // their eval_check, specialised at registration (NVRTC, sm_100a)
     uint32_t max_po2 = 0;
+    char circuit_info[17] = {0};  // upstream CircuitImpl::CIRCUIT_INFO: second commit of every transcript (poseidon2.cuh)
     int device_id = 0;
     Arena arena;
     bool debug_checkpoints = false;
@@ -122,9 +123,10 @@ struct Prover {
     uint64_t host_syncs = 0, host_syncs_at_begin = 0;
 
     void init(int device, uint32_t max_po2_, uint32_t wc, uint32_t wd, uint32_t wa, const IrTap* taps = nullptr, size_t n_taps = 0,
-              const IrStep* steps = nullptr, size_t n_steps = 0, uint32_t ret = 0, uint32_t n_mix_ir = 0) {
+              const IrStep* steps = nullptr, size_t n_steps = 0, uint32_t ret = 0, uint32_t n_mix_ir = 0, const uint8_t* info16 = nullptr) {
         if (max_po2_ < 12 || max_po2_ > 22) throw Err("max_po2 must be in [12, 22]");
         max_po2 = max_po2_;
+        set_circuit_info(circuit_info, taps != nullptr, info16);
 #ifndef HFB200_EMU
         int count = 0;
         cudaError_t e = cudaGetDeviceCount(&count);
@@ -395,8 +397,7 @@ struct Prover {
         const bool chunked = sg.chunked, use_control = sg.use_control;
         const size_t N = (size_t)1 << po2;
         mark(1);
-        const Digest8 gh = host_hash_elems(globals, N_GLOBAL);
-        rng.mix(gh.w);
+        const Digest8 gh = transcript_header(rng, circuit_info, globals, N_GLOBAL, po2);
         proof.insert(proof.end(), globals, globals + N_GLOBAL);
         proof.push_back(po2);
         cp_add("globals_hash", gh.w, 8);
@@ -851,7 +852,8 @@ struct Prover {
         ensure_out((words + cp_words) * 4);
         uint32_t* seal_pin = reinterpret_cast<uint32_t*>(out_h);
         uint32_t* cp_pin = seal_pin + words;
-        const Digest8 gh = host_hash_elems(globals, N_GLOBAL);
+        HostRng r0;
+        const Digest8 gh = transcript_header(r0, circuit_info, globals, N_GLOBAL, po2);  // host-computed in every transcript mode
         bool chunked = sg.chunked;
         uint32_t round = 0;
         uint32_t* fin = nullptr;
@@ -866,7 +868,6 @@ struct Prover {
         h2d_small(d_key, &blind_key, sizeof blind_key);
         // header: the globals are the caller's, so their hash and the RNG state after mixing it are computed here and uploaded
         {
-            HostRng r0; r0.mix(gh.w);
             TxState h{};
             std::memcpy(h.cells, r0.cells, sizeof h.cells);
             h2d_small(d_tx, &h, sizeof h);

@@ -49,6 +49,13 @@ HD void tx_permute(const KCtx& cx, uint32_t* cells) {
 }
 // Poseidon2Rng::mix(digest)
 HD void tx_mix(const KCtx& cx, TxState* t, const uint32_t* d8) {
+    if (t->pool_used != 0) {  // switching from squeezing: one permutation first (uniform across the warp)
+        cx.sync();
+        tx_permute(cx, t->cells);
+        cx.sync();
+        if (cx.tid == 0) t->pool_used = 0;
+        cx.sync();
+    }
     for (uint32_t i = cx.tid; i < 8; i += cx.nt) t->cells[i] = fadd(t->cells[i], d8[i]);
     cx.sync();
     tx_permute(cx, t->cells);

@@ -79,9 +79,11 @@ struct VCircuit {
     GenericCircuitHost g;   // taps / regs / combos (+ bytecode for data-defined circuits); host tables only
     bool builtin = false;
     CircuitHost ch;         // built-in circuit: picks / chain sources (host copies only)
+    char info[17] = {0};    // CIRCUIT_INFO hashed into the transcript header
 
     void init_builtin(uint32_t wc, uint32_t wd, uint32_t wa) {
         builtin = true;
+        set_circuit_info(info, false, nullptr);
         ch.init_host(wc, wd, wa);
         std::vector<IrTap> taps;
         for (uint32_t c = 0; c < wa; c++) { taps.push_back(IrTap{GROUP_ACCUM, c, 0}); taps.push_back(IrTap{GROUP_ACCUM, c, 1}); }
@@ -90,8 +92,10 @@ struct VCircuit {
         g.w[GROUP_ACCUM] = wa; g.w[GROUP_CODE] = wc; g.w[GROUP_DATA] = wd; g.n_mix = 4 * ch.cd.n_chains;
         g.analyze_taps(taps.data(), taps.size());
     }
-    void init_ir(uint32_t wc, uint32_t wd, uint32_t wa, uint32_t n_mix, const IrTap* tp, size_t n_taps, const IrStep* st, size_t n_steps, uint32_t ret) {
+    void init_ir(uint32_t wc, uint32_t wd, uint32_t wa, uint32_t n_mix, const IrTap* tp, size_t n_taps, const IrStep* st, size_t n_steps, uint32_t ret,
+                 const uint8_t* info16 = nullptr) {
         builtin = false;
+        set_circuit_info(info, true, info16);
         g.init(nullptr, wc, wd, wa, n_mix, tp, n_taps, st, n_steps, ret);
     }
 
@@ -236,7 +240,7 @@ static inline void verify_segment(const VCircuit& vc, const uint32_t* seal, size
     const uint32_t po2 = iop.read_u32();
     if (po2 < 12 || po2 > 24) vfail("po2 out of range");  // the prover (and the oracle) start at 12
     if (po2_out) *po2_out = po2;
-    iop.commit(host_hash_elems(globals, N_GLOBAL));
+    transcript_header(iop.rng, vc.info, globals, N_GLOBAL, po2);
     const size_t N = (size_t)1 << po2, domain = N * V_INV_RATE;
 
     VMerkle code_v(iop, domain, g.w[GROUP_CODE]);

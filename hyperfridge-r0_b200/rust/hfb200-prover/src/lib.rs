@@ -85,6 +85,7 @@ impl CircuitTables {
             steps: self.steps.as_ptr(),
             n_steps: self.steps.len(),
             ret: self.ret,
+            info: CircuitImpl::CIRCUIT_INFO.0, // the same 16 bytes upstream's prover and verifier hash into the transcript
         }
     }
 }

@@ -48,6 +48,8 @@ pub struct hfb200_circuit_ir {
     pub steps: *const hfb200_poly_step,
     pub n_steps: usize,
     pub ret: u32,
+    /// upstream `CircuitImpl::CIRCUIT_INFO` (16 bytes); all zero selects "RV32IM:v2_______"
+    pub info: [u8; 16],
 }
 
 #[repr(C)]

@@ -59,6 +59,8 @@ typedef struct {
     const hfb200_poly_step* steps;
     size_t n_steps;
     uint32_t ret;
+    uint8_t info[16];                 /* upstream `CircuitImpl::CIRCUIT_INFO` (risc0-zkp `ProtocolInfo`): hashed into the transcript right
+                                         after the proof-system info; all zero = "RV32IM:v2_______" (upstream's rv32im-v2 string) */
 } hfb200_circuit_ir;
 
 #define HFB200_N_GLOBAL 32u

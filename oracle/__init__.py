@@ -57,6 +57,7 @@ def lib():
         L.orc_rng_bits.restype = C.c_uint32
         L.orc_rng_bits.argtypes = [vp, C.c_uint, C.c_size_t]
         L.orc_rng_draw.argtypes = [vp, C.c_size_t, vp, C.c_size_t]
+        L.orc_rng_mix_draw_mix.argtypes = [vp, C.c_size_t, vp, vp, C.c_size_t]
         L.orc_hash_elems.argtypes = [vp, C.c_size_t, vp]
         L.orc_hash_pair.argtypes = [vp, vp, vp]
         L.orc_poseidon2_mix.argtypes = [vp]
@@ -80,7 +81,7 @@ def lib():
         L.orc_circuit_new.restype = vp
         L.orc_circuit_new.argtypes = [C.c_uint32] * 4
         L.orc_circuit_free.argtypes = [vp]
-        L.orc_circuit_set_ir.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_uint32]
+        L.orc_circuit_set_ir.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_uint32, C.c_char_p]
         L.orc_h_n_taps.restype = C.c_size_t
         L.orc_h_n_taps.argtypes = [vp]
         L.orc_h_taps.argtypes = [vp, vp]
@@ -165,6 +166,14 @@ def rng_draw(digests, n_out):
     return out
 
 
+def rng_mix_draw_mix(d1, n_skip, d2, n_out):
+    """Poseidon2Rng: mix(d1), draw n_skip elements, mix(d2), draw n_out elements."""
+    d1, d2 = _u32(d1), _u32(d2)
+    out = np.zeros(n_out, np.uint32)
+    lib().orc_rng_mix_draw_mix(_p(d1), n_skip, _p(d2), _p(out), n_out)
+    return out
+
+
 def interpolate_ntt(cols):
     a = _u32(cols).copy()
     a2 = a.reshape(-1, a.shape[-1])
@@ -229,7 +238,7 @@ class Circuit:
         if use_ir:
             from . import synth_ir
             self.ir = synth_ir.build(self.w, variant)
-            self.set_ir(self.ir["taps"], self.ir["steps"], self.ir["ret"])
+            self.set_ir(self.ir["taps"], self.ir["steps"], self.ir["ret"], self.ir.get("info"))
         self.n_taps = lib().orc_h_n_taps(self._h)
 
     def __del__(self):
@@ -240,9 +249,12 @@ class Circuit:
         except Exception:
             pass
 
-    def set_ir(self, taps, steps, ret):
+    def set_ir(self, taps, steps, ret, info=None):
+        """info: the circuit's 16-byte CIRCUIT_INFO hashed into the transcript header (None = upstream's b"RV32IM:v2_______")."""
         taps, steps = _u32(taps), _u32(steps)
-        _check(lib().orc_circuit_set_ir(self._h, _p(taps), taps.size // 3, _p(steps), steps.size // 4, ret))
+        if info is not None and len(info) != 16:
+            raise ValueError("circuit info must be 16 bytes")
+        _check(lib().orc_circuit_set_ir(self._h, _p(taps), taps.size // 3, _p(steps), steps.size // 4, ret, info))
 
     def taps(self):
         out = np.zeros((lib().orc_h_n_taps(self._h), 3), np.uint32)

@@ -50,6 +50,14 @@ void orc_rng_draw(const uint32_t* digests, size_t n_digests, uint32_t* out, size
     for (size_t i = 0; i < n_digests; i++) r.mix(*reinterpret_cast<const Digest*>(digests + 8 * i));
     for (size_t i = 0; i < n_out; i++) out[i] = r.random_elem().v;
 }
+// mix(d1), draw n_skip elements, mix(d2), draw n_out elements: the squeeze -> absorb switch of Poseidon2Rng::mix
+void orc_rng_mix_draw_mix(const uint32_t* d1, size_t n_skip, const uint32_t* d2, uint32_t* out, size_t n_out) {
+    Poseidon2Rng r;
+    r.mix(*reinterpret_cast<const Digest*>(d1));
+    for (size_t i = 0; i < n_skip; i++) (void)r.random_elem();
+    r.mix(*reinterpret_cast<const Digest*>(d2));
+    for (size_t i = 0; i < n_out; i++) out[i] = r.random_elem().v;
+}
 uint32_t orc_rng_bits(const uint32_t* digest, unsigned bits, size_t skip) {
     Poseidon2Rng r; r.mix(*reinterpret_cast<const Digest*>(digest));
     uint32_t v = 0;
@@ -128,7 +136,8 @@ void* orc_circuit_new(uint32_t wc, uint32_t wd, uint32_t wa, uint32_t variant) {
 }
 void orc_circuit_free(void* h) { delete static_cast<Circuit*>(h); }
 // taps: n_taps triples (group, offset, back) sorted; steps: n_steps quads (op, a, b, c); ret: mix var holding the result
-int orc_circuit_set_ir(void* h, const uint32_t* taps, size_t n_taps, const uint32_t* steps, size_t n_steps, uint32_t ret) {
+// info16: the circuit's 16-byte CIRCUIT_INFO (NULL = upstream's "RV32IM:v2_______")
+int orc_circuit_set_ir(void* h, const uint32_t* taps, size_t n_taps, const uint32_t* steps, size_t n_steps, uint32_t ret, const uint8_t* info16) {
     ORC_TRY
     Circuit* c = static_cast<Circuit*>(h);
     if (taps) {
@@ -138,7 +147,7 @@ int orc_circuit_set_ir(void* h, const uint32_t* taps, size_t n_taps, const uint3
     }
     std::vector<PolyStep> st(n_steps);
     for (size_t i = 0; i < n_steps; i++) st[i] = PolyStep{steps[4 * i], steps[4 * i + 1], steps[4 * i + 2], steps[4 * i + 3]};
-    c->set_ir(st, ret);
+    c->set_ir(st, ret, info16);
     ORC_CATCH
 }
 size_t orc_h_n_taps(void* h) { return static_cast<Circuit*>(h)->taps.size(); }

@@ -11,6 +11,7 @@
 //   gen_code / gen_data <->  control columns / WitnessGenerator stand-in
 // The CUDA product implements the same definition independently (hyperfridge-r0_b200/csrc/circuit.cuh).
 #pragma once
+#include <cstring>
 #include <vector>
 #include <algorithm>
 #include <tuple>
@@ -101,7 +102,13 @@ struct Circuit {
             group_tap_begin[g] = k;
         }
     }
-    void set_ir(const std::vector<PolyStep>& steps, uint32_t ret) { ir = steps; ir_ret = ret; }
+    // upstream `CircuitImpl::CIRCUIT_INFO` (risc0-zkp `ProtocolInfo`, 16 bytes): hashed into the transcript before anything else.
+    // The built-in stand-in names itself; a data-defined circuit (upstream's tables) carries upstream's rv32im-v2 string.
+    char circuit_info[17] = "SYNTH_RV32IM:v1_";
+    void set_ir(const std::vector<PolyStep>& steps, uint32_t ret, const uint8_t* info16 = nullptr) {
+        ir = steps; ir_ret = ret;
+        if (info16) { std::memcpy(circuit_info, info16, 16); circuit_info[16] = 0; } else std::memcpy(circuit_info, "RV32IM:v2_______", 17);
+    }
     uint32_t group_width(uint32_t g) const { return g == GROUP_ACCUM ? w_accum : g == GROUP_CODE ? w_code : w_data; }
     uint32_t n_constraints() const { return n_free + 4 * n_chains + 1; }
     uint32_t n_mix() const { return 4 * n_chains; }

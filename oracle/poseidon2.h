@@ -106,7 +106,12 @@ static inline Digest hash_pair(const Digest& a, const Digest& b) {
 struct Poseidon2Rng {
     Fp cells[CELLS];
     int pool_used = 0;
+    // risc0-zkp 3.0.4 `core/hash/poseidon2/rng.rs`, `Poseidon2Rng::mix`: "if switching from squeezing, do a poseidon2 mix";
+    // "Add in CELLS_OUT elements (also # of digest words)"; "Mix".  The first step (a permutation when elements were drawn
+    // since the last mix) was missing from SURVEY.md Appendix A.3's restatement and was added in round 2 from recollection
+    // of that source file.
     void mix(const Digest& d) {
+        if (pool_used != 0) { poseidon2_mix(cells); pool_used = 0; }
         for (int i = 0; i < CELLS_OUT; i++) cells[i] += Fp::raw(d.w[i]);
         poseidon2_mix(cells);
         pool_used = 0;

@@ -63,6 +63,24 @@ static void fri_prove(WriteIOP& iop, Checkpoints& cp, std::vector<Fp> coeffs /* 
     for (FriRoundTree* rt : rounds) { delete rt->merkle; delete rt; }
 }
 
+// risc0-zkp `ProtocolInfo::encode`: one field element per byte of the 16-byte info string
+static Digest protocol_info_digest(const char* info16) {
+    Fp e[16];
+    for (int i = 0; i < 16; i++) e[i] = Fp::from_u32((uint8_t)info16[i]);
+    return hash_elems(e, 16);
+}
+// The three commits every transcript starts with (prover and verifier); returns the header digest H(globals ++ [po2]).
+static Digest transcript_header(Poseidon2Rng& rng, const char* circuit_info, const Fp* globals, uint32_t po2) {
+    rng.mix(protocol_info_digest("RISC0_STARK:v1__"));  // risc0-zkp PROOF_SYSTEM_INFO
+    rng.mix(protocol_info_digest(circuit_info));
+    Fp header[Circuit::N_GLOBAL + 1];
+    for (size_t i = 0; i < Circuit::N_GLOBAL; i++) header[i] = globals[i];
+    header[Circuit::N_GLOBAL] = Fp::raw(po2);
+    const Digest d = hash_elems(header, Circuit::N_GLOBAL + 1);
+    rng.mix(d);
+    return d;
+}
+
 SegmentProof prove_segment(const Circuit& cir, unsigned po2, const Fp* globals, const Fp* code, const Fp* data,
                            uint64_t blind_seed, OracleTimes* times) {
     if (po2 < 12 || po2 > 24) throw std::runtime_error("prove: po2 out of range");
@@ -72,8 +90,10 @@ SegmentProof prove_segment(const Circuit& cir, unsigned po2, const Fp* globals, 
     Checkpoints& cp = out.cp;
     WriteIOP iop;
 
-    Digest gh = hash_elems(globals, Circuit::N_GLOBAL);
-    iop.commit(gh);
+    // risc0-circuit-rv32im `SegmentProver::prove`: "At the start of the protocol, seed the Fiat-Shamir transcript with context
+    // information about the proof system and circuit": commit(H(PROOF_SYSTEM_INFO.encode())), commit(H(CIRCUIT_INFO.encode()));
+    // then "Concat globals and po2 into a vector": commit(H(header)), write header (po2 as a raw word).
+    Digest gh = transcript_header(iop.rng, cir.circuit_info, globals, po2);
     iop.write_elems(globals, Circuit::N_GLOBAL);
     uint32_t po2w = po2;
     iop.write_u32s(&po2w, 1);
@@ -260,7 +280,7 @@ void verify_segment(const Circuit& cir, const uint32_t* seal, size_t seal_words,
     iop.read_u32s(&po2, 1);
     if (po2 < 12 || po2 > 24) fail("po2 out of range");
     if (po2_out) *po2_out = po2;
-    iop.commit(hash_elems(globals, Circuit::N_GLOBAL));
+    transcript_header(iop.rng, cir.circuit_info, globals, po2);
     const size_t N = (size_t)1 << po2, domain = N * INV_RATE;
 
     MerkleTreeVerifier code_v(iop, domain, cir.w_code);

@@ -103,7 +103,7 @@ def build(widths, variant=0, nest=False):
             m = mixv(7, m, mul(active, sub(acc[k], pr)))
     m = mixv(7, m, mul(first, sub(get(DATA, 0), glob(0, 0))))
     return {"taps": np.array(taps, np.uint32), "steps": np.array(steps, np.uint32), "ret": m, "n_globals": 32, "n_mix": 4 * nch,
-            "widths": tuple(widths)}
+            "widths": tuple(widths), "info": b"SYNTH_RV32IM:v1_"}  # the stand-in circuit itself, as data: same CIRCUIT_INFO as the built-in form
 
 
 def build_scaled(widths=(24, 320, 56), n_groups=420, per_group=16, seed=7):
@@ -172,4 +172,4 @@ def build_scaled(widths=(24, 320, 56), n_groups=420, per_group=16, seed=7):
             n_cons += 1
         m = mixv(8, m, sel, inner)
     return {"taps": np.array(taps, np.uint32), "steps": np.array(steps, np.uint32), "ret": m, "n_globals": 32, "n_mix": wa,
-            "widths": tuple(widths), "n_constraints": n_cons}
+            "widths": tuple(widths), "n_constraints": n_cons, "info": None}  # None: the default of a data-defined circuit (upstream's rv32im-v2 string)

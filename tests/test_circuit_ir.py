@@ -34,7 +34,7 @@ def test_data_defined_circuit_matches_oracle(pkg, emu_lib, orc, variant, nest):
     cir, g, code, data = _segment(orc, widths, po2, variant)
     ir = synth_ir.build(widths, variant, nest=nest)
     cir_ir = orc.Circuit(*widths, variant=variant)
-    cir_ir.set_ir(ir["taps"], ir["steps"], ir["ret"])
+    cir_ir.set_ir(ir["taps"], ir["steps"], ir["ret"], ir.get("info"))
     oseal, ocps, _ = cir_ir.prove(po2, g, code, data, 1)
     with pkg.Context(0, po2, widths, lib=emu_lib, ir=ir) as c:
         mix = c.segment_begin(po2, g, code, data, 1)
@@ -114,7 +114,7 @@ def test_chunked_program_equals_the_monolithic_one(pkg, emu_lib, orc, monkeypatc
     code = cir.gen_code(po2); g = cir.gen_globals(5); data = cir.gen_data(po2, code, g, 5, 1)
     ir = synth_ir.build(widths, 1, nest=True)
     cir_ir = orc.Circuit(*widths, variant=1)
-    cir_ir.set_ir(ir["taps"], ir["steps"], ir["ret"])
+    cir_ir.set_ir(ir["taps"], ir["steps"], ir["ret"], ir.get("info"))
     oseal, ocps, _ = cir_ir.prove(po2, g, code, data, 1)
     for chunk in ("64", "150", "100000"):
         monkeypatch.setenv("HFB200_IR_CHUNK", chunk)
@@ -140,7 +140,7 @@ def test_data_defined_circuit_at_rv32im_scale(pkg, emu_lib, orc):
     code = cir.gen_code(po2); g = cir.gen_globals(9)
     data = rng.integers(0, orc.P, size=(W[1], 1 << po2), dtype=np.uint32)
     cir_ir = orc.Circuit(*W)
-    cir_ir.set_ir(ir["taps"], ir["steps"], ir["ret"])
+    cir_ir.set_ir(ir["taps"], ir["steps"], ir["ret"], ir.get("info"))
     oseal, ocps, _ = cir_ir.prove(po2, g, code, data, 1)
     with pkg.Context(0, po2, W, lib=emu_lib, ir=ir) as c:
         mix = c.segment_begin(po2, g, code, data, 1)

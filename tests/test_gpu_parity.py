@@ -23,9 +23,13 @@ def ctx(pkg, gpu_lib):
 def test_poseidon2_permutation(ctx, orc):
     st = rand_elems(np.random.default_rng(0), (1000, 24))
     st[0] = 0
+    st[1] = orc.encode(list(range(24)))
     got = ctx.op_poseidon2(st)
     exp = np.stack([orc.poseidon2_mix(s) for s in st])
     assert (got == exp).all()
+    # upstream's own known-answer vector (risc0-zkp `poseidon2_test_vectors`, see tests/test_poseidon2.py) on the GPU kernel
+    from test_poseidon2 import UPSTREAM_KAT_0_TO_23
+    assert [int(v) for v in orc.decode(got[1])] == UPSTREAM_KAT_0_TO_23
 
 
 @pytest.mark.parametrize("lg", [1, 4, 10, 11, 12, 14, 15, 16, 17, 18, 19, 20, 21])
@@ -297,7 +301,7 @@ def test_data_defined_circuit_on_gpu(pkg, gpu_lib, orc, widths, po2, variant, ne
     code = cir.gen_code(po2); g = cir.gen_globals(5); data = cir.gen_data(po2, code, g, 5, 1)
     ir = synth_ir.build(widths, variant, nest=nest)
     cir_ir = orc.Circuit(*widths, variant=variant)
-    cir_ir.set_ir(ir["taps"], ir["steps"], ir["ret"])
+    cir_ir.set_ir(ir["taps"], ir["steps"], ir["ret"], ir.get("info"))
     oseal, ocps, _ = cir_ir.prove(po2, g, code, data, 1)
     with pkg.Context(0, po2, widths, lib=gpu_lib, ir=ir) as c:
         mix = c.segment_begin(po2, g, code, data, 1)
@@ -321,7 +325,7 @@ def test_jit_and_interpreter_agree_on_gpu(pkg, gpu_lib, orc, monkeypatch):
     code = cir.gen_code(po2); g = cir.gen_globals(5); data = cir.gen_data(po2, code, g, 5, 1)
     ir = synth_ir.build(widths, variant, nest=True)
     cir_ir = orc.Circuit(*widths, variant=variant)
-    cir_ir.set_ir(ir["taps"], ir["steps"], ir["ret"])
+    cir_ir.set_ir(ir["taps"], ir["steps"], ir["ret"], ir.get("info"))
     oseal, ocps, _ = cir_ir.prove(po2, g, code, data, 1)
     seals = {}
     for mode in ("1", "0"):
@@ -348,7 +352,7 @@ def test_data_defined_circuit_at_rv32im_scale_on_gpu(pkg, gpu_lib, orc, monkeypa
     code = cir.gen_code(po2); g = cir.gen_globals(9)
     data = rng.integers(0, orc.P, size=(W[1], 1 << po2), dtype=np.uint32)
     cir_ir = orc.Circuit(*W)
-    cir_ir.set_ir(ir["taps"], ir["steps"], ir["ret"])
+    cir_ir.set_ir(ir["taps"], ir["steps"], ir["ret"], ir.get("info"))
     oseal, ocps, _ = cir_ir.prove(po2, g, code, data, 1)
     for mode in ("1", "0"):
         monkeypatch.setenv("HFB200_IR_JIT", mode)

@@ -102,7 +102,7 @@ def test_data_defined_circuit(pkg, gpu_lib, orc, variant, nest):
     g = cir.gen_globals(5)
     data = cir.gen_data(po2, code, g, 5, 1)
     ir = synth_ir.build(widths, variant, nest=nest)
-    cir.set_ir(ir["taps"], ir["steps"], ir["ret"])
+    cir.set_ir(ir["taps"], ir["steps"], ir["ret"], ir.get("info"))
     seal, cps, _ = cir.prove(po2, g, code, data, 1)
     assert pkg.verify_segment(seal, cps["code_root"], widths, ir=ir, lib=gpu_lib) == po2
     if variant == 0:
@@ -197,3 +197,31 @@ def test_batch_verifier_fans_out_and_names_the_first_bad_seal(pkg, gpu_lib, orc)
         pkg.verify_segments(seals, [roots[0]] * 6, SMALL, lib=gpu_lib)
     with pytest.raises(pkg.Hfb200Error, match="one 8-word control id per seal"):
         pkg.verify_segments(seals, roots[:3], SMALL, lib=gpu_lib)
+
+
+def test_transcript_header_binds_proof_system_circuit_and_po2(pkg, gpu_lib, orc):
+    """Upstream seeds the transcript with H(PROOF_SYSTEM_INFO), H(CIRCUIT_INFO) and H(globals ++ [po2]) before anything else
+    (risc0-circuit-rv32im `SegmentProver::prove`, risc0-zkp `verify`).  The header digest is the hash of the 33-word header; the
+    same constraint tables under another CIRCUIT_INFO string are another statement: neither verifier accepts the seal."""
+    from oracle import synth_ir
+    widths, po2 = (12, 24, 8), 12
+    cir = orc.Circuit(*widths)
+    code = cir.gen_code(po2); g = cir.gen_globals(5); data = cir.gen_data(po2, code, g, 5, 1)
+    seal, cps, _ = cir.prove(po2, g, code, data, 1)
+    assert (cps["globals_hash"] == orc.hash_elems(np.concatenate([g, np.array([po2], np.uint32)]))).all()
+    ir = synth_ir.build(widths, 0)
+    assert ir["info"] == b"SYNTH_RV32IM:v1_"
+    assert pkg.verify_segment(seal, cps["code_root"], widths, ir=ir, lib=gpu_lib) == po2       # same circuit as data, same info
+    for info in (None, b"RV32IM:v2_______", b"SYNTH_RV32IM:v2_"):                                # None = the data-defined default
+        other = dict(ir, info=info)
+        with pytest.raises(pkg.Hfb200Error, match="verify"):
+            pkg.verify_segment(seal, cps["code_root"], widths, ir=other, lib=gpu_lib)
+        c2 = orc.Circuit(*widths)
+        c2.set_ir(ir["taps"], ir["steps"], ir["ret"], info)
+        with pytest.raises(RuntimeError):
+            c2.verify(seal, cps["code_root"])
+        s2, cps2, _ = c2.prove(po2, g, code, data, 1)                                            # and its own seals verify under that info only
+        assert pkg.verify_segment(s2, cps2["code_root"], widths, ir=other, lib=gpu_lib) == po2
+        assert (cps2["code_root"] == cps["code_root"]).all() and not (cps2["accum_mix"] == cps["accum_mix"]).all()
+    with pytest.raises(pkg.Hfb200Error, match="16 bytes"):
+        pkg.verify_segment(seal, cps["code_root"], widths, ir=dict(ir, info=b"short"), lib=gpu_lib)
