@@ -764,6 +764,7 @@ struct MiddleKernel2 {
 
 }  // namespace hf
 #include "ntt_tma.cuh"  // strided stages of the 2^10-row plans through TMA tensor maps (device builds only)
+#include "ntt_mid.cuh"  // fused middle stage of the main-group LDE, one warp per (column, chunk) (device builds only)
 namespace hf {
 
 // ---- host-side planning / launching ---------------------------------------------------------------
@@ -896,6 +897,9 @@ struct Ntt {
 
     void middle(const uint32_t* in, uint64_t in_stride, uint32_t* out, uint64_t out_stride, uint32_t ncols, int n, int a, int e, uint32_t flags) {
         if (a < 5) { middle_small(in, in_stride, out, out_stride, ncols, n, a, e, flags); return; }
+#ifndef HFB200_EMU
+        if (mid_warp(dev, rt, in, in_stride, out, out_stride, ncols, n, a, e, flags)) return;  // fused iNTT + x4 LDE of 2^10 chunks (ntt_mid.cuh)
+#endif
         Mid2Args p{};
         p.in = in; p.out = out; p.in_stride = in_stride; p.out_stride = out_stride; p.ncols = ncols;
         p.n = n; p.a = a; p.b = n - a; p.e = e; p.flags = flags;
