@@ -421,7 +421,7 @@ def main():
             traffic = float(json.load(f)["bytes_per_trace_element"]) * W * N
     except Exception:
         pass
-    roofline = {"kernel": "NTT/LDE pipeline of the 3 main groups: strided_tma_kernel<inverse> (TMA tensor-map tiles, 3-buffer pipeline) + MiddleKernel2 (fused iNTT.zk_shift.expand.NTT chunk stage) + strided_tma_kernel<forward>, 9 launches/segment",
+    roofline = {"kernel": "NTT/LDE pipeline of the 3 main groups: strided_tma_kernel<inverse> (TMA tensor-map tiles, 3-buffer pipeline) + mid_warp_kernel (fused iNTT.zk_shift.expand.NTT chunk stage: one warp per transform, four-warp teams, radix-32 register rounds, 16-byte stores) + strided_tma_kernel<forward>, 9 launches/segment",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes": ntt_bytes, "ms": ntt_ms, "peak_source": peak_src,
                 "note": "traffic = dram__bytes_read+write of the 3 kernels from one ncu --set full capture of THIS round's kernels (profiles/r2_ntt_traffic.json, 59.2 B per trace element) scaled to W*N elements; by design 60*W*N (8+20+32 B per element over the three passes) vs 28*W*N algorithmic; the binding units are the integer-multiply and ALU pipes, not HBM (DESIGN.md section 5)"}
