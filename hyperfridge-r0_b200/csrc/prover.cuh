@@ -60,6 +60,23 @@ struct Stats {
 
 struct Tree { uint32_t* matrix; uint64_t col_stride; uint32_t rows, cols; uint32_t* nodes; };
 
+#ifndef HFB200_EMU
+// Trace uploads of the contexts that share a device are CHAINED: a context's data copies start when the previous context's have
+// landed (a stream-order wait on that context's last chunk event, no host involvement).  Copies queued together from several
+// streams share the copy engine and the host's memory bandwidth, so k contexts starting together all get their trace after k
+// uploads' worth of time; in FIFO order the first one has it after one and its NTTs start while the others still copy.  Matters
+// where the host side is the narrow part (8 GPUs pulling from one host: ~15 GB/s per GPU).  HFB200_UPLOAD_CHAIN=0 disables it.
+struct UploadChain {
+    std::mutex mu;
+    cudaEvent_t last = nullptr;  // last chunk event of the most recent upload queued on this device (owned by its context)
+    static UploadChain& of(int device) {
+        static UploadChain chains[Dev::MAX_DEVICES];
+        return chains[device >= 0 && device < Dev::MAX_DEVICES ? device : 0];
+    }
+    static bool enabled() { static const bool on = [] { const char* e = std::getenv("HFB200_UPLOAD_CHAIN"); return !e || std::atoi(e) != 0; }(); return on; }
+};
+#endif
+
 struct Prover {
     Dev dev;
     Ntt ntt;
@@ -211,6 +228,11 @@ struct Prover {
         ntt.destroy();
 #ifndef HFB200_EMU
         for (auto& ev_ : evs) if (ev_) cudaEventDestroy(ev_);
+        {
+            UploadChain& chain = UploadChain::of(device_id);
+            std::lock_guard<std::mutex> lock(chain.mu);
+            if (chain.last == chunk_ev[H2D_CHUNKS - 1]) chain.last = nullptr;  // nobody may wait on an event that is about to go
+        }
         for (auto& ev_ : chunk_ev) if (ev_) cudaEventDestroy(ev_);
         if (copy_gate) cudaEventDestroy(copy_gate);
         if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -360,11 +382,18 @@ struct Prover {
             // stream (a previous segment's readers) has finished
             CUDA_CHECK(cudaEventRecord(copy_gate, dev.stream));
             CUDA_CHECK(cudaStreamWaitEvent(copy_stream, copy_gate, 0));
+            UploadChain& chain = UploadChain::of(device_id);
+            std::unique_lock<std::mutex> chain_lock(chain.mu, std::defer_lock);
+            if (UploadChain::enabled()) {
+                chain_lock.lock();  // held while this upload is queued: the chain order is the queueing order
+                if (chain.last && chain.last != chunk_ev[H2D_CHUNKS - 1]) CUDA_CHECK(cudaStreamWaitEvent(copy_stream, chain.last, 0));
+            }
             for (int k = 0; k < H2D_CHUNKS; k++) {
                 const uint32_t c0 = cir.cd.w_data * k / H2D_CHUNKS, c1 = cir.cd.w_data * (k + 1) / H2D_CHUNKS;
                 CUDA_CHECK(cudaMemcpyAsync(tr[GROUP_DATA] + (size_t)c0 * N, data_h + (size_t)c0 * N, (size_t)(c1 - c0) * N * 4, cudaMemcpyHostToDevice, copy_stream));
                 CUDA_CHECK(cudaEventRecord(chunk_ev[k], copy_stream));
             }
+            if (chain_lock.owns_lock()) chain.last = chunk_ev[H2D_CHUNKS - 1];
             chunked = true;
         } else
 #endif
