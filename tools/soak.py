@@ -3,6 +3,7 @@
 same (context, po2, blinding seed) -- catches rare races between contexts (stream / attribute / table sharing).
 Usage: soak.py [seconds=40] [contexts=4]"""
 import os
+os.environ.setdefault("HFB200_DETERMINISTIC_BLINDING", "1")  # seals must be reproducible for the comparison
 import sys
 import threading
 import time
