@@ -436,3 +436,18 @@ def test_cuda_graph_replay_on_gpu(pkg, gpu_lib, orc):
             assert (c.prove_resident(blind) == cir.prove(13, g3, code3, data3, blind)[0]).all()
         c.set_transcript(0)                                 # back to the host transcript: same seal
         assert (c.prove_resident(1) == cir.prove(13, g3, code3, data3, 1)[0]).all()
+
+
+@pytest.mark.gpu
+def test_chunk_stage_kernels_agree():
+    """The fused chunk NTT stage exists twice: `mid_warp_kernel` (one warp per transform, four-warp teams; the default) and
+    `MiddleKernel2` (the host emulator's kernel, HFB200_MID_WARP=0).  Exact field arithmetic: the LDE of the same random columns
+    must be bit-identical through both, for full and ragged quads of columns, 2^11 .. 2^21 rows (tools/lde_stress.py --digests)."""
+    import subprocess
+    import sys
+    tool = os.path.join(ROOT, "tools", "lde_stress.py")
+    out = {}
+    for mode in ("0", "1"):
+        env = dict(os.environ, HFB200_MID_WARP=mode)
+        out[mode] = subprocess.check_output([sys.executable, tool, "--digests"], env=env, timeout=600).decode().split()
+    assert len(out["1"]) == 8 and out["0"] == out["1"]
