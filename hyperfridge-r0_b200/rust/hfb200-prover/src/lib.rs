@@ -284,3 +284,20 @@ pub fn verify_seal(seal: &[u32], control_id: &[u32; 8]) -> Result<u32> {
     sys::ffi_wrap(|| unsafe { sys::hfb200_verify_segment(std::ptr::null(), &ir, seal.as_ptr(), seal.len(), control_id.as_ptr(), &mut po2) })?;
     Ok(po2)
 }
+
+/// All segment seals of a composite receipt in one call, fanned out over the host's threads (`hfb200_verify_segments`);
+/// `control_ids[i]` is the control id of seal i's po2.  Returns the po2 of every seal; the error names the first rejected seal.
+pub fn verify_seals(seals: &[&[u32]], control_ids: &[[u32; 8]]) -> Result<Vec<u32>> {
+    anyhow::ensure!(seals.len() == control_ids.len(), "one control id per seal");
+    let tables = CircuitTables::rv32im_v2();
+    let ir = tables.ir();
+    let ptrs: Vec<*const u32> = seals.iter().map(|s| s.as_ptr()).collect();
+    let lens: Vec<usize> = seals.iter().map(|s| s.len()).collect();
+    let roots: Vec<u32> = control_ids.iter().flat_map(|d| d.iter().copied()).collect();
+    let mut po2 = vec![0u32; seals.len()];
+    let mut first_bad = 0usize;
+    sys::ffi_wrap(|| unsafe {
+        sys::hfb200_verify_segments(std::ptr::null(), &ir, ptrs.as_ptr(), lens.as_ptr(), seals.len(), roots.as_ptr(), po2.as_mut_ptr(), 0, &mut first_bad)
+    })?;
+    Ok(po2)
+}

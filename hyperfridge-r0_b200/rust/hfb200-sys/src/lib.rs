@@ -144,6 +144,9 @@ extern "C" {
         circuit: *const hfb200_circuit_desc, ir: *const hfb200_circuit_ir, seals: *const *const u32, seal_words: *const usize, n: usize,
         code_roots: *const u32, po2_out: *mut u32, threads: c_uint, first_bad: *mut usize,
     ) -> *const c_char;
+    /// Where the Fiat-Shamir transcript runs: 0 host (default), 1 device, 2 device replayed as a CUDA graph.  Identical seals.
+    pub fn hfb200_set_transcript(ctx: *mut hfb200_ctx, mode: c_int) -> *const c_char;
+    pub fn hfb200_graph_launches(ctx: *const hfb200_ctx) -> u64;
     /// Control id of (circuit, po2): Merkle root of the committed control columns, computed on the GPU.
     pub fn hfb200_control_root(ctx: *mut hfb200_ctx, po2: u32, code: *const u32, root_out: *mut u32) -> *const c_char;
 }
