@@ -16,7 +16,8 @@
 //     and after a team barrier the four planes leave as 16-byte stores (c-major, all four cosets of an element together): every
 //     32-byte sector is written whole.  (Two cosets per warp with 8-byte stores was measured first: half-filled sectors cost
 //     +2.0 GB of DRAM reads and +1.8 GB of writes per 192 columns, L2 evict_last hints did not change that.)
-//   * 8 planes of 1056 words per team = 33.8 KB, four teams per CTA: 135 KB + 88 KB of tables, one CTA of 16 warps per SM;
+//   * 8 planes of 1088 words per team = 34.8 KB (two pad words per 32: 64-bit shared accesses, conflict-free both ways), four teams
+//     per CTA: 139 KB + 88 KB of tables, one CTA of 16 warps per SM;
 //   * tables for phase 4 are stored coset-major so that consecutive lanes read consecutive (w, w') pairs;
 //   * butterfly outputs that only feed a product (the last level of phases 2 and 4) skip their range correction.
 // Same arithmetic and output as MiddleKernel2 (exact field arithmetic: the LDE is bit-identical); the host emulator keeps
