@@ -3,8 +3,11 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
 this package.  The product (hyperfridge-r0_b200/) never does.
 
-PARITY UNPINNED: the oracle restates risc0-zkp 3.0.4 / risc0-core 3.0.1 from SURVEY.md Appendix A; the
-upstream crates are not vendored under /root/reference and the reference ships no golden seal.
+PARITY UNPINNED for whole seals: the oracle restates risc0-zkp 3.0.4 / risc0-core 3.0.1 from SURVEY.md Appendix A (plus two
+corrections from recollection of upstream's sources); the upstream crates are not vendored under
+/root/reference, the reference ships no golden seal, and the circuit is a declared stand-in.  Pinned to upstream: the
+Poseidon2 permutation (upstream's own known-answer vector `poseidon2_test_vectors`, tests/test_poseidon2.py), the BabyBear
+constants (re-derived), and the seal-length model (the reference's five published seal sizes).
 """
 import ctypes as C
 import os

@@ -7,6 +7,8 @@
 // Coefficient-space DEEP quotient with synthetic division, like upstream's CPU HAL -- deliberately a
 // different algorithm from the CUDA product (which forms the quotient point-wise on the trace domain),
 // so seal equality is a real cross-check.
+// Pinned to upstream where that is possible without the sources: the Poseidon2 permutation reproduces upstream's known-answer
+// vector (tests/test_poseidon2.py), the seal-length model the reference's five published seal sizes; whole seals stay unpinned.
 #pragma once
 #include <map>
 #include <functional>
