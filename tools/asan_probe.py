@@ -67,4 +67,20 @@ with pkg.Context(0, 12, big["widths"], lib=lib, ir=big, deterministic=True) as c
     accum = rng2.integers(0, pkg.P, size=(W[2], 4096), dtype=np.uint32)
     ctx.segment_begin(12, g, code, data, 1); ctx.segment_finish(accum)
 d = pkg.digest_bytes(b"journal", lib=lib); pkg.digest_pair(d, d, lib=lib); pkg.claim_next_state(d, 3, 20, lib=lib)
+# round 2, second half: batch verifier on host threads, graph-replay mode (plain device transcript in the emulator), circuit info
+cir_seals = [host, host.copy(), host]
+with pkg.Context(0, 13, (16, 64, 16), lib=lib, deterministic=True) as ctx:
+    g = ctx.witgen_synth(13, 5, 2)
+    code = ctx.read_group(1)
+    root = ctx.control_root(13, code)
+    assert pkg.verify_segments(cir_seals, [root] * 3, (16, 64, 16), threads=3, lib=lib) == [13, 13, 13]
+    bad = host.copy(); bad[300] ^= 1
+    try:
+        pkg.verify_segments([host, bad], [root] * 2, (16, 64, 16), threads=2, lib=lib)
+        raise SystemExit("tampered seal accepted")
+    except pkg.Hfb200Error:
+        pass
+    ctx.set_transcript(2)
+    ctx.witgen_synth(13, 5, 2)
+    assert (ctx.prove_resident(2) == host).all() and (ctx.prove_resident(2) == host).all()
 print("asan probe 3 ok")
