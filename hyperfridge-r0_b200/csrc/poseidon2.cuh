@@ -392,7 +392,8 @@ struct Merkle {
         uint32_t level = rows / 2;
 #ifndef HFB200_EMU
         // big levels: one thread per node (throughput); <= 4096 nodes: one warp per node (latency); <= 32: one block
-        for (; level > 4096; level >>= 1) dev->launch<HashFoldKernel, 128, 1>((level + T - 1) / T, 1, T, 0, nodes, level);
+        static const uint32_t warp_max = [] { const char* e = std::getenv("HFB200_FOLD_WARP_MAX"); const int v = e ? std::atoi(e) : 0; return v >= 64 ? (uint32_t)v : 4096u; }();
+        for (; level > warp_max; level >>= 1) dev->launch<HashFoldKernel, 128, 1>((level + T - 1) / T, 1, T, 0, nodes, level);
         for (; level > 32; level >>= 1) dev->launch<HashFoldWarpKernel, 256, 1>((level * 32 + 255) / 256, 1, 256, 0, nodes, level);
         if (level >= 1) dev->launch<HashFoldWarpTailKernel, 1024, 1>(1, 1, 1024, 0, nodes, level);
 #else
